@@ -1,0 +1,168 @@
+"""ctypes front-end of the CPU oracle (oracle/taco_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; the
+product package (taco_b200/) never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_I32P = ctypes.POINTER(ctypes.c_int32)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libtaco_oracle.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "taco_oracle.c")):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.oracle_get_max_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def max_threads():
+    return lib().oracle_get_max_threads()
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    assert dtype in (np.dtype(np.float32), np.dtype(np.float64)), dtype
+    return "f32" if dtype == np.float32 else "f64"
+
+
+def spmv(pos, crd, vals, x):
+    pos, crd = _i32(pos), _i32(crd)
+    n = pos.size - 1
+    vals = np.ascontiguousarray(vals)
+    x = np.ascontiguousarray(x, dtype=vals.dtype)
+    y = np.empty(n, dtype=vals.dtype)
+    getattr(lib(), "oracle_spmv_" + _sfx(vals.dtype))(ctypes.c_int32(n), _p(pos), _p(crd), _p(vals), _p(x), _p(y))
+    return y
+
+
+def spmm(pos, crd, vals, B):
+    pos, crd = _i32(pos), _i32(crd)
+    n = pos.size - 1
+    vals = np.ascontiguousarray(vals)
+    B = np.ascontiguousarray(B, dtype=vals.dtype)
+    K = B.shape[1]
+    C = np.empty((n, K), dtype=vals.dtype)
+    getattr(lib(), "oracle_spmm_" + _sfx(vals.dtype))(ctypes.c_int32(n), ctypes.c_int32(K), _p(pos), _p(crd), _p(vals),
+                                                     _p(B), _p(C))
+    return C
+
+
+def sddmm(pos, crd, bvals, C, D):
+    """returns (A_pos, A_crd, A_vals)"""
+    pos, crd = _i32(pos), _i32(crd)
+    n = pos.size - 1
+    bvals = np.ascontiguousarray(bvals)
+    C = np.ascontiguousarray(C, dtype=bvals.dtype)
+    D = np.ascontiguousarray(D, dtype=bvals.dtype)
+    K = C.shape[1]
+    apos = np.empty(n + 1, dtype=np.int32)
+    crd_ptr = _I32P()
+    lib().oracle_sddmm_assemble(ctypes.c_int32(n), _p(pos), _p(crd), _p(apos), ctypes.byref(crd_ptr))
+    nnz = int(apos[n])
+    acrd = np.ctypeslib.as_array(crd_ptr, shape=(max(nnz, 1),))[:nnz].copy()
+    lib().oracle_free(crd_ptr)
+    avals = np.empty(nnz, dtype=bvals.dtype)
+    getattr(lib(), "oracle_sddmm_" + _sfx(bvals.dtype))(ctypes.c_int32(n), ctypes.c_int32(K), _p(pos), _p(crd),
+                                                      _p(bvals), _p(C), _p(D), _p(avals))
+    return apos, acrd, avals
+
+
+def _csf_args(t):
+    keys = ["B1_pos", "B1_crd", "B2_pos", "B2_crd", "B3_pos", "B3_crd"]
+    arrs = [_i32(t[k]) for k in keys]
+    return arrs
+
+
+def mttkrp(t, C, D, I):
+    vals = np.ascontiguousarray(t["B_vals"])
+    C = np.ascontiguousarray(C, dtype=vals.dtype)
+    D = np.ascontiguousarray(D, dtype=vals.dtype)
+    R = C.shape[1]
+    A = np.empty((I, R), dtype=vals.dtype)
+    a = _csf_args(t)
+    getattr(lib(), "oracle_mttkrp_" + _sfx(vals.dtype))(ctypes.c_int32(R), *[_p(x) for x in a], _p(vals), _p(C), _p(D),
+                                                       ctypes.c_int32(I), _p(A))
+    return A
+
+
+def ttv(t, c, I, K):
+    vals = np.ascontiguousarray(t["B_vals"])
+    c = np.ascontiguousarray(c, dtype=vals.dtype)
+    A = np.empty((I, K), dtype=vals.dtype)
+    a = _csf_args(t)
+    getattr(lib(), "oracle_ttv_" + _sfx(vals.dtype))(*[_p(x) for x in a], _p(vals), _p(c), ctypes.c_int32(I),
+                                                    ctypes.c_int32(K), _p(A))
+    return A
+
+
+def ttm(t, C, I, K):
+    vals = np.ascontiguousarray(t["B_vals"])
+    C = np.ascontiguousarray(C, dtype=vals.dtype)
+    R = C.shape[1]
+    A = np.empty((I, K, R), dtype=vals.dtype)
+    a = _csf_args(t)
+    getattr(lib(), "oracle_ttm_" + _sfx(vals.dtype))(ctypes.c_int32(R), *[_p(x) for x in a], _p(vals), _p(C),
+                                                    ctypes.c_int32(I), ctypes.c_int32(K), _p(A))
+    return A
+
+
+def _sparse_out(assemble_fn, compute_name, n, head_args, struct_args, Aval, Bval):
+    cpos = np.empty(n + 1, dtype=np.int32)
+    crd_ptr = _I32P()
+    assemble_fn(*head_args, *[_p(x) for x in struct_args], _p(cpos), ctypes.byref(crd_ptr))
+    nnz = int(cpos[n])
+    ccrd = np.ctypeslib.as_array(crd_ptr, shape=(max(nnz, 1),))[:nnz].copy()
+    lib().oracle_free(crd_ptr)
+    cvals = np.empty(nnz, dtype=Aval.dtype)
+    Apos, Acrd, Bpos, Bcrd = struct_args
+    getattr(lib(), compute_name + _sfx(Aval.dtype))(*head_args, _p(Apos), _p(Acrd), _p(Aval), _p(Bpos), _p(Bcrd),
+                                                   _p(Bval), _p(cpos), _p(cvals))
+    return cpos, ccrd, cvals
+
+
+def spadd(Apos, Acrd, Aval, Bpos, Bcrd, Bval):
+    """returns (C_pos, C_crd, C_vals)"""
+    Apos, Acrd, Bpos, Bcrd = _i32(Apos), _i32(Acrd), _i32(Bpos), _i32(Bcrd)
+    Aval = np.ascontiguousarray(Aval)
+    Bval = np.ascontiguousarray(Bval, dtype=Aval.dtype)
+    n = Apos.size - 1
+    return _sparse_out(lib().oracle_spadd_assemble, "oracle_spadd_compute_", n, [ctypes.c_int32(n)],
+                       [Apos, Acrd, Bpos, Bcrd], Aval, Bval)
+
+
+def spgemm(Apos, Acrd, Aval, Bpos, Bcrd, Bval, ncols):
+    """returns (C_pos, C_crd, C_vals)"""
+    Apos, Acrd, Bpos, Bcrd = _i32(Apos), _i32(Acrd), _i32(Bpos), _i32(Bcrd)
+    Aval = np.ascontiguousarray(Aval)
+    Bval = np.ascontiguousarray(Bval, dtype=Aval.dtype)
+    n = Apos.size - 1
+    return _sparse_out(lib().oracle_spgemm_assemble, "oracle_spgemm_compute_", n,
+                       [ctypes.c_int32(n), ctypes.c_int32(ncols)], [Apos, Acrd, Bpos, Bcrd], Aval, Bval)

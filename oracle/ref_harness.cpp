@@ -1,0 +1,327 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the UNMODIFIED reference (tensor-compiler/taco, linked from oracle/_ref/libtaco.so) through its own
+// public C++ API, exactly the way the reference's tests do (test/tests-scheduling-eval.cpp):
+//     Tensor<T> result; result(i..) = expr; stmt = result.getAssignment().concretize(); [schedule]
+//     result.compile(stmt); result.assemble(); result.compute();
+// The reference lowers the statement, emits C (src/codegen/codegen_c.cpp), shells out to `cc`
+// (src/codegen/module.cpp:111-167) and calls the generated kernel through taco_tensor_t.  Operands are attached
+// zero-copy (makeCSR, include/taco/tensor.h:774-797; Index/ModeIndex for CSF, include/taco/storage/index.h:20-75).
+//
+// usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
+//                         [--threads N] [--reps R]
+//   kernel in {spmv, spmm, sddmm, mttkrp, spadd, spgemm, ttv, ttm}
+// Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
+//
+// Input arrays (tbin.h): dims (int32), and per kernel
+//   spmv   : A_pos A_crd A_vals x                          -> y
+//   spmm   : A_pos A_crd A_vals B                          -> C            dims = n m K
+//   sddmm  : B_pos B_crd B_vals C D                        -> A_pos A_crd A_vals      dims = n m K
+//   mttkrp : B1_pos B1_crd B2_pos B2_crd B3_pos B3_crd B_vals C D -> A     dims = I K L R
+//   ttv    : B1..B3, B_vals, c                             -> A (I x K dense)         dims = I K L
+//   ttm    : B1..B3, B_vals, C (L x R)                     -> A (I x K x R dense)     dims = I K L R
+//   spadd  : A_* B_*                                       -> C_pos C_crd C_vals      dims = n m
+//   spgemm : A_* B_*                                       -> C_pos C_crd C_vals      dims = n m o
+#include <chrono>
+#include <iostream>
+#include <string>
+#include <vector>
+#include <cstring>
+
+#include "taco.h"
+#include "taco/index_notation/transformations.h"
+#include "taco/index_notation/index_notation.h"
+#include "taco/storage/index.h"
+#include "taco/storage/array.h"
+#include "tbin.h"
+
+using namespace taco;
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T> static uint32_t tbin_dtype();
+template <> uint32_t tbin_dtype<float>() { return 1; }
+template <> uint32_t tbin_dtype<double>() { return 2; }
+
+static tbin_array* need(tbin_file& f, const char* name) {
+  tbin_array* a = tbin_get(&f, name);
+  if (!a) { std::cerr << "missing input array " << name << std::endl; exit(2); }
+  return a;
+}
+
+template <typename T>
+static Tensor<T> attachDense(const std::string& name, std::vector<int> dims, T* data) {
+  std::vector<ModeFormatPack> mf(dims.size(), Dense);
+  Tensor<T> t(name, dims, Format(mf));
+  auto st = t.getStorage();
+  std::vector<ModeIndex> mi;
+  size_t n = 1;
+  for (int d : dims) { mi.push_back(ModeIndex({makeArray(std::vector<int>{d})})); n *= (size_t)d; }
+  st.setIndex(Index(t.getFormat(), mi));
+  st.setValues(makeArray(data, n, Array::UserOwns));
+  t.setStorage(st);
+  return t;
+}
+
+template <typename T>
+static Tensor<T> attachCSR(const std::string& name, std::vector<int> dims, tbin_file& f, const std::string& p) {
+  int* pos = (int*)need(f, (p + "_pos").c_str())->data;
+  int* crd = (int*)need(f, (p + "_crd").c_str())->data;
+  T* vals = (T*)need(f, (p + "_vals").c_str())->data;
+  return makeCSR<T>(name, dims, pos, crd, vals);
+}
+
+template <typename T>
+static Tensor<T> attachCSF3(const std::string& name, std::vector<int> dims, tbin_file& f, const std::string& p) {
+  Tensor<T> t(name, dims, Format({Sparse, Sparse, Sparse}));
+  auto st = t.getStorage();
+  std::vector<ModeIndex> mi;
+  for (int l = 1; l <= 3; l++) {
+    tbin_array* pos = need(f, (p + std::to_string(l) + "_pos").c_str());
+    tbin_array* crd = need(f, (p + std::to_string(l) + "_crd").c_str());
+    mi.push_back(ModeIndex({makeArray((int*)pos->data, pos->count, Array::UserOwns),
+                            makeArray((int*)crd->data, crd->count, Array::UserOwns)}));
+  }
+  tbin_array* v = need(f, (p + "_vals").c_str());
+  st.setIndex(Index(t.getFormat(), mi));
+  st.setValues(makeArray((T*)v->data, v->count, Array::UserOwns));
+  t.setStorage(st);
+  return t;
+}
+
+static void dumpSource(const TensorBase& t) {
+  static bool done = false;
+  if (!done && getenv("TACO_REF_DUMP")) { std::cerr << t.getSource() << std::endl; done = true; }
+}
+
+struct Times { std::vector<double> assemble, compute; double compile = 0; };
+
+// Schedules follow the reference's own CPU schedules, test/tests-scheduling-eval.cpp:41-184.
+template <typename T>
+static int run(const std::string& kernel, tbin_file& in, const char* outPath, const std::string& schedule,
+               int reps, Times& tm) {
+  int* dims = (int*)need(in, "dims")->data;
+  IndexVar i("i"), j("j"), k("k"), l("l");
+  std::vector<tbin_array> outs;
+  bool tuned = (schedule == "cpu");
+
+  for (int rep = 0; rep < reps; rep++) {
+    bool last = (rep == reps - 1);
+    outs.clear();
+    if (kernel == "spmv") {
+      int n = dims[0], m = dims[1];
+      Tensor<T> A = attachCSR<T>("A", {n, m}, in, "A");
+      Tensor<T> x = attachDense<T>("x", {m}, (T*)need(in, "x")->data);
+      Tensor<T> y("y", {n}, Format({Dense}));
+      y(i) = A(i, j) * x(j);
+      IndexStmt stmt = y.getAssignment().concretize();
+      if (tuned) {
+        IndexVar i0("i0"), i1("i1");
+        stmt = stmt.split(i, i0, i1, 16).reorder({i0, i1, j})
+                   .parallelize(i0, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces);
+      }
+      double t0 = now_ms(); if (tuned) y.compile(stmt); else y.compile();
+      double t1 = now_ms(); dumpSource(y); y.assemble();
+      double t2 = now_ms(); y.compute();
+      double t3 = now_ms();
+      if (rep == 0) tm.compile = t1 - t0;
+      tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+      if (last) {
+        tbin_array a; strcpy(a.name, "y"); a.dtype = tbin_dtype<T>(); a.count = n;
+        a.data = y.getStorage().getValues().getData(); outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "spmm") {
+      int n = dims[0], m = dims[1], K = dims[2];
+      Tensor<T> A = attachCSR<T>("A", {n, m}, in, "A");
+      Tensor<T> B = attachDense<T>("B", {m, K}, (T*)need(in, "B")->data);
+      Tensor<T> C("C", {n, K}, Format({Dense, Dense}));
+      C(i, k) = A(i, j) * B(j, k);
+      IndexStmt stmt = C.getAssignment().concretize();
+      if (tuned) {
+        IndexVar i0("i0"), i1("i1"), jpos("jpos"), jpos0("jpos0"), jpos1("jpos1");
+        stmt = stmt.split(i, i0, i1, 16).pos(j, jpos, A(i, j)).split(jpos, jpos0, jpos1, 8)
+                   .reorder({i0, i1, jpos0, k, jpos1})
+                   .parallelize(i0, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces)
+                   .parallelize(k, ParallelUnit::CPUVector, OutputRaceStrategy::IgnoreRaces);
+      }
+      double t0 = now_ms(); if (tuned) C.compile(stmt); else C.compile();
+      double t1 = now_ms(); dumpSource(C); C.assemble();
+      double t2 = now_ms(); C.compute();
+      double t3 = now_ms();
+      if (rep == 0) tm.compile = t1 - t0;
+      tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+      if (last) {
+        tbin_array a; strcpy(a.name, "C"); a.dtype = tbin_dtype<T>(); a.count = (uint64_t)n * K;
+        a.data = C.getStorage().getValues().getData(); outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "sddmm") {
+      int n = dims[0], m = dims[1], K = dims[2];
+      Tensor<T> B = attachCSR<T>("B", {n, m}, in, "B");
+      Tensor<T> C = attachDense<T>("C", {n, K}, (T*)need(in, "C")->data);
+      Tensor<T> D = attachDense<T>("D", {m, K}, (T*)need(in, "D")->data);
+      Tensor<T> A("A", {n, m}, CSR);
+      A(i, j) = B(i, j) * C(i, k) * D(j, k);
+      double t0 = now_ms(); A.compile();
+      double t1 = now_ms(); dumpSource(A); A.assemble();
+      double t2 = now_ms(); A.compute();
+      double t3 = now_ms();
+      if (rep == 0) tm.compile = t1 - t0;
+      tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+      if (last) {
+        int *pos, *crd; T* vals;
+        getCSRArrays<T>(A, &pos, &crd, &vals);
+        tbin_array a; strcpy(a.name, "A_pos"); a.dtype = 0; a.count = n + 1; a.data = pos; outs.push_back(a);
+        strcpy(a.name, "A_crd"); a.dtype = 0; a.count = pos[n]; a.data = crd; outs.push_back(a);
+        strcpy(a.name, "A_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "mttkrp" || kernel == "ttv" || kernel == "ttm") {
+      int I = dims[0], K = dims[1], L = dims[2];
+      Tensor<T> B = attachCSF3<T>("B", {I, K, L}, in, "B");
+      if (kernel == "mttkrp") {
+        int R = dims[3];
+        Tensor<T> C = attachDense<T>("C", {K, R}, (T*)need(in, "C")->data);
+        Tensor<T> D = attachDense<T>("D", {L, R}, (T*)need(in, "D")->data);
+        Tensor<T> A("A", {I, R}, Format({Dense, Dense}));
+        A(i, j) = B(i, k, l) * C(k, j) * D(l, j);
+        IndexStmt stmt = A.getAssignment().concretize();
+        if (tuned) {
+          IndexVar i1("i1"), i2("i2");
+          IndexExpr pre = stmt.as<Forall>().getStmt().as<Forall>().getStmt().as<Forall>().getStmt()
+                              .as<Forall>().getStmt().as<Assignment>().getRhs().as<Mul>().getA();
+          TensorVar w("w", Type(type<T>(), {(size_t)R}), taco::dense);
+          stmt = stmt.split(i, i1, i2, 16).reorder({i1, i2, k, l, j});
+          stmt = stmt.precompute(pre, j, j, w);
+          stmt = stmt.parallelize(i1, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces);
+        }
+        double t0 = now_ms(); if (tuned) A.compile(stmt); else A.compile();
+        double t1 = now_ms(); dumpSource(A); A.assemble();
+        double t2 = now_ms(); A.compute();
+        double t3 = now_ms();
+        if (rep == 0) tm.compile = t1 - t0;
+        tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+        if (last) {
+          tbin_array a; strcpy(a.name, "A"); a.dtype = tbin_dtype<T>(); a.count = (uint64_t)I * R;
+          a.data = A.getStorage().getValues().getData(); outs.push_back(a);
+          tbin_write(outPath, outs.data(), outs.size());
+        }
+      } else if (kernel == "ttv") {
+        Tensor<T> c = attachDense<T>("c", {L}, (T*)need(in, "c")->data);
+        Tensor<T> A("A", {I, K}, Format({Dense, Dense}));
+        A(i, j) = B(i, j, k) * c(k);
+        double t0 = now_ms(); A.compile();
+        double t1 = now_ms(); dumpSource(A); A.assemble();
+        double t2 = now_ms(); A.compute();
+        double t3 = now_ms();
+        if (rep == 0) tm.compile = t1 - t0;
+        tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+        if (last) {
+          tbin_array a; strcpy(a.name, "A"); a.dtype = tbin_dtype<T>(); a.count = (uint64_t)I * K;
+          a.data = A.getStorage().getValues().getData(); outs.push_back(a);
+          tbin_write(outPath, outs.data(), outs.size());
+        }
+      } else {
+        int R = dims[3];
+        Tensor<T> C = attachDense<T>("C", {L, R}, (T*)need(in, "C")->data);
+        Tensor<T> A("A", {I, K, R}, Format({Dense, Dense, Dense}));
+        A(i, j, l) = B(i, j, k) * C(k, l);
+        double t0 = now_ms(); A.compile();
+        double t1 = now_ms(); dumpSource(A); A.assemble();
+        double t2 = now_ms(); A.compute();
+        double t3 = now_ms();
+        if (rep == 0) tm.compile = t1 - t0;
+        tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+        if (last) {
+          tbin_array a; strcpy(a.name, "A"); a.dtype = tbin_dtype<T>(); a.count = (uint64_t)I * K * R;
+          a.data = A.getStorage().getValues().getData(); outs.push_back(a);
+          tbin_write(outPath, outs.data(), outs.size());
+        }
+      }
+    } else if (kernel == "spadd" || kernel == "spgemm") {
+      bool add = (kernel == "spadd");
+      int n = dims[0], m = dims[1], o = add ? dims[1] : dims[2];
+      Tensor<T> A = attachCSR<T>("A", {n, m}, in, "A");
+      Tensor<T> B = attachCSR<T>("B", add ? std::vector<int>{n, m} : std::vector<int>{m, o}, in, "B");
+      Tensor<T> C("C", {n, o}, CSR);
+      if (add) C(i, j) = A(i, j) + B(i, j);
+      else     C(i, k) = A(i, j) * B(j, k);
+      IndexStmt stmt = C.getAssignment().concretize();
+      if (tuned) {
+        // scheduleSpAddCPU / scheduleSpGEMMCPU(doPrecompute=true): two-phase Insert assembly, rows in parallel.
+        Assignment assign = add ? stmt.as<Forall>().getStmt().as<Forall>().getStmt().as<Assignment>()
+                                : stmt.as<Forall>().getStmt().as<Forall>().getStmt().as<Forall>().getStmt().as<Assignment>();
+        TensorVar result = assign.getLhs().getTensorVar();
+        stmt = reorderLoopsTopologically(stmt);
+        if (!add) {
+          IndexVar jj = assign.getLhs().getIndexVars()[1];
+          TensorVar w("w", Type(result.getType().getDataType(), {result.getType().getShape().getDimension(1)}), taco::dense);
+          stmt = stmt.precompute(assign.getRhs(), jj, jj, w);
+        }
+        stmt = stmt.assemble(result, AssembleStrategy::Insert, true);
+        IndexStmt q = stmt.as<Assemble>().getQueries();
+        IndexVar qi = isa<Where>(q) ? q.as<Where>().getConsumer().as<Forall>().getIndexVar()
+                                    : q.as<Forall>().getIndexVar();
+        stmt = stmt.parallelize(i, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces)
+                   .parallelize(qi, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces);
+      }
+      double t0 = now_ms(); if (tuned) C.compile(stmt); else C.compile();
+      double t1 = now_ms(); dumpSource(C); C.assemble();
+      double t2 = now_ms(); C.compute();
+      double t3 = now_ms();
+      if (rep == 0) tm.compile = t1 - t0;
+      tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+      if (last) {
+        int *pos, *crd; T* vals;
+        getCSRArrays<T>(C, &pos, &crd, &vals);
+        tbin_array a; strcpy(a.name, "C_pos"); a.dtype = 0; a.count = n + 1; a.data = pos; outs.push_back(a);
+        strcpy(a.name, "C_crd"); a.dtype = 0; a.count = pos[n]; a.data = crd; outs.push_back(a);
+        strcpy(a.name, "C_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else {
+      std::cerr << "unknown kernel " << kernel << std::endl;
+      return 2;
+    }
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) {
+    std::cerr << "usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]"
+                 " [--threads N] [--reps R]" << std::endl;
+    return 2;
+  }
+  std::string kernel = argv[1], dtype = "f64", schedule = "default";
+  int threads = 1, reps = 1;
+  for (int a = 4; a + 1 < argc; a += 2) {
+    std::string key = argv[a], val = argv[a + 1];
+    if (key == "--dtype") dtype = val;
+    else if (key == "--schedule") schedule = val;
+    else if (key == "--threads") threads = atoi(val.c_str());
+    else if (key == "--reps") reps = atoi(val.c_str());
+  }
+  tbin_file in;
+  if (tbin_read(argv[2], &in) != 0) { std::cerr << "cannot read " << argv[2] << std::endl; return 2; }
+  taco_set_num_threads(threads);
+  Times tm;
+  int rc = 1;
+  try {
+    rc = (dtype == "f32") ? run<float>(kernel, in, argv[3], schedule, reps, tm)
+                          : run<double>(kernel, in, argv[3], schedule, reps, tm);
+  } catch (const TacoException& e) {
+    std::cerr << "TacoException: " << e.what() << std::endl;
+    return 3;
+  }
+  std::cout << "{\"kernel\":\"" << kernel << "\",\"dtype\":\"" << dtype << "\",\"schedule\":\"" << schedule
+            << "\",\"threads\":" << threads << ",\"compile_ms\":" << tm.compile << ",\"assemble_ms\":[";
+  for (size_t r = 0; r < tm.assemble.size(); r++) std::cout << (r ? "," : "") << tm.assemble[r];
+  std::cout << "],\"compute_ms\":[";
+  for (size_t r = 0; r < tm.compute.size(); r++) std::cout << (r ? "," : "") << tm.compute[r];
+  std::cout << "]}" << std::endl;
+  return rc;
+}
