@@ -1,0 +1,169 @@
+// common.cuh -- shared declarations of libtaco_b200 (runtime context, tensor views, device helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/taco_b200.h"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);   // records thread-local message, returns code
+#define TB_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return tb::fail(TACO_B200_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define TB_TRY(expr)                    \
+  do {                                  \
+    int _rc = (expr);                   \
+    if (_rc != TACO_B200_OK) return _rc; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// runtime context (runtime.cu)
+// ---------------------------------------------------------------------------------------------------------
+int ensure_init();
+cudaStream_t stream();
+int num_sms();
+void count_launch(int n = 1);
+int result_space();
+
+enum class Mem { Host, Pinned, Device };
+Mem classify(const void* p);
+
+// A read-only operand array made visible to the device for the duration of one call.
+// dev() is usable on stream() after acquire(); release happens in the destructor (stream-ordered free).
+struct In {
+  const void* dptr = nullptr;
+  void* owned = nullptr;    // optional per-kernel timing (taco_b200_profile_enable): CUDA events recorded on the launch stream around a kernel
+struct ProfScope {
+  int slot = -1;
+  explicit ProfScope(const char* kernel_name);
+  ~ProfScope();
+};
+
+// stream-ordered scratch to free
+  ~In();
+  int acquire(const void* p, size_t bytes);
+  template <typename T> const T* as() const { return (const T*)dptr; }
+};
+
+// A result array: device buffer the kernels write, copied back to the caller's pointer if that is host memory.
+struct Out {
+  void* dptr = nullptr;
+  void* owned = nullptr;
+  void* host_dst = nullptr;
+  size_t bytes = 0;
+  ~Out();
+  int acquire(void* p, size_t bytes);      // p: where the caller wants the result (host or device)
+  int commit();                            // enqueue D2H if needed; sets need_sync()
+  template <typename T> T* as() const { return (T*)dptr; }
+};
+bool need_sync();          // a host-visible result was produced in this call
+void clear_need_sync();
+int finish_call();         // synchronise the stream iff need_sync()
+
+// optional per-kernel timing (taco_b200_profile_enable): CUDA events recorded on the launch stream around a kernel
+struct ProfScope {
+  int slot = -1;
+  explicit ProfScope(const char* kernel_name);
+  ~ProfScope();
+};
+
+// stream-ordered scratch
+int scratch_alloc(void** p, size_t bytes);
+void scratch_free(void* p);
+
+// result allocation in the configured result space (HOST: malloc, DEVICE: cudaMalloc)
+void* result_alloc(size_t bytes);
+// copy a small device array to host synchronously (e.g. pos[n] after the scan)
+int read_back(void* host, const void* dev, size_t bytes);
+// read one int32 that may live on host or device
+int read_i32(const int32_t* p, int32_t* out);
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor views (abi.cu) -- validate a taco_tensor_t against the format a kernel family expects
+// ---------------------------------------------------------------------------------------------------------
+enum class DType { F32, F64 };
+int dtype_of(const taco_tensor_t* t, DType* out);
+inline size_t dsize(DType d) { return d == DType::F32 ? 4 : 8; }
+
+struct DenseView {   // {Dense,...}: vals only
+  int32_t order; int32_t dim[3]; int32_t mode_order[3]; void* vals; DType dt;
+  size_t count() const { size_t n = 1; for (int i = 0; i < order; i++) n *= (size_t)dim[i]; return n; }
+};
+struct CsrView {     // {Dense, Compressed}, mode ordering {0,1}
+  int32_t rows, cols; int32_t* pos; int32_t* crd; void* vals; DType dt;
+};
+struct Csf3View {    // {Compressed, Compressed, Compressed}, mode ordering {0,1,2}
+  int32_t dim[3]; int32_t* pos[3]; int32_t* crd[3]; void* vals; DType dt;
+};
+int view_dense(const taco_tensor_t* t, int order, const char* name, DenseView* v);
+int view_csr(const taco_tensor_t* t, const char* name, CsrView* v);
+int view_csf3(const taco_tensor_t* t, const char* name, Csf3View* v);
+
+}  // namespace tb
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace tbd {
+
+// streaming 128-bit loads that bypass L1 allocation (crd / vals are touched exactly once)
+__device__ __forceinline__ int4 ldg_stream_i4(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const void* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_stream_d2(const void* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ldg_stream_i32(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+// streaming stores (results are written once, never re-read by the kernel)
+__device__ __forceinline__ void stg_stream_f4(void* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_d2(void* p, double2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// largest r in [lo, hi] with a[r] <= target   (a non-decreasing, a[lo] <= target assumed)
+__device__ __forceinline__ int search_last_le(const int* __restrict__ a, int lo, int hi, int target) {
+  while (lo < hi) {
+    int mid = lo + ((hi - lo + 1) >> 1);
+    if (__ldg(a + mid) <= target) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// smallest r in [lo, hi] with a[r] >= target; returns hi+1 if none
+__device__ __forceinline__ int search_first_ge(const int* __restrict__ a, int lo, int hi, int target) {
+  int end = hi + 1;
+  while (lo < end) {
+    int mid = lo + ((end - lo) >> 1);
+    if (__ldg(a + mid) >= target) end = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+}  // namespace tbd
+#endif

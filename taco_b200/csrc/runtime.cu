@@ -1,0 +1,371 @@
+// runtime.cu -- device-resident storage / launch layer of libtaco_b200.
+//
+// Replaces the reference's CUDA runtime shim (/root/reference/src/cuda.cpp:11-72: two global switches plus
+// cudaMallocManaged/cudaFree) and the unified-memory allocation convention of
+// /root/reference/src/taco_tensor_t.cpp:10-67 and src/storage/array.cpp:212-219.  Instead of managed memory that
+// page-faults to the GPU on first touch, operands are explicit HBM residents:
+//   * device pointers inside a taco_tensor_t are used in place,
+//   * pinned host arrays are DMA'd on the compute stream,
+//   * pageable host arrays go through cudaMemcpyAsync staging,
+//   * arrays registered with taco_b200_make_resident() are uploaded once and reused across calls,
+// and all temporaries come from the stream-ordered pool (cudaMallocAsync), so assemble/compute are stream-ordered
+// end to end (the reference synchronises the whole device after every launch, codegen_cuda.cpp:608-609).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tb {
+
+static thread_local char g_err[1024] = "";
+static thread_local bool g_need_sync = false;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct Resident { void* dptr; size_t bytes; };
+struct ProfEntry {
+  std::string name;
+  double ms = 0;
+  long launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct Context {
+  std::mutex mu;
+  bool ready = false;
+  int device = 0;
+  int sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t cur_stream = nullptr;
+  int space = TACO_B200_SPACE_HOST;
+  long launches = 0;
+  std::unordered_map<const void*, Resident> resident;
+  bool profile = false;
+  std::vector<ProfEntry> prof;
+};
+static Context g;
+
+static int init_locked(int device) {
+  if (g.ready) return TACO_B200_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(TACO_B200_ERR_CUDA, "no CUDA device available (%s); libtaco_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(TACO_B200_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  TB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(TACO_B200_ERR_CUDA, "device %d is sm_%d%d; libtaco_b200 is built for sm_100a only", device, prop.major,
+                prop.minor);
+  g.device = device;
+  g.sms = prop.multiProcessorCount;
+  TB_CUDA(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+  g.cur_stream = g.own_stream;
+  cudaMemPool_t pool;
+  TB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;   // never trim the pool between calls: temporaries are recycled
+  TB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  g.ready = true;
+  return TACO_B200_OK;
+}
+
+int ensure_init() {
+  if (g.ready) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != g.device) cudaSetDevice(g.device);
+    return TACO_B200_OK;
+  }
+  std::lock_guard<std::mutex> lk(g.mu);
+  int dev = 0;
+  const char* env = getenv("TACO_B200_DEVICE");
+  if (env) dev = atoi(env);
+  else if ((env = getenv("LOCAL_RANK"))) {   // one process per GPU under torchrun
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) dev = atoi(env) % n;
+  }
+  return init_locked(dev);
+}
+
+cudaStream_t stream() { return g.cur_stream; }
+int num_sms() { return g.sms; }
+void count_launch(int n) { g.launches += n; }
+int result_space() { return g.space; }
+bool need_sync() { return g_need_sync; }
+void clear_need_sync() { g_need_sync = false; }
+
+int finish_call() {
+  if (g_need_sync) {
+    g_need_sync = false;
+    TB_CUDA(cudaStreamSynchronize(g.cur_stream));
+  } else {
+    TB_CUDA(cudaPeekAtLastError());
+  }
+  return TACO_B200_OK;
+}
+
+Mem classify(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return Mem::Host;
+  }
+  switch (a.type) {
+    case cudaMemoryTypeDevice: return Mem::Device;
+    case cudaMemoryTypeManaged: return Mem::Device;   // managed memory is dereferenceable on the device
+    case cudaMemoryTypeHost: return Mem::Pinned;
+    default: return Mem::Host;
+  }
+}
+
+ProfScope::ProfScope(const char* kernel_name) {
+  if (!g.profile) return;
+  std::lock_guard<std::mutex> lk(g.mu);
+  for (size_t i = 0; i < g.prof.size(); i++)
+    if (g.prof[i].name == kernel_name) slot = (int)i;
+  if (slot < 0) {
+    g.prof.push_back(ProfEntry());
+    g.prof.back().name = kernel_name;
+    slot = (int)g.prof.size() - 1;
+  }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, g.cur_stream);
+  g.prof[slot].pending.push_back({a, b});
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g.mu);
+  cudaEventRecord(g.prof[slot].pending.back().second, g.cur_stream);
+}
+
+int scratch_alloc(void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(p, bytes, g.cur_stream);
+  if (e != cudaSuccess) return fail(TACO_B200_ERR_ALLOC, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+  return TACO_B200_OK;
+}
+void scratch_free(void* p) {
+  if (p) cudaFreeAsync(p, g.cur_stream);
+}
+
+In::~In() { scratch_free(owned); }
+int In::acquire(const void* p, size_t bytes) {
+  if (p == nullptr) return fail(TACO_B200_ERR_ARG, "NULL operand array");
+  Mem m = classify(p);
+  if (m == Mem::Device) { dptr = p; return TACO_B200_OK; }
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    auto it = g.resident.find(p);
+    if (it != g.resident.end() && it->second.bytes >= bytes) { dptr = it->second.dptr; return TACO_B200_OK; }
+  }
+  TB_TRY(scratch_alloc(&owned, bytes));
+  dptr = owned;
+  if (bytes) TB_CUDA(cudaMemcpyAsync(owned, p, bytes, cudaMemcpyHostToDevice, g.cur_stream));
+  return TACO_B200_OK;
+}
+
+Out::~Out() { scratch_free(owned); }
+int Out::acquire(void* p, size_t nbytes) {
+  if (p == nullptr) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  bytes = nbytes;
+  if (classify(p) == Mem::Device) { dptr = p; return TACO_B200_OK; }
+  TB_TRY(scratch_alloc(&owned, nbytes));
+  dptr = owned;
+  host_dst = p;
+  return TACO_B200_OK;
+}
+int Out::commit() {
+  if (host_dst && bytes) {
+    TB_CUDA(cudaMemcpyAsync(host_dst, dptr, bytes, cudaMemcpyDeviceToHost, g.cur_stream));
+    g_need_sync = true;
+  }
+  return TACO_B200_OK;
+}
+
+void* result_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (g.space == TACO_B200_SPACE_DEVICE) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  }
+  return malloc(bytes);
+}
+
+int read_back(void* host, const void* dev, size_t bytes) {
+  TB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g.cur_stream));
+  TB_CUDA(cudaStreamSynchronize(g.cur_stream));
+  return TACO_B200_OK;
+}
+
+int read_i32(const int32_t* p, int32_t* out) {
+  if (classify(p) == Mem::Device) return read_back(out, p, sizeof(int32_t));
+  *out = *p;
+  return TACO_B200_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+const char* taco_b200_last_error(void) { return g_err; }
+const char* taco_b200_version(void) { return "taco_b200 0.1 (sm_100a)"; }
+
+int taco_b200_init(int device) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.ready && device != g.device)
+    return fail(TACO_B200_ERR_ARG, "already initialised on device %d (one process per GPU)", g.device);
+  return init_locked(device);
+}
+
+int taco_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int taco_b200_set_stream(void* s) {
+  TB_TRY(ensure_init());
+  g.cur_stream = s ? (cudaStream_t)s : g.own_stream;
+  return TACO_B200_OK;
+}
+void* taco_b200_get_stream(void) { return ensure_init() == TACO_B200_OK ? (void*)g.cur_stream : nullptr; }
+
+int taco_b200_synchronize(void) {
+  TB_TRY(ensure_init());
+  TB_CUDA(cudaStreamSynchronize(g.cur_stream));
+  return TACO_B200_OK;
+}
+
+int taco_b200_launch_count(void) { return (int)g.launches; }
+
+int taco_b200_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.profile = on != 0;
+  return TACO_B200_OK;
+}
+
+static void prof_drain(ProfEntry& e) {
+  for (auto& pr : e.pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      e.ms += ms;
+      e.launches++;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  e.pending.clear();
+}
+
+int taco_b200_profile_get(const char* kernel_name, double* total_ms, int* launches) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  for (auto& e : g.prof) {
+    if (e.name == kernel_name) {
+      prof_drain(e);
+      if (total_ms) *total_ms = e.ms;
+      if (launches) *launches = (int)e.launches;
+      return TACO_B200_OK;
+    }
+  }
+  return fail(TACO_B200_ERR_ARG, "no profile entry named '%s'", kernel_name);
+}
+
+int taco_b200_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  for (auto& e : g.prof) prof_drain(e);
+  g.prof.clear();
+  return TACO_B200_OK;
+}
+
+int taco_b200_set_result_space(int space) {
+  if (space != TACO_B200_SPACE_HOST && space != TACO_B200_SPACE_DEVICE)
+    return fail(TACO_B200_ERR_ARG, "unknown result space %d", space);
+  g.space = space;
+  return TACO_B200_OK;
+}
+int taco_b200_get_result_space(void) { return g.space; }
+
+void* taco_b200_host_alloc(size_t bytes) {
+  if (ensure_init() != TACO_B200_OK) return nullptr;
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    fail(TACO_B200_ERR_ALLOC, "cudaHostAlloc(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void taco_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+void* taco_b200_device_alloc(size_t bytes) {
+  if (ensure_init() != TACO_B200_OK) return nullptr;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+    fail(TACO_B200_ERR_ALLOC, "cudaMalloc(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void taco_b200_free(void* p) {
+  if (!p) return;
+  Mem m = classify(p);
+  if (m == Mem::Device) cudaFree(p);
+  else if (m == Mem::Pinned) cudaFreeHost(p);
+  else free(p);
+}
+
+int taco_b200_make_resident(const void* host_ptr, size_t bytes) {
+  TB_TRY(ensure_init());
+  if (!host_ptr) return fail(TACO_B200_ERR_ARG, "NULL host_ptr");
+  if (classify(host_ptr) == Mem::Device) return TACO_B200_OK;
+  void* d = nullptr;
+  TB_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+  cudaError_t e = cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, g.cur_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.cur_stream);
+  if (e != cudaSuccess) { cudaFree(d); return fail(TACO_B200_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
+  std::lock_guard<std::mutex> lk(g.mu);
+  auto it = g.resident.find(host_ptr);
+  if (it != g.resident.end()) cudaFree(it->second.dptr);
+  g.resident[host_ptr] = Resident{d, bytes};
+  return TACO_B200_OK;
+}
+
+int taco_b200_invalidate(const void* host_ptr) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  auto it = g.resident.find(host_ptr);
+  if (it != g.resident.end()) {
+    cudaFree(it->second.dptr);
+    g.resident.erase(it);
+  }
+  return TACO_B200_OK;
+}
+
+int taco_b200_drop_all_resident(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  for (auto& kv : g.resident) cudaFree(kv.second.dptr);
+  g.resident.clear();
+  return TACO_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// sddmm.cu -- A(i,j) = B(i,j) * C(i,k) * D(j,k); A, B CSR (A takes B's structure); C, D dense row-major.
+//
+// Replaces the CUDA the reference emits for scheduleSDDMMGPU (/root/reference/test/tests-scheduling-eval.cpp:270-287):
+//   reference: dense n x n output (impossible at config C3), warp walks 256 nnz, lanes split the contraction,
+//              atomicAddWarp (shuffle tree + one global atomic) per (nnz, dense_val), binary search per thread.
+//   here     : CSR output in B's structure (SURVEY.md Appendix A.1 "SDDMM, CSR output"), pure nnz-split (every
+//              output value is independent, so no reduction across slots): a group of G = K/VEC lanes owns one
+//              nonzero, reads the C row (L1-resident across the row's nonzeros) and gathers the D row with
+//              128-bit loads, reduces inside the group with xor shuffles and the warp writes 32 results with one
+//              coalesced store.  Row of each nonzero: one binary search per nonzero inside the slot's row range.
+//   assemble : the result structure is B's (append assembly of the reference yields exactly B's pos/crd,
+//              src/lower/lowerer_impl_imperative.cpp:3157-3308): two device copies.
+// Algorithmic bytes per launch: nnz*(4 + 2*sizeof T) + 4(n+1) + 2*sizeof T*n*K (+ 8*nnz+4(n+1) when assembling).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int SDDMM_W = 128;       // nonzeros per warp slot
+constexpr int SDDMM_WARPS = 8;
+
+__global__ void slot_first_row_kernel(const int* __restrict__ pos, int rows, int nnz, int slot, int nslots,
+                                      int* __restrict__ first) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > nslots) return;
+  long long lo = (long long)w * slot;
+  first[w] = (w == nslots || lo >= nnz) ? max(rows - 1, 0) : tbd::search_last_le(pos, 0, rows, (int)lo);
+}
+
+template <typename T, int VEC> struct Ld;
+template <> struct Ld<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+};
+template <> struct Ld<double, 2> {
+  static __device__ __forceinline__ void ld(const double* p, double (&v)[2]) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p)); v[0] = a.x; v[1] = a.y;
+  }
+};
+template <typename T> struct Ld<T, 1> {
+  static __device__ __forceinline__ void ld(const T* p, T (&v)[1]) { v[0] = __ldg(p); }
+};
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(SDDMM_WARPS * 32)
+sddmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ bvals,
+                 const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ avals, int rows, int K, int nnz,
+                 int nslots, const int* __restrict__ slot_first) {
+  constexpr int NG = 32 / G;           // nonzeros processed concurrently by a warp
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * SDDMM_WARPS + (threadIdx.x >> 5);
+  if (w >= nslots) return;
+  const int lo = w * SDDMM_W, hi = min(lo + SDDMM_W, nnz);
+  const int rlo = __ldg(slot_first + w), rhi = __ldg(slot_first + w + 1);
+  const int g = lane / G, gl = lane % G;
+  for (int base = lo; base < hi; base += 32) {
+    const int p = base + lane;
+    const bool ok = p < hi;
+    int my_row = 0, my_col = 0;
+    T my_b = T(0);
+    if (ok) {
+      my_row = tbd::search_last_le(pos, rlo, rhi, p);
+      my_col = tbd::ldg_stream_i32(crd + p);
+      my_b = __ldg(bvals + p);
+    }
+    T res[G];
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      const int q = t * NG + g;
+      const int i = __shfl_sync(0xffffffffu, my_row, q);
+      const int j = __shfl_sync(0xffffffffu, my_col, q);
+      const T b = __shfl_sync(0xffffffffu, my_b, q);
+      const T* c = C + (size_t)i * K;
+      const T* d = D + (size_t)j * K;
+      T part = T(0);
+      for (int kk = gl * VEC; kk < K; kk += G * VEC) {
+        T cv[VEC], dv[VEC];
+        Ld<T, VEC>::ld(c + kk, cv);
+        Ld<T, VEC>::ld(d + kk, dv);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) part = part + (b * cv[x]) * dv[x];     // reference association (B*C)*D
+      }
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      res[t] = part;
+    }
+    T out = T(0);
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      T v = __shfl_sync(0xffffffffu, res[t], (lane % NG) * G);
+      if (lane / NG == t) out = v;
+    }
+    if (ok) avals[p] = out;
+  }
+}
+
+template <typename T, int VEC>
+static int sddmm_launch_g(const int* pos, const int* crd, const T* bvals, const T* C, const T* D, T* avals, int rows,
+                          int K, int nnz) {
+  if (nnz == 0) return TACO_B200_OK;
+  int nslots = (nnz + SDDMM_W - 1) / SDDMM_W;
+  void* first = nullptr;
+  TB_TRY(scratch_alloc(&first, sizeof(int) * (size_t)(nslots + 1)));
+  slot_first_row_kernel<<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rows, nnz, SDDMM_W, nslots, (int*)first);
+  int groups = (K + VEC - 1) / VEC;
+  int grid = (nslots + SDDMM_WARPS - 1) / SDDMM_WARPS;
+#define TB_SDDMM_GO(GG)                                                                                              \
+  sddmm_csr_kernel<T, VEC, GG><<<grid, SDDMM_WARPS * 32, 0, stream()>>>(pos, crd, bvals, C, D, avals, rows, K, nnz, \
+                                                                        nslots, (const int*)first)
+  {
+  ProfScope ps("sddmm_csr");
+  if (groups <= 1) TB_SDDMM_GO(1);
+  else if (groups <= 2) TB_SDDMM_GO(2);
+  else if (groups <= 4) TB_SDDMM_GO(4);
+  else if (groups <= 8) TB_SDDMM_GO(8);
+  else if (groups <= 16) TB_SDDMM_GO(16);
+  else TB_SDDMM_GO(32);
+  }
+#undef TB_SDDMM_GO
+  count_launch(2);
+  scratch_free(first);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
+template <typename T>
+static int sddmm_launch(const int* pos, const int* crd, const T* bvals, const T* C, const T* D, T* avals, int rows,
+                        int K, int nnz) {
+  constexpr int V = 16 / sizeof(T);
+  bool vec_ok = (K % V == 0) && (((uintptr_t)C | (uintptr_t)D) & 15) == 0;
+  if (vec_ok) return sddmm_launch_g<T, V>(pos, crd, bvals, C, D, avals, rows, K, nnz);
+  return sddmm_launch_g<T, 1>(pos, crd, bvals, C, D, avals, rows, K, nnz);
+}
+
+int csr_nnz(const CsrView& A, int32_t vals_size_hint, int32_t* nnz);   // spmv.cu
+
+struct SddmmViews { CsrView A, B; DenseView C, D; };
+
+static int sddmm_views(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D, SddmmViews* v) {
+  TB_TRY(ensure_init());
+  TB_TRY(view_csr(A, "A", &v->A));
+  TB_TRY(view_csr(B, "B", &v->B));
+  TB_TRY(view_dense(C, 2, "C", &v->C));
+  TB_TRY(view_dense(D, 2, "D", &v->D));
+  if (v->C.mode_order[0] != 0 || v->D.mode_order[0] != 0)
+    return fail(TACO_B200_ERR_FORMAT, "sddmm: C and D must be row-major {Dense,Dense}");
+  if (v->A.rows != v->B.rows || v->A.cols != v->B.cols || v->C.dim[0] != v->B.rows || v->D.dim[0] != v->B.cols ||
+      v->C.dim[1] != v->D.dim[1])
+    return fail(TACO_B200_ERR_ARG, "sddmm: dimension mismatch");
+  if (v->A.dt != v->B.dt || v->C.dt != v->B.dt || v->D.dt != v->B.dt)
+    return fail(TACO_B200_ERR_FORMAT, "sddmm: mixed component types");
+  return TACO_B200_OK;
+}
+
+// copy `bytes` from an operand array (host or device) into a freshly allocated result array
+static int clone_to_result(const void* src, size_t bytes, void** out) {
+  void* dst = result_alloc(bytes);
+  if (!dst) return fail(TACO_B200_ERR_ALLOC, "cannot allocate %zu result bytes", bytes);
+  *out = dst;
+  if (bytes == 0) return TACO_B200_OK;
+  bool sdev = classify(src) == Mem::Device, ddev = result_space() == TACO_B200_SPACE_DEVICE;
+  if (!sdev && !ddev) { memcpy(dst, src, bytes); return TACO_B200_OK; }
+  TB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream()));
+  if (!ddev) TB_CUDA(cudaStreamSynchronize(stream()));
+  return TACO_B200_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int taco_b200_sddmm_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  SddmmViews v;
+  TB_TRY(sddmm_views(A, B, C, D, &v));
+  int32_t nnz = 0;
+  TB_TRY(csr_nnz(v.B, B->vals_size, &nnz));
+  void *pos = nullptr, *crd = nullptr;
+  TB_TRY(clone_to_result(v.B.pos, sizeof(int32_t) * ((size_t)v.B.rows + 1), &pos));
+  TB_TRY(clone_to_result(v.B.crd ? (void*)v.B.crd : (void*)v.B.pos, sizeof(int32_t) * (size_t)nnz, &crd));
+  void* vals = result_alloc(dsize(v.B.dt) * (size_t)nnz);
+  if (!vals) return fail(TACO_B200_ERR_ALLOC, "sddmm: cannot allocate result values");
+  A->indices[1][0] = (uint8_t*)pos;
+  A->indices[1][1] = (uint8_t*)crd;
+  A->vals = (uint8_t*)vals;
+  A->vals_size = nnz;
+  return TACO_B200_OK;
+}
+
+int taco_b200_sddmm_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  SddmmViews v;
+  TB_TRY(sddmm_views(A, B, C, D, &v));
+  int32_t nnz = 0;
+  TB_TRY(csr_nnz(v.B, B->vals_size, &nnz));
+  if (nnz < 0) return fail(TACO_B200_ERR_ARG, "sddmm: negative nnz");
+  const int K = v.C.dim[1];
+  size_t es = dsize(v.B.dt);
+  In pos, crd, bvals, cin, din; Out aout;
+  TB_TRY(pos.acquire(v.B.pos, sizeof(int32_t) * ((size_t)v.B.rows + 1)));
+  TB_TRY(crd.acquire(v.B.crd ? (void*)v.B.crd : (void*)v.B.pos, sizeof(int32_t) * (size_t)nnz));
+  TB_TRY(bvals.acquire(v.B.vals ? v.B.vals : (void*)v.B.pos, es * (size_t)nnz));
+  TB_TRY(cin.acquire(v.C.vals, es * (size_t)v.B.rows * K));
+  TB_TRY(din.acquire(v.D.vals, es * (size_t)v.B.cols * K));
+  if (nnz > 0) {
+    TB_TRY(aout.acquire(v.A.vals, es * (size_t)nnz));
+    if (v.B.dt == DType::F32)
+      TB_TRY(sddmm_launch<float>(pos.as<int>(), crd.as<int>(), bvals.as<float>(), cin.as<float>(), din.as<float>(),
+                                 aout.as<float>(), v.B.rows, K, nnz));
+    else
+      TB_TRY(sddmm_launch<double>(pos.as<int>(), crd.as<int>(), bvals.as<double>(), cin.as<double>(), din.as<double>(),
+                                  aout.as<double>(), v.B.rows, K, nnz));
+    TB_TRY(aout.commit());
+  }
+  return finish_call();
+}
+
+int taco_b200_sddmm_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  TB_TRY(taco_b200_sddmm_assemble(A, B, C, D));
+  return taco_b200_sddmm_compute(A, B, C, D);
+}
+
+}  // extern "C"

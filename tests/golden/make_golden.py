@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (oracle/_ref/taco_ref_harness -> libtaco.so built from
+/root/reference by oracle/Makefile) on small seeded inputs.  Run in the build container only (the GPU box has no
+/root/reference and only consumes the committed .npz files):
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Inputs mimic the reference's own scheduling tests (test/tests-scheduling-eval.cpp): srand-style sparse fills with
+shapes taken from spmvGPU :1210, spmmGPU :1258, sddmmGPU :1360, mttkrpGPU :1526, spmataddCPU :664, spgemm :600 --
+once with small-integer values (sums are exact in any order, the trick those tests rely on) and once with
+fractional values (order-sensitive; compared with the north-star tolerances).
+The reference's C is JIT-compiled with TACO_CFLAGS="-O3 -std=c99" (the default adds -ffast-math,
+/root/reference/src/codegen/module.cpp:134).
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from taco_b200 import formats, tbin  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "taco_ref_harness")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_ref(kernel, arrays, dtype, schedule):
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.tbin"), os.path.join(td, "out.tbin")
+        tbin.write(fin, arrays)
+        env = dict(os.environ, TACO_CFLAGS="-O3 -std=c99 -fPIC -shared", OMP_NUM_THREADS="4")
+        r = subprocess.run([HARNESS, kernel, fin, fout, "--dtype", dtype, "--schedule", schedule, "--threads", "4"],
+                           capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"{kernel}/{schedule}: {r.stderr[-2000:]}")
+        json.loads(r.stdout.strip().splitlines()[-1])
+        return tbin.read(fout)
+
+
+def sparse_fill(rng, shape, sparsity, integer, dtype):
+    mask = rng.random(shape) < sparsity
+    if integer:
+        vals = np.floor(rng.random(shape) * 3 / max(sparsity, 0.05)).astype(dtype) + 1
+    else:
+        vals = (rng.random(shape) + 0.25).astype(dtype)
+    return np.where(mask, vals, 0).astype(dtype)
+
+
+def dense_fill(rng, shape, integer, dtype):
+    if integer:
+        return np.floor(rng.random(shape) * 9).astype(dtype)
+    return (rng.random(shape) - 0.3).astype(dtype)
+
+
+def csf_from_dense(d):
+    i, k, l = np.nonzero(d)
+    return formats.coo_to_csf3(i, k, l, d[i, k, l])
+
+
+def main():
+    cases = {}
+    for integer in (True, False):
+        tag = "int" if integer else "frac"
+        for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
+            rng = np.random.default_rng(94353 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
+            # ---- spmv (rows 5.. are empty, one long row) -------------------------------------------------------
+            A = sparse_fill(rng, (102, 103), 0.08, integer, dtype)
+            A[5:9] = 0
+            A[40] = dense_fill(rng, 103, integer, dtype) + 1
+            p, c, v = formats.csr_from_dense(A)
+            x = dense_fill(rng, 103, integer, dtype)
+            inp = dict(dims=np.array([102, 103], np.int32), A_pos=p, A_crd=c, A_vals=v, x=x)
+            for sched in ("default", "cpu"):
+                out = run_ref("spmv", inp, sfx, sched)
+                cases[f"spmv_{tag}_{sfx}_{sched}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            # ---- spmm -----------------------------------------------------------------------------------------
+            for K in (12, 7):
+                A = sparse_fill(rng, (51, 47), 0.3, integer, dtype)
+                A[7] = 0
+                p, c, v = formats.csr_from_dense(A)
+                B = dense_fill(rng, (47, K), integer, dtype)
+                inp = dict(dims=np.array([51, 47, K], np.int32), A_pos=p, A_crd=c, A_vals=v, B=B)
+                out = run_ref("spmm", inp, sfx, "default")
+                cases[f"spmm_{tag}_{sfx}_K{K}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            # ---- sddmm ----------------------------------------------------------------------------------------
+            Bm = sparse_fill(rng, (40, 38), 0.2, integer, dtype)
+            p, c, v = formats.csr_from_dense(Bm)
+            C = dense_fill(rng, (40, 16), integer, dtype)
+            D = dense_fill(rng, (38, 16), integer, dtype)
+            inp = dict(dims=np.array([40, 38, 16], np.int32), B_pos=p, B_crd=c, B_vals=v, C=C, D=D)
+            out = run_ref("sddmm", inp, sfx, "default")
+            cases[f"sddmm_{tag}_{sfx}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            if sfx == "f32":
+                continue
+            # ---- mttkrp / ttv / ttm (reference GPU test shape 25 x 25 x 30, rank 32) ---------------------------
+            Bt = sparse_fill(rng, (25, 25, 30), 0.1, integer, dtype)
+            Bt[3] = 0
+            t = csf_from_dense(Bt)
+            Cm = dense_fill(rng, (25, 32), integer, dtype)
+            Dm = dense_fill(rng, (30, 32), integer, dtype)
+            inp = dict(dims=np.array([25, 25, 30, 32], np.int32), C=Cm, D=Dm, **t)
+            out = run_ref("mttkrp", inp, sfx, "default")
+            cases[f"mttkrp_{tag}_{sfx}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            cvec = dense_fill(rng, 30, integer, dtype)
+            inp = dict(dims=np.array([25, 25, 30], np.int32), c=cvec, **t)
+            out = run_ref("ttv", inp, sfx, "default")
+            cases[f"ttv_{tag}_{sfx}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            inp = dict(dims=np.array([25, 25, 30, 8], np.int32), C=Dm[:, :8].copy(), **t)
+            out = run_ref("ttm", inp, sfx, "default")
+            cases[f"ttm_{tag}_{sfx}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            # ---- spadd (reference shape 1000 x 10, sparsity .15 scaled down) + spgemm (100^3, .03) -------------
+            A = sparse_fill(rng, (300, 10), 0.15, integer, dtype)
+            Bm = sparse_fill(rng, (300, 10), 0.15, integer, dtype)
+            if not integer:
+                Bm[A != 0] = np.where(rng.random(np.count_nonzero(A)) < 0.3, -A[A != 0], Bm[A != 0])  # explicit zeros in C
+            ap, ac, av = formats.csr_from_dense(A)
+            bp, bc, bv = formats.csr_from_dense(Bm)
+            inp = dict(dims=np.array([300, 10], np.int32), A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv)
+            for sched in ("default", "cpu"):
+                out = run_ref("spadd", inp, sfx, sched)
+                cases[f"spadd_{tag}_{sfx}_{sched}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+            A = sparse_fill(rng, (100, 100), 0.03, integer, dtype)
+            Bm = sparse_fill(rng, (100, 100), 0.03, integer, dtype)
+            A[10] = sparse_fill(rng, 100, 0.6, integer, dtype)       # a row with many products
+            ap, ac, av = formats.csr_from_dense(A)
+            bp, bc, bv = formats.csr_from_dense(Bm)
+            inp = dict(dims=np.array([100, 100, 100], np.int32), A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc,
+                       B_vals=bv)
+            for sched in ("default", "cpu"):
+                out = run_ref("spgemm", inp, sfx, sched)
+                cases[f"spgemm_{tag}_{sfx}_{sched}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    for name, arrs in cases.items():
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(f"wrote {len(cases)} golden cases to {OUT}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""Shared test helpers: golden fixtures and the reference's own known-answer fixtures."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases(prefix):
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, prefix + "_*.npz")))
+    assert paths, f"no golden fixtures for {prefix}"
+    return [os.path.basename(p)[:-4] for p in paths]
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def tol(dtype):
+    """north-star tolerances: 1e-12 relative for fp64, 1e-5 for fp32 (reduction reordering)"""
+    return 1e-12 if np.dtype(dtype) == np.float64 else 1e-5
+
+
+def assert_close(actual, expected, dtype, scale=None):
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape, (actual.shape, expected.shape)
+    rt = tol(dtype)
+    denom = np.maximum(np.abs(expected), 0 if scale is None else scale)
+    err = np.abs(actual.astype(np.float64) - expected.astype(np.float64))
+    bad = err > rt * np.maximum(denom, np.finfo(np.float64).tiny) + (0 if scale is not None else 0)
+    # entries whose expected value is exactly 0 must match to within rt * scale (or exactly when no scale is given)
+    assert not bad.any(), f"max rel err {np.max(err / np.maximum(denom, 1e-300)):.3e} > {rt:g} at {np.argmax(bad)}"
+
+
+# ---- fixtures of the reference's own tests, /root/reference/test/test_tensors.cpp --------------------------
+def d33a():   # :205-211
+    d = np.zeros((3, 3)); d[0, 1] = 2; d[2, 0] = 3; d[2, 2] = 4
+    return d
+
+
+def d33b():   # :221-227
+    d = np.zeros((3, 3)); d[0, 0] = 10; d[0, 1] = 20; d[2, 1] = 30
+    return d
+
+
+def d3b():    # :89-94
+    return np.array([2.0, 0.0, 3.0])
+
+
+def d34a():   # :237-244
+    d = np.zeros((3, 4)); d[0, 0] = 2; d[0, 2] = 3; d[2, 0] = 4; d[2, 3] = 5
+    return d
+
+
+def d34b():   # :246-253
+    d = np.zeros((3, 4)); d[0, 0] = 2; d[0, 3] = 3; d[2, 0] = 4; d[2, 2] = 5
+    return d
+
+
+def d233a():  # :296-305  -> (i, k, l, vals)
+    c = [(0, 0, 0, 2), (0, 0, 1, 3), (0, 2, 2, 4), (1, 0, 1, 5), (1, 2, 0, 6), (1, 2, 2, 7)]
+    i, k, l, v = map(np.array, zip(*c))
+    return i, k, l, v.astype(np.float64)
+
+
+def d333a():  # :328-339  -> (i, j, k, vals)
+    c = [(0, 0, 0, 2), (0, 0, 1, 3), (0, 2, 2, 4), (1, 0, 1, 5), (1, 2, 0, 6), (1, 2, 2, 7), (2, 1, 2, 8), (2, 2, 1, 9)]
+    i, j, k, v = map(np.array, zip(*c))
+    return i, j, k, v.astype(np.float64)

@@ -1,0 +1,347 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the taco_tensor_t C ABI, against
+  (a) the reference's own known-answer vectors,
+  (b) outputs of the reference itself (tests/golden/*.npz),
+  (c) the CPU oracle on seeded synthetic inputs (host-buffer AND device-resident calling conventions),
+  (d) edge cases (empty tensors, empty rows, ragged widths, hub rows, rows with thousands of products).
+Bar (north star): pos/crd bit-exact; values <= 1e-12 relative (fp64) / 1e-5 (fp32) -- and bit-exact wherever the
+kernel keeps the reference's operation order (SpMV, SpMM non-hub rows, MTTKRP, TTV, TTM, SpAdd, SpGEMM).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import oracle  # noqa: E402
+import helpers as H  # noqa: E402
+import gpu_util as G  # noqa: E402
+import taco_b200 as tb  # noqa: E402
+from taco_b200 import formats, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SPACES = ["host", "device"]
+
+
+def place(w, space):
+    return G.to_device(w) if space == "device" else w
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (a) reference known-answer vectors through the C ABI
+# ---------------------------------------------------------------------------------------------------------
+def test_kat_spmv():
+    p, c, v = formats.csr_from_dense(H.d33a())
+    y = G.run("spmv", dict(dims=[3, 3], A_pos=p, A_crd=c, A_vals=v, x=H.d3b()))
+    assert y.tolist() == [0, 0, 18]
+
+
+def test_kat_matrix_add_structure():
+    ap, ac, av = formats.csr_from_dense(H.d33a())
+    bp, bc, bv = formats.csr_from_dense(H.d33b())
+    pos, crd, vals = G.run("spadd", dict(dims=[3, 3], A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv))
+    assert pos.tolist() == [0, 2, 2, 5] and crd.tolist() == [0, 1, 0, 1, 2] and vals.tolist() == [10, 22, 3, 30, 4]
+    ap, ac, av = formats.csr_from_dense(H.d34a())
+    bp, bc, bv = formats.csr_from_dense(H.d34b())
+    pos, crd, vals = G.run("spadd", dict(dims=[3, 4], A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv),
+                           phases="separate")
+    assert pos.tolist() == [0, 3, 3, 6] and crd.tolist() == [0, 2, 3, 0, 2, 3] and vals.tolist() == [4, 3, 3, 8, 5, 5]
+
+
+def test_kat_matrix_mul():
+    ap, ac, av = formats.csr_from_dense(H.d33a())
+    C = G.run("spmm", dict(dims=[3, 3, 3], A_pos=ap, A_crd=ac, A_vals=av, B=H.d33b().reshape(-1)))
+    assert C.tolist() == [0, 0, 0, 0, 0, 0, 30, 180, 0]
+    Ct = G.run("spmm", dict(dims=[3, 3, 3], A_pos=ap, A_crd=ac, A_vals=av, B=H.d33b().reshape(-1)), colmajor_c=True)
+    assert Ct.reshape(3, 3).T.reshape(-1).tolist() == C.tolist()
+    bp, bc, bv = formats.csr_from_dense(H.d33b())
+    pos, crd, vals = G.run("spgemm", dict(dims=[3, 3, 3], A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv))
+    assert pos.tolist() == [0, 0, 0, 2] and crd.tolist() == [0, 1] and vals.tolist() == [30, 180]
+
+
+def test_kat_mttkrp_ttv_ttm():
+    t = formats.coo_to_csf3(*H.d233a())
+    A = G.run("mttkrp", dict(dims=[2, 3, 3, 3], C=H.d33a().reshape(-1), D=H.d33b().reshape(-1), **t))
+    assert A.tolist() == [0, 80, 0, 180, 0, 0]
+    A = G.run("ttm", dict(dims=[2, 3, 3, 3], C=H.d33a().reshape(-1), **t))
+    assert A.tolist() == [0, 4, 0, 0, 0, 0, 12, 0, 16, 0, 0, 0, 0, 0, 0, 21, 12, 28]
+    t3 = formats.coo_to_csf3(*H.d333a())
+    A = G.run("ttv", dict(dims=[3, 3, 3], c=H.d3b(), **t3))
+    assert A.tolist() == [4, 0, 12, 0, 0, 33, 0, 24, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (b) outputs of the reference itself
+# ---------------------------------------------------------------------------------------------------------
+def _inputs(g):
+    return {k: v for k, v in g.items() if not k.startswith("out_")}
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("spmv"))
+def test_golden_spmv(name, space):
+    g = H.load_golden(name)
+    y = G.run("spmv", place(_inputs(g), space))
+    if name.endswith("_default") or "_int_" in name:
+        assert np.array_equal(y, g["out_y"])          # same operation order as the reference's C kernel
+    else:
+        H.assert_close(y, g["out_y"], y.dtype)
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("spmm"))
+def test_golden_spmm(name, space):
+    g = H.load_golden(name)
+    C = G.run("spmm", place(_inputs(g), space))
+    assert np.array_equal(C, g["out_C"])
+    n, m, K = g["dims"]
+    Ct = G.run("spmm", place(_inputs(g), space), colmajor_c=True)
+    assert np.array_equal(Ct.reshape(K, n).T.reshape(-1), g["out_C"])
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("sddmm"))
+def test_golden_sddmm(name, space):
+    g = H.load_golden(name)
+    pos, crd, vals = G.run("sddmm", place(_inputs(g), space))
+    assert np.array_equal(pos, g["out_A_pos"]) and np.array_equal(crd, g["out_A_crd"])
+    if "_int_" in name:
+        assert np.array_equal(vals, g["out_A_vals"])
+    else:   # the K-contraction is a shuffle tree here: reduction reordering, north-star tolerance
+        H.assert_close(vals, g["out_A_vals"], vals.dtype, scale=np.abs(g["out_A_vals"]).max())
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("fam", ["mttkrp", "ttv", "ttm"])
+@pytest.mark.parametrize("tag", ["int", "frac"])
+def test_golden_csf(fam, tag, space):
+    g = H.load_golden(f"{fam}_{tag}_f64")
+    A = G.run(fam, place(_inputs(g), space))
+    assert np.array_equal(A, g["out_A"])
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("phases", ["evaluate", "separate"])
+@pytest.mark.parametrize("name", H.golden_cases("spadd") + H.golden_cases("spgemm"))
+def test_golden_sparse_output(name, space, phases):
+    g = H.load_golden(name)
+    fam = name.split("_")[0]
+    pos, crd, vals = G.run(fam, place(_inputs(g), space), phases=phases)
+    assert np.array_equal(pos, g["out_C_pos"]), "pos must be bit-exact"
+    assert np.array_equal(crd, g["out_C_crd"]), "crd must be bit-exact"
+    assert np.array_equal(vals, g["out_C_vals"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (c) oracle on seeded synthetic inputs
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_oracle_spmv(space, dtype):
+    w = synth.make("spmv", None, n=200_003, deg=10, dtype=dtype)
+    y = G.run("spmv", place(w, space))
+    assert np.array_equal(y, oracle.spmv(w["A_pos"], w["A_crd"], w["A_vals"], w["x"]))
+
+
+def test_oracle_spmv_powerlaw_long_rows():
+    # R-MAT structure: empty rows, rows far longer than one staging tile (slow path with carries)
+    pos, crd, vals = synth.csr_rmat(synth.backend(None), 16, 16, 123, np.float64)
+    assert np.diff(pos).max() > 2048
+    x = synth.dense(synth.backend(None), 1 << 16, 1, 5, np.float64)
+    w = dict(dims=[1 << 16, 1 << 16], A_pos=pos, A_crd=crd, A_vals=vals, x=x)
+    for space in SPACES:
+        y = G.run("spmv", place(w, space))
+        assert np.array_equal(y, oracle.spmv(pos, crd, vals, x))
+
+
+def _spmm_check(w, C, dtype):
+    n, m, K = w["dims"]
+    want = oracle.spmm(w["A_pos"], w["A_crd"], w["A_vals"], w["B"].reshape(m, K))
+    C = C.reshape(n, K)
+    deg = np.diff(w["A_pos"])
+    short = deg <= 512
+    assert np.array_equal(C[short], want[short]), "non-hub rows keep the reference's operation order: bit-exact"
+    if (~short).any():   # hub rows are split across slots and combined with red.global.add: reordered sums
+        H.assert_close(C[~short], want[~short], dtype)
+    return int((~short).sum())
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("K,dtype", [(128, "float32"), (64, "float64"), (100, "float32"), (33, "float32"), (7, "float64")])
+def test_oracle_spmm(space, K, dtype):
+    w = synth.make("spmm", None, scale=15, K=K, dtype=dtype)
+    C = G.run("spmm", place(w, space))
+    hubs = _spmm_check(w, C, dtype)
+    assert hubs > 0, "the R-MAT case is meant to exercise the hub-row path"
+
+
+@pytest.mark.parametrize("K,dtype", [(64, "float32"), (64, "float64"), (20, "float32"), (5, "float64"), (256, "float32")])
+def test_oracle_sddmm(K, dtype):
+    w = synth.make("sddmm", None, n=30_011, deg=20, K=K, dtype=dtype)
+    n = w["dims"][0]
+    ap, ac, av = oracle.sddmm(w["B_pos"], w["B_crd"], w["B_vals"], w["C"].reshape(n, K), w["D"].reshape(n, K))
+    for space in SPACES:
+        pos, crd, vals = G.run("sddmm", place(w, space))
+        assert np.array_equal(pos, ap) and np.array_equal(crd, ac)
+        H.assert_close(vals, av, dtype)
+
+
+@pytest.mark.parametrize("R,dtype", [(32, "float64"), (16, "float64"), (40, "float32")])
+def test_oracle_mttkrp(R, dtype):
+    w = synth.make("mttkrp", None, I=20_000, K=3_000, L=2_500, nnz=400_000, R=R, dtype=dtype)
+    I, K, L, _ = w["dims"]
+    want = oracle.mttkrp(w, w["C"].reshape(K, R), w["D"].reshape(L, R), I)
+    for space in SPACES:
+        A = G.run("mttkrp", place(w, space))
+        assert np.array_equal(A.reshape(I, R), want)
+
+
+def test_oracle_mttkrp_long_fibers_and_gaps():
+    # few slices (gaps in mode 0), long fibers: exercises the >32-leaf path and the zero fill of unoccupied rows
+    w = synth.make("mttkrp", None, I=5_000, K=40, L=3_000, nnz=150_000, R=32, dtype="float64")
+    keep = w["B1_crd"] % 3 != 1
+    i, k, l, v = formats.csf3_to_coo(w)
+    sel = keep[np.searchsorted(w["B1_crd"], i)]
+    t = formats.coo_to_csf3(i[sel], k[sel], l[sel], v[sel])
+    w2 = dict(dims=w["dims"], C=w["C"], D=w["D"], **t)
+    want = oracle.mttkrp(t, w["C"].reshape(40, 32), w["D"].reshape(3000, 32), 5000)
+    A = G.run("mttkrp", G.to_device(w2))
+    assert np.array_equal(A.reshape(5000, 32), want)
+
+
+def test_oracle_ttv_ttm():
+    w = synth.make("mttkrp", None, I=3_000, K=500, L=800, nnz=200_000, R=16, dtype="float64")
+    I, K, L, R = w["dims"]
+    t = {k: v for k, v in w.items() if k.startswith("B")}
+    c = w["D"][:L].copy()
+    A = G.run("ttv", G.to_device(dict(dims=[I, K, L], c=c, **t)))
+    assert np.array_equal(A.reshape(I, K), oracle.ttv(t, c, I, K))
+    A = G.run("ttm", G.to_device(dict(dims=[I, K, L, R], C=w["D"], **t)))
+    assert np.array_equal(A.reshape(I, K, R), oracle.ttm(t, w["D"].reshape(L, R), I, K))
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_oracle_spadd(space, dtype):
+    w = synth.make("spadd", None, n=100_003, deg=10, dtype=dtype)
+    w["B_vals"][::7] = -1.0                       # some sums cancel to an explicit zero when columns coincide
+    cp, cc, cv = oracle.spadd(w["A_pos"], w["A_crd"], w["A_vals"], w["B_pos"], w["B_crd"], w["B_vals"])
+    pos, crd, vals = G.run("spadd", place(w, space), phases="separate")
+    assert np.array_equal(pos, cp) and np.array_equal(crd, cc) and np.array_equal(vals, cv)
+
+
+@pytest.mark.parametrize("space", SPACES)
+def test_oracle_spgemm(space):
+    w = synth.make("spgemm", None, n=40_009, deg=10, dtype="float64")
+    n = w["dims"][0]
+    cp, cc, cv = oracle.spgemm(w["A_pos"], w["A_crd"], w["A_vals"], w["B_pos"], w["B_crd"], w["B_vals"], n)
+    pos, crd, vals = G.run("spgemm", place(w, space), phases="separate")
+    assert np.array_equal(pos, cp) and np.array_equal(crd, cc), "structure must be bit-exact"
+    assert np.array_equal(vals, cv)
+
+
+def test_oracle_spgemm_powerlaw_all_bins():
+    # R-MAT x R-MAT: rows with > 256 products (CTA-sort bin) and > 8192 products (bitmap bin), many collisions
+    xp = synth.backend(None)
+    ap, ac, av = synth.csr_rmat(xp, 12, 8, 77, np.float64)
+    bp, bc, bv = synth.csr_rmat(xp, 12, 8, 78, np.float64)
+    n = 1 << 12
+    csum = np.concatenate([[0], np.cumsum(np.diff(bp)[ac])])
+    ub = csum[ap[1:]] - csum[ap[:-1]]                                   # products per row
+    assert ub.max() > 8192 and (ub > 256).sum() > 10
+    cp, cc, cv = oracle.spgemm(ap, ac, av, bp, bc, bv, n)
+    w = dict(dims=[n, n, n], A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv)
+    for space in SPACES:
+        pos, crd, vals = G.run("spgemm", place(w, space))
+        assert np.array_equal(pos, cp) and np.array_equal(crd, cc)
+        assert np.array_equal(vals, cv)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (d) edge cases
+# ---------------------------------------------------------------------------------------------------------
+def _empty_csr(n):
+    return np.zeros(n + 1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64)
+
+
+@pytest.mark.parametrize("space", SPACES)
+def test_empty_operands(space):
+    p, c, v = _empty_csr(5)
+    y = G.run("spmv", place(dict(dims=[5, 4], A_pos=p, A_crd=c, A_vals=v, x=np.ones(4)), space))
+    assert y.tolist() == [0] * 5
+    C = G.run("spmm", place(dict(dims=[5, 4, 8], A_pos=p, A_crd=c, A_vals=v, B=np.ones(32)), space))
+    assert C.tolist() == [0] * 40
+    q, d, u = formats.csr_from_dense(np.array([[0, 1.0, 0, 2], [0, 0, 0, 0], [3, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]))
+    pos, crd, vals = G.run("spadd", place(dict(dims=[5, 4], A_pos=p, A_crd=c, A_vals=v, B_pos=q, B_crd=d, B_vals=u), space))
+    assert pos.tolist() == q.tolist() and crd.tolist() == d.tolist() and vals.tolist() == u.tolist()
+    pos, crd, vals = G.run("spadd", place(dict(dims=[5, 4], A_pos=p, A_crd=c, A_vals=v, B_pos=p, B_crd=c, B_vals=v), space))
+    assert pos.tolist() == [0] * 6 and crd.size == 0 and vals.size == 0
+    p4, c4, v4 = _empty_csr(4)
+    pos, crd, vals = G.run("spgemm", place(dict(dims=[5, 4, 4], A_pos=q, A_crd=d, A_vals=u, B_pos=p4, B_crd=c4, B_vals=v4), space))
+    assert pos.tolist() == [0] * 6 and crd.size == 0
+    pos, crd, vals = G.run("sddmm", place(dict(dims=[5, 4, 3], B_pos=p, B_crd=c, B_vals=v, C=np.ones(15), D=np.ones(12)), space))
+    assert pos.tolist() == [0] * 6 and vals.size == 0
+
+
+def test_empty_csf():
+    t = formats.coo_to_csf3(np.zeros(0, int), np.zeros(0, int), np.zeros(0, int), np.zeros(0))
+    A = G.run("mttkrp", dict(dims=[4, 3, 3, 8], C=np.ones(24), D=np.ones(24), **t))
+    assert A.tolist() == [0] * 32
+
+
+def test_leading_trailing_empty_rows_and_single_row():
+    d = np.zeros((70, 9))
+    d[33] = np.arange(1, 10)
+    d[34, 2] = 5
+    p, c, v = formats.csr_from_dense(d)
+    x = np.arange(9, dtype=np.float64) + 1
+    y = G.run("spmv", dict(dims=[70, 9], A_pos=p, A_crd=c, A_vals=v, x=x))
+    assert np.array_equal(y, d @ x)
+    B = np.arange(9 * 8, dtype=np.float64).reshape(9, 8)
+    C = G.run("spmm", dict(dims=[70, 9, 8], A_pos=p, A_crd=c, A_vals=v, B=B.reshape(-1)))
+    assert np.array_equal(C.reshape(70, 8), d @ B)
+
+
+def test_dimension_and_type_errors():
+    p, c, v = formats.csr_from_dense(np.eye(3))
+    A = tb.makeCSR("A", [3, 3], p, c, v)
+    x = tb.makeDense("x", [4], np.ones(4))
+    y = tb.Tensor("y", [3], tb.Format([tb.dense]))
+    k = tb.compile("y(i) = A(i,j) * x(j)", y, A, tb.makeDense("x", [3], np.ones(3)))
+    with pytest.raises(tb.TacoError) as ei:
+        k(y, A, x)
+    assert ei.value.code == 3
+    with pytest.raises(tb.TacoError):   # compute without assemble: result has no storage
+        k.compute(tb.Tensor("y", [3], tb.Format([tb.dense])), A, tb.makeDense("x", [3], np.ones(3)))
+
+
+def test_resident_cache_and_launch_count():
+    from taco_b200 import _lib
+    import ctypes
+    w = synth.make("spmv", None, n=50_000, deg=10)
+    for key in ("A_pos", "A_crd", "A_vals"):
+        a = w[key]
+        tb._lib.check(_lib.lib.taco_b200_make_resident(ctypes.c_void_p(a.ctypes.data), a.nbytes))
+    before = tb.launch_count()
+    y1 = G.run("spmv", w)
+    assert tb.launch_count() > before, "the library must have launched its own kernels"
+    w["A_vals"][:] = 0                      # host copy changes, resident mirror does not ...
+    y2 = G.run("spmv", w)
+    assert np.array_equal(y1, y2)
+    _lib.lib.taco_b200_invalidate(ctypes.c_void_p(w["A_vals"].ctypes.data))   # ... until it is invalidated
+    y3 = G.run("spmv", w)
+    assert not y3.any()
+    _lib.lib.taco_b200_drop_all_resident()
+
+
+def test_partition_pos_device_matches_host():
+    import torch
+    w = synth.make("spmm", None, scale=14, K=4)
+    n = w["dims"][0]
+    host = tb.partition_pos(w["A_pos"], n, 8)
+    dev = tb.partition_pos(torch.as_tensor(w["A_pos"]).cuda(), n, 8)
+    assert host.tolist() == dev.tolist()
+    sizes = np.diff(w["A_pos"][host])
+    assert sizes.max() - sizes.min() <= np.diff(w["A_pos"]).max()      # nnz-balanced up to one row
