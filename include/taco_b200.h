@@ -74,7 +74,8 @@ const char* taco_b200_version(void);
 /* ---- runtime (replaces src/cuda.cpp: cuda_unified_alloc/free, should_use_CUDA_*) ---------------------- */
 int  taco_b200_init(int device);                  /* idempotent; selects the device for this process */
 int  taco_b200_device_count(void);
-int  taco_b200_set_stream(void* cuda_stream);     /* cudaStream_t; NULL restores the private stream */
+int  taco_b200_set_stream(void* cuda_stream);     /* cudaStream_t; NULL restores the private stream; pass
+                                                     cudaStreamLegacy (0x1) for the legacy default stream */
 void* taco_b200_get_stream(void);
 int  taco_b200_synchronize(void);
 int  taco_b200_launch_count(void);                /* number of kernels launched by this library so far */

@@ -261,26 +261,30 @@ def csr_rmat(xp, scale, edge_factor, seed, dtype, abcd=(0.57, 0.19, 0.19, 0.05))
 
 
 def csf3_uniform(xp, I, K, L, nnz, seed, dtype):
-    """order-3 CSF {Compressed x3} (mode order 0,1,2) with ~nnz uniform coordinates (duplicates removed)."""
+    """order-3 CSF {Compressed x3} (mode order 0,1,2) with ~nnz uniform coordinates (duplicates removed).
+    Sorted lexicographically with two stable sorts (by l, then by i*K+k): the full key would not fit 63 bits at
+    10M x 1M x 1M."""
     e = xp.arange(nnz)
     i = uniform_int(xp, e, seed, I)
     k = uniform_int(xp, e, seed + 1, K)
     l = uniform_int(xp, e, seed + 2, L)
-    kb = max(1, (K - 1).bit_length())
-    lb = max(1, (L - 1).bit_length())
-    assert (I - 1).bit_length() + kb + lb <= 62
-    key = xp.sort((i << (kb + lb)) | (k << lb) | l)
+    assert I * K < (1 << 62)
+    ik = i * K + k
+    del i, k, e
+    o = xp.argsort(l)
+    l, ik = l[o], ik[o]
+    o = xp.argsort(ik)
+    l, ik = l[o], ik[o]
+    del o
     keep = xp.ones_bool(nnz)
-    keep[1:] = key[1:] != key[:-1]
-    key = key[keep]
-    nnz = int(key.shape[0])
-    ik = key >> lb
-    l = key & ((1 << lb) - 1)
+    keep[1:] = (ik[1:] != ik[:-1]) | (l[1:] != l[:-1])
+    ik, l = ik[keep], l[keep]
+    nnz = int(ik.shape[0])
     new_fib = xp.ones_bool(nnz)
     new_fib[1:] = ik[1:] != ik[:-1]
     fib_start = xp.nonzero(new_fib)
     fib_ik = ik[fib_start]
-    fib_i = fib_ik >> kb
+    fib_i = fib_ik // K
     nf = int(fib_start.shape[0])
     new_slice = xp.ones_bool(nf)
     new_slice[1:] = fib_i[1:] != fib_i[:-1]
@@ -289,7 +293,7 @@ def csf3_uniform(xp, I, K, L, nnz, seed, dtype):
         B1_pos=xp.i32(xp.cat([xp.scalar(0), xp.scalar(int(slice_start.shape[0]))])),
         B1_crd=xp.i32(fib_i[slice_start]),
         B2_pos=xp.i32(xp.cat([slice_start, xp.scalar(nf)])),
-        B2_crd=xp.i32(fib_ik & ((1 << kb) - 1)),
+        B2_crd=xp.i32(fib_ik % K),
         B3_pos=xp.i32(xp.cat([fib_start, xp.scalar(nnz)])),
         B3_crd=xp.i32(l),
         B_vals=values(xp, xp.arange(nnz), seed + 3, dtype),

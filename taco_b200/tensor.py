@@ -330,7 +330,10 @@ def set_result_space(space):
 
 def use_torch_stream():
     """Enqueue all library work on torch's current CUDA stream (so torch.cuda.Event brackets it)."""
-    check(lib.taco_b200_set_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    h = torch.cuda.current_stream().cuda_stream
+    # torch's default stream is the legacy NULL stream (handle 0); the C ABI keeps NULL for "private stream", so
+    # pass the explicit cudaStreamLegacy handle (0x1) instead
+    check(lib.taco_b200_set_stream(ctypes.c_void_p(h if h else 1)))
 
 
 def synchronize():

@@ -245,8 +245,8 @@ def test_oracle_spgemm(space):
 def test_oracle_spgemm_powerlaw_all_bins():
     # R-MAT x R-MAT: rows with > 256 products (CTA-sort bin) and > 8192 products (bitmap bin), many collisions
     xp = synth.backend(None)
-    ap, ac, av = synth.csr_rmat(xp, 12, 8, 77, np.float64)
-    bp, bc, bv = synth.csr_rmat(xp, 12, 8, 78, np.float64)
+    ap, ac, av = synth.csr_rmat(xp, 12, 24, 77, np.float64)
+    bp, bc, bv = synth.csr_rmat(xp, 12, 24, 78, np.float64)
     n = 1 << 12
     csum = np.concatenate([[0], np.cumsum(np.diff(bp)[ac])])
     ub = csum[ap[1:]] - csum[ap[:-1]]                                   # products per row
