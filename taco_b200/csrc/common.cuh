@@ -41,14 +41,7 @@ Mem classify(const void* p);
 // dev() is usable on stream() after acquire(); release happens in the destructor (stream-ordered free).
 struct In {
   const void* dptr = nullptr;
-  void* owned = nullptr;    // optional per-kernel timing (taco_b200_profile_enable): CUDA events recorded on the launch stream around a kernel
-struct ProfScope {
-  int slot = -1;
-  explicit ProfScope(const char* kernel_name);
-  ~ProfScope();
-};
-
-// stream-ordered scratch to free
+  void* owned = nullptr;    // stream-ordered scratch to free
   ~In();
   int acquire(const void* p, size_t bytes);
   template <typename T> const T* as() const { return (const T*)dptr; }
@@ -82,6 +75,9 @@ void scratch_free(void* p);
 
 // result allocation in the configured result space (HOST: malloc, DEVICE: cudaMalloc)
 void* result_alloc(size_t bytes);
+// pooled device arrays that may be handed to the caller (released with taco_b200_free / device_result_free)
+int device_result_alloc(void** p, size_t bytes);
+void device_result_free(void* p);
 // copy a small device array to host synchronously (e.g. pos[n] after the scan)
 int read_back(void* host, const void* dev, size_t bytes);
 // read one int32 that may live on host or device
@@ -137,6 +133,33 @@ __device__ __forceinline__ double2 ldg_stream_d2(const void* p) {
 __device__ __forceinline__ int ldg_stream_i32(const int* p) {
   int r;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+// L2 cache policies (createpolicy): evict_last for the one operand with re-use, evict_first for streams
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// single-element streaming loads: no L1 allocation, first to leave L2
+__device__ __forceinline__ int ldg_stream_i32(const int* p, uint64_t strm) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(strm));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream(const float* p, uint64_t strm) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(strm));
+  return r;
+}
+__device__ __forceinline__ double ldg_stream(const double* p, uint64_t strm) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(strm));
   return r;
 }
 // streaming stores (results are written once, never re-read by the kernel)

@@ -14,6 +14,9 @@
 // accumulated in leaf order with the reference association (B*C)*D -> bit-identical to the oracle.
 // Unoccupied rows of A are zeroed by a memset node (they have no owner slice).
 // Algorithmic bytes: nnz*(4+sizeof T) + 8*nfib + 8*nslice + sizeof T*R*(K + L + I).
+#include <climits>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tb {
@@ -117,6 +120,184 @@ csf3_ttv_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, 
   }
 }
 
+// =========================================================================================================
+// MTTKRP: nnz-balanced slice-aligned slots
+// =========================================================================================================
+// The leaf level is cut into slots of MK_W leaves; slot w (one warp) OWNS the mode-0 slices whose first leaf lies in
+// [w*W,(w+1)*W) and computes their rows of A completely in registers (lane <-> rank column), storing each row once:
+// no atomics, no zero-fill pass, summation in leaf order with the reference association (B*C)*D => bit-identical to
+// the reference's C kernel.  Only slices longer than MK_LONG leaves are split across the slots they span (partials
+// combined with red.global.add into a row the pre-pass zeroed).  Per 32 leaves: one coalesced load of B3_crd / B_vals,
+// the fiber of each leaf from a guessed position (exact when fibers are singletons) or a binary search in the slice's
+// B3_pos window, (k, l, val) staged in shared memory and read back as one 16-byte broadcast per leaf, U leaves = 2U
+// independent factor-row gathers in flight per warp.
+constexpr int MK_W = 64;
+constexpr int MK_LONG = 512;
+
+template <typename T> struct MkLeaf { int k, l; T v; };
+template <> struct __align__(16) MkLeaf<double> { int k, l; double v; };
+template <> struct __align__(16) MkLeaf<float> { int k, l; float v; int pad; };
+
+template <typename T>
+__device__ __forceinline__ T ld_keep(const T* p, uint64_t keep) {
+  T r;
+  if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(keep));
+  else asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(keep));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v, uint64_t strm) {
+  if constexpr (sizeof(T) == 8) asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(strm) : "memory");
+  else asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(strm) : "memory");
+}
+
+// slot_slices[w] = first slice s (0..nslices) whose first leaf B3_pos[B2_pos[s]] is >= w*W; slot_slices[nslots] = nslices.
+// Also zeroes the A row of every hub slice (by the slot in which the slice's first slot boundary falls).
+template <typename T>
+__global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd,
+                                          const int* __restrict__ B2_pos, const int* __restrict__ B3_pos, int nnz, int nslots,
+                                          int R, int* __restrict__ slot_slices, T* __restrict__ A) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > nslots) return;
+  const int s_base = __ldg(B1_pos), nslices = __ldg(B1_pos + 1) - s_base;
+  if (w == nslots) { slot_slices[w] = nslices; return; }
+  const int target = w * MK_W;
+  int lo = 0, end = nslices + 1;                 // smallest s in [0, nslices] with leafstart(s) >= target
+  while (lo < end) {
+    const int mid = lo + ((end - lo) >> 1);
+    if (__ldg(B3_pos + __ldg(B2_pos + s_base + mid)) >= target) end = mid; else lo = mid + 1;
+  }
+  slot_slices[w] = lo;
+  if (target < nnz && lo > 0) {
+    // slice lo-1 starts before `target`; if it is a hub slice and this is its first slot boundary, zero its row
+    const int s = s_base + lo - 1;
+    const int l0 = __ldg(B3_pos + __ldg(B2_pos + s)), l1 = __ldg(B3_pos + __ldg(B2_pos + s + 1));
+    if (l1 > target && l1 - l0 > MK_LONG && target - l0 <= MK_W) {
+      T* row = A + (size_t)__ldg(B1_crd + s) * R;
+      for (int j = 0; j < R; j++) row[j] = T(0);
+    }
+  }
+}
+
+template <typename T, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
+                  const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
+                  const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices) {
+  __shared__ MkLeaf<T> stage_all[WARPS][32];
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= nslots) return;
+  MkLeaf<T>* stage = stage_all[threadIdx.x >> 5];
+  const int lo = w * MK_W, hi = min(lo + MK_W, nnz);
+  if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(B3_crd + lo + lane * 32));
+  else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bv + lo + (lane - 2) * (128 / (int)sizeof(T))));
+  const uint64_t keep = tbd::policy_evict_last(), strm = tbd::policy_evict_first();
+  const int s_base = __ldg(B1_pos), nslices = __ldg(B1_pos + 1) - s_base;
+  const int S0 = __ldg(slot_slices + w), S1 = __ldg(slot_slices + w + 1);
+
+  // the piece of a hub slice that started in an earlier slot and covers leaf `lo`
+  bool tail = false;
+  int t_f0 = 0, t_f1 = 0, t_l1 = 0;
+  if (S0 > 0 && lo < nnz) {
+    t_f0 = __ldg(B2_pos + s_base + S0 - 1);
+    t_f1 = __ldg(B2_pos + s_base + S0);
+    const int l0 = __ldg(B3_pos + t_f0);
+    t_l1 = __ldg(B3_pos + t_f1);
+    tail = t_l1 > lo && t_l1 - l0 > MK_LONG;
+  }
+  for (int sb = tail ? S0 - 32 : S0; sb < S1; sb += 32) {
+    const bool is_tail = sb < S0;
+    const int sl = sb + lane;
+    const bool valid = !is_tail && sl < S1;
+    int f0 = 0, f1 = 0, l0 = 0, l1 = 0, irow = 0, zlo = 0, zhi = 0;
+    if (valid) {
+      const int s = s_base + sl;
+      f0 = __ldg(B2_pos + s); f1 = __ldg(B2_pos + s + 1);
+      l0 = __ldg(B3_pos + f0); l1 = __ldg(B3_pos + f1);
+      irow = __ldg(B1_crd + s);
+      // rows of A without a slice are zeroed by the owner of the next occupied row (and the last owner zeroes the end)
+      zlo = (sl == 0) ? 0 : __ldg(B1_crd + s - 1) + 1;
+      zhi = (sl == nslices - 1) ? Idim : irow + 1;
+    }
+    if (is_tail && lane == 0) { f0 = t_f0; f1 = t_f1; l0 = lo; l1 = min(hi, t_l1); irow = __ldg(B1_crd + s_base + S0 - 1); }
+    unsigned work = is_tail ? 1u : __ballot_sync(0xffffffffu, valid);
+    while (work) {
+      const int h = __ffs(work) - 1;
+      work &= work - 1;
+      const int hf0 = __shfl_sync(0xffffffffu, f0, h), hf1 = __shfl_sync(0xffffffffu, f1, h);
+      const int hl0 = __shfl_sync(0xffffffffu, l0, h);
+      int hl1 = __shfl_sync(0xffffffffu, l1, h);
+      const int hi_row = __shfl_sync(0xffffffffu, irow, h);
+      const int hzlo = __shfl_sync(0xffffffffu, zlo, h), hzhi = __shfl_sync(0xffffffffu, zhi, h);
+      const bool hub = is_tail || hl1 - hl0 > MK_LONG;
+      if (hub) hl1 = min(hi, hl1);
+      if (!is_tail) {
+        for (int r = hzlo; r < hzhi; r++) {
+          if (r == hi_row) continue;
+          for (int j = lane; j < R; j += 32) st_stream(A + (size_t)r * R + j, T(0), strm);
+        }
+      }
+      for (int j0 = 0; j0 < R; j0 += 32) {
+        const bool active = j0 + lane < R;
+        const T* Cj = C + (active ? j0 + lane : 0);
+        const T* Dj = D + (active ? j0 + lane : 0);
+        T acc = T(0);
+        for (int pb = hl0; pb < hl1; pb += 32) {
+          const int cnt = min(32, hl1 - pb);
+          if (lane < cnt) {
+            const int p = pb + lane;
+            MkLeaf<T> m;
+            m.l = tbd::ldg_stream_i32(B3_crd + p, strm);
+            m.v = tbd::ldg_stream(Bv + p, strm);
+            int f = min(hf0 + (p - hl0), hf1 - 1);          // exact when every fiber of the slice is a singleton
+            if (!(__ldg(B3_pos + f) <= p && __ldg(B3_pos + f + 1) > p)) f = tbd::search_last_le(B3_pos, hf0, hf1 - 1, p);
+            m.k = __ldg(B2_crd + f);
+            stage[lane] = m;
+          }
+          __syncwarp();
+          int q = 0;
+          for (; q + U <= cnt; q += U) {
+            T cv[U], dv[U], vv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const MkLeaf<T> m = stage[q + u];
+              vv[u] = m.v;
+              cv[u] = ld_keep(Cj + (size_t)m.k * R, keep);
+              dv[u] = ld_keep(Dj + (size_t)m.l * R, keep);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) acc = acc + (vv[u] * cv[u]) * dv[u];
+          }
+          if (q < cnt) {
+            const int rem = cnt - q;
+            T cv[U - 1], dv[U - 1], vv[U - 1];
+#pragma unroll
+            for (int u = 0; u < U - 1; u++) {
+              if (u < rem) {
+                const MkLeaf<T> m = stage[q + u];
+                vv[u] = m.v;
+                cv[u] = ld_keep(Cj + (size_t)m.k * R, keep);
+                dv[u] = ld_keep(Dj + (size_t)m.l * R, keep);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U - 1; u++)
+              if (u < rem) acc = acc + (vv[u] * cv[u]) * dv[u];
+          }
+          __syncwarp();
+        }
+        if (active) {
+          T* dst = A + (size_t)hi_row * R + j0 + lane;
+          if (hub) atomicAdd(dst, acc);
+          else st_stream(dst, acc, strm);
+        }
+      }
+    }
+  }
+}
+
 struct CsfCall {
   Csf3View B; DType dt; int32_t nslices, nfib, nnz;
   In p1, c1, p2, c2, p3, c3, vals;
@@ -156,20 +337,40 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
   return TACO_B200_OK;
 }
 
+template <typename T, int U, int WARPS>
+static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices) {
+  mttkrp_csf_kernel<T, U, WARPS><<<(nslots + WARPS - 1) / WARPS, WARPS * 32, 0, stream()>>>(
+      cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D,
+      A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
+}
+
 template <typename T>
 static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_count, int R) {
-  if (cc.nslices == 0 || R == 0) {
+  if (cc.nslices == 0 || R == 0 || cc.nnz == 0) {
+    // no slice owns any row (or every slice is empty): the result is all zeros
     TB_CUDA(cudaMemsetAsync(A, 0, a_count * sizeof(T), stream()));
     count_launch(1);
+    return TACO_B200_OK;
   }
-  if (cc.nslices > 0 && R > 0) {
-    long long ctas = ((long long)cc.nslices + CSF_WARPS - 1) / CSF_WARPS;
-    int grid = (int)(ctas < (1 << 22) ? ctas : (1 << 22));
+  if (cc.nnz > INT32_MAX - 65536) return fail(TACO_B200_ERR_ARG, "mttkrp: nnz too close to the int32 limit");
+  const int nslots = (cc.nnz + MK_W - 1) / MK_W;
+  void* slot_slices = nullptr;
+  TB_TRY(scratch_alloc(&slot_slices, sizeof(int) * (size_t)(nslots + 1)));
+  mttkrp_slot_slices_kernel<T><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(
+      cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.p3.as<int>(), cc.nnz, nslots, R, (int*)slot_slices, A);
+  static const int variant = getenv("TACO_B200_MTTKRP_VARIANT") ? atoi(getenv("TACO_B200_MTTKRP_VARIANT")) : 0;
+  {
     ProfScope ps("mttkrp_csf");
-    csf3_rows_kernel<T, 0><<<grid, CSF_WARPS * 32, 0, stream()>>>(cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(),
-        cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D, A, R, 0, cc.B.dim[0]);
-    count_launch(1);
+    const int* ss = (const int*)slot_slices;
+    switch (variant) {
+      case 1: mttkrp_go<T, 4, 8>(cc, C, D, A, R, nslots, ss); break;
+      case 2: mttkrp_go<T, 8, 4>(cc, C, D, A, R, nslots, ss); break;
+      case 3: mttkrp_go<T, 4, 4>(cc, C, D, A, R, nslots, ss); break;
+      default: mttkrp_go<T, 8, 8>(cc, C, D, A, R, nslots, ss); break;
+    }
   }
+  count_launch(2);
+  scratch_free(slot_slices);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -52,6 +53,7 @@ struct Context {
   int space = TACO_B200_SPACE_HOST;
   long launches = 0;
   std::unordered_map<const void*, Resident> resident;
+  std::unordered_set<const void*> pooled;   // device result arrays handed to the caller that came from the pool
   bool profile = false;
   std::vector<ProfEntry> prof;
 };
@@ -198,11 +200,28 @@ int Out::commit() {
   return TACO_B200_OK;
 }
 
+// Device result arrays come from the stream-ordered pool (release threshold = never trim), so a loop of
+// assemble/compute/free calls recycles the same HBM without cudaMalloc/cudaFree (which synchronise the device).
+int device_result_alloc(void** p, size_t bytes) {
+  TB_TRY(scratch_alloc(p, bytes));
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.pooled.insert(*p);
+  return TACO_B200_OK;
+}
+void device_result_free(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.pooled.erase(p);
+  }
+  cudaFreeAsync(p, g.cur_stream);
+}
+
 void* result_alloc(size_t bytes) {
   if (bytes == 0) bytes = 16;
   if (g.space == TACO_B200_SPACE_DEVICE) {
     void* p = nullptr;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (device_result_alloc(&p, bytes) != TACO_B200_OK) { cudaGetLastError(); return nullptr; }
     return p;
   }
   return malloc(bytes);
@@ -329,6 +348,14 @@ void* taco_b200_device_alloc(size_t bytes) {
 }
 void taco_b200_free(void* p) {
   if (!p) return;
+  {
+    std::unique_lock<std::mutex> lk(g.mu);
+    if (g.pooled.count(p)) {
+      lk.unlock();
+      device_result_free(p);      // stream-ordered: returns to the pool after the work already enqueued
+      return;
+    }
+  }
   Mem m = classify(p);
   if (m == Mem::Device) cudaFree(p);
   else if (m == Mem::Pinned) cudaFreeHost(p);

@@ -316,8 +316,8 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
     TB_CUDA(cudaMemcpyAsync(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, stream()));
     if (nnzC) TB_CUDA(cudaMemcpyAsync(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC, cudaMemcpyDeviceToHost, stream()));
     TB_CUDA(cudaStreamSynchronize(stream()));
-    cudaFree(dpos);
-    cudaFree(dcrd);
+    device_result_free(dpos);
+    device_result_free(dcrd);
     C->indices[1][0] = (uint8_t*)hpos;
     C->indices[1][1] = (uint8_t*)hcrd;
     C->vals = (uint8_t*)vals;
@@ -329,7 +329,7 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
 static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s) {
   const int n = s.A.rows;
   int* dpos = nullptr;
-  TB_CUDA(cudaMalloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
+  TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
   {
     ProfScope ps("spadd_symbolic");
     spadd_count_kernel<<<(n + 1 + 255) / 256, 256, 0, stream()>>>(n, s.apos.as<int>(), s.acrd.as<int>(), s.bpos.as<int>(),
@@ -340,7 +340,7 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s) {
   int32_t nnzC = 0;
   TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
   int* dcrd = nullptr;
-  TB_CUDA(cudaMalloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
+  TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
   if (n > 0) {
     spadd_fill_kernel<double, true, false><<<(n + 255) / 256, 256, 0, stream()>>>(
         n, s.apos.as<int>(), s.acrd.as<int>(), nullptr, s.bpos.as<int>(), s.bcrd.as<int>(), nullptr, dpos, dcrd, nullptr);
@@ -367,7 +367,7 @@ static int spadd_numeric(Csr3& s, const In& av, const In& bv, const In& cpos, Ou
 static int spgemm_assemble_impl(taco_tensor_t* C, Csr3& s) {
   const int n = s.A.rows, ncols = s.B.cols;
   int* dpos = nullptr;
-  TB_CUDA(cudaMalloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
+  TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
   void *bin_count = nullptr, *bin_rows = nullptr, *bitmaps = nullptr;
   TB_TRY(scratch_alloc(&bin_count, sizeof(int) * 4));
   TB_TRY(scratch_alloc(&bin_rows, sizeof(int) * 3 * (size_t)(n > 0 ? n : 1)));
@@ -394,7 +394,7 @@ static int spgemm_assemble_impl(taco_tensor_t* C, Csr3& s) {
     if (pass == 1) {
       TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
       TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
-      TB_CUDA(cudaMalloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
+      TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
     }
 #define TB_SG_ARGS s.apos.as<int>(), s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), dpos, dpos, dcrd
     ProfScope ps("spgemm_symbolic");

@@ -17,26 +17,27 @@
 //              Inside a row the products are accumulated in ascending position order with separate multiply and
 //              add -- the reference C kernel's order (Appendix A.1) -- so non-hub rows are bit-identical to it.
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*K*(cols + rows).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tb {
 
 constexpr int SPMM_W = 64;          // nonzeros per slot (one warp)
 constexpr int SPMM_LONG = 512;      // rows longer than this are split across slots
-constexpr int SPMM_UNROLL = 8;      // independent B-row gathers in flight per warp
-constexpr int SPMM_WARPS = 8;       // warps per CTA
 
 template <typename T, int VEC> struct Frag { T v[VEC]; };
 
+// A lane's 16-byte piece of a gathered B row.  L1-allocating (hot columns of a power-law matrix are re-used inside an
+// SM) and tagged evict_last in L2: the dense operand is the only array with re-use, the CSR arrays and C stream by.
 template <typename T, int VEC>
-__device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p) {
+__device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p, uint64_t keep) {
   Frag<T, VEC> f;
   if constexpr (VEC == 4 && sizeof(T) == 4) {
-    float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    f.v[0] = a.x; f.v[1] = a.y; f.v[2] = a.z; f.v[3] = a.w;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(f.v[0]), "=f"(f.v[1]), "=f"(f.v[2]), "=f"(f.v[3]) : "l"(p), "l"(keep));
   } else if constexpr (VEC == 2 && sizeof(T) == 8) {
-    double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    f.v[0] = a.x; f.v[1] = a.y;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(f.v[0]), "=d"(f.v[1]) : "l"(p), "l"(keep));
   } else {
     f.v[0] = __ldg(p);
   }
@@ -44,15 +45,22 @@ __device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p) {
 }
 
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void store_row(T* __restrict__ C, int row, int col, int rows, int K, const Frag<T, VEC>& f) {
+__device__ __forceinline__ void store_row(T* __restrict__ C, int row, int col, int rows, int K, const Frag<T, VEC>& f,
+                                          uint64_t strm) {
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) C[(size_t)(col + e) * rows + row] = f.v[e];
   } else {
     T* p = C + (size_t)row * K + col;
-    if constexpr (VEC == 4 && sizeof(T) == 4) tbd::stg_stream_f4(p, make_float4(f.v[0], f.v[1], f.v[2], f.v[3]));
-    else if constexpr (VEC == 2 && sizeof(T) == 8) tbd::stg_stream_d2(p, make_double2(f.v[0], f.v[1]));
-    else p[0] = f.v[0];
+    if constexpr (VEC == 4 && sizeof(T) == 4) {
+      asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(f.v[0]),
+                   "f"(f.v[1]), "f"(f.v[2]), "f"(f.v[3]), "l"(strm) : "memory");
+    } else if constexpr (VEC == 2 && sizeof(T) == 8) {
+      asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(f.v[0]), "d"(f.v[1]),
+                   "l"(strm) : "memory");
+    } else {
+      p[0] = f.v[0];
+    }
   }
 }
 
@@ -93,109 +101,131 @@ __global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, int rows, int
   }
 }
 
-// Accumulate nonzeros [a,b) (all of one row piece, or a run of whole rows) into acc with row tracking.
-// ROWS=true : the range is a run of whole short rows rb .. rb+nrows-1 whose end offsets are in register `e` of lane
-//             (row - rb); every finished row (including empty ones) is stored.
-// ROWS=false: the range is a piece of hub row `rb`; the partial sum is added atomically.
-template <typename T, int VEC, bool COLMAJOR, bool ROWS>
-__device__ __forceinline__ void spmm_walk(const int* __restrict__ crd, const T* __restrict__ vals,
-                                          const T* __restrict__ B, T* __restrict__ C, int rows, int K, int col,
-                                          bool active, int lane, int a, int b, int rb, int nrows, int e) {
-  Frag<T, VEC> acc;
-#pragma unroll
-  for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-  int cur = 0;
-  int cur_end = ROWS ? __shfl_sync(0xffffffffu, e, 0) : b;
+// acc += sum over nonzeros p in [a,b) of vals[p] * B[crd[p], col..col+VEC), in ascending p with separate multiply and
+// add (the reference C kernel's order, Appendix A.1).  32 nonzeros are fetched with one coalesced load per array and
+// broadcast by shuffle; U independent B-row gathers are in flight per warp.
+template <typename T, int VEC, int U>
+__device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __restrict__ crd, const T* __restrict__ vals,
+                                                const T* __restrict__ Bcol, int K, int a, int b, int lane, uint64_t keep,
+                                                uint64_t strm) {
   for (int pb = a; pb < b; pb += 32) {
     const int cnt = min(32, b - pb);
     int my_c = 0;
     T my_v = T(0);
     if (lane < cnt) {
-      my_c = tbd::ldg_stream_i32(crd + pb + lane);
-      my_v = __ldg(vals + pb + lane);
+      my_c = tbd::ldg_stream_i32(crd + pb + lane, strm);
+      my_v = tbd::ldg_stream(vals + pb + lane, strm);
     }
-    for (int j0 = 0; j0 < cnt; j0 += SPMM_UNROLL) {
-      Frag<T, VEC> bv[SPMM_UNROLL];
+    int j = 0;
+    for (; j + U <= cnt; j += U) {
+      Frag<T, VEC> bv[U];
 #pragma unroll
-      for (int u = 0; u < SPMM_UNROLL; u++) {
-        if (j0 + u < cnt) {
-          int c = __shfl_sync(0xffffffffu, my_c, j0 + u);
-          if (active) bv[u] = load_row<T, VEC>(B + (size_t)c * K + col);
+      for (int u = 0; u < U; u++) {
+        const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+        bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K, keep);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const T v = __shfl_sync(0xffffffffu, my_v, j + u);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];   // mul then add: never fused
+      }
+    }
+    if (j < cnt) {                      // 1 .. U-1 left: same two phases, warp-uniform predicates
+      const int rem = cnt - j;
+      Frag<T, VEC> bv[U - 1];
+#pragma unroll
+      for (int u = 0; u < U - 1; u++) {
+        if (u < rem) {
+          const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+          bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K, keep);
         }
       }
 #pragma unroll
-      for (int u = 0; u < SPMM_UNROLL; u++) {
-        if (j0 + u < cnt) {
-          if constexpr (ROWS) {
-            const int p = pb + j0 + u;
-            while (p == cur_end) {       // warp-uniform: row rb+cur is complete (possibly empty)
-              if (active) store_row<T, VEC, COLMAJOR>(C, rb + cur, col, rows, K, acc);
+      for (int u = 0; u < U - 1; u++) {
+        if (u < rem) {
+          const T v = __shfl_sync(0xffffffffu, my_v, j + u);
 #pragma unroll
-              for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-              cur++;
-              cur_end = __shfl_sync(0xffffffffu, e, cur);
-            }
-          }
-          T v = __shfl_sync(0xffffffffu, my_v, j0 + u);
-          if (active) {
-#pragma unroll
-            for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];   // mul then add: never fused
-          }
+          for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];
         }
       }
     }
-  }
-  if constexpr (ROWS) {
-    while (cur < nrows) {                // last row of the run, then trailing empty rows
-      if (active) store_row<T, VEC, COLMAJOR>(C, rb + cur, col, rows, K, acc);
-#pragma unroll
-      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      cur++;
-    }
-  } else {
-    if (active) red_row<T, VEC, COLMAJOR>(C, rb, col, rows, K, acc);
   }
 }
 
-template <typename T, int VEC, bool COLMAJOR>
-__global__ void __launch_bounds__(SPMM_WARPS * 32)
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, int nnz, int nslots,
                 const int* __restrict__ slot_rows) {
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
+  const int lo = w * SPMM_W, hi = min(lo + SPMM_W, nnz);
+  // the slot's own window of crd / vals is needed a few dependent loads from now: pull it into L2 meanwhile
+  if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
+  else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
+  const uint64_t keep = tbd::policy_evict_last(), strm = tbd::policy_evict_first();
   const int col = (blockIdx.y * 32 + lane) * VEC;
   const bool active = col < K;
-  const int lo = w * SPMM_W, hi = min(lo + SPMM_W, nnz);
+  const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
   const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
 
-  // (1) the tail of a hub row that started in an earlier slot and covers nonzero `lo`
+  // Work items of the slot, all run through ONE copy of the accumulate loop:
+  //   group -1 (optional): the piece [lo, min(hi,e)) of a hub row that started in an earlier slot (added atomically),
+  //   groups 0..: the rows this slot owns, 32 at a time -- empty rows are zeroed, every other row is accumulated in
+  //   registers and written exactly once; a hub row (always the last row a slot owns) contributes its first piece
+  //   atomically into the row the pre-pass zeroed.
+  int tail_e = 0;
+  bool tail = false;
   if (R0 > 0 && lo < nnz) {
-    const int s = __ldg(pos + R0 - 1), e = __ldg(pos + R0);
-    if (e > lo && e - s > SPMM_LONG)
-      spmm_walk<T, VEC, COLMAJOR, false>(crd, vals, B, C, rows, K, col, active, lane, lo, min(hi, e), R0 - 1, 1, 0);
+    const int s = __ldg(pos + R0 - 1);
+    tail_e = __ldg(pos + R0);
+    tail = tail_e > lo && tail_e - s > SPMM_LONG;
   }
-  // (2) the rows this slot owns, 32 at a time
-  for (int rb = R0; rb < R1; rb += 32) {
+  for (int rb = tail ? R0 - 32 : R0; rb < R1; rb += 32) {
+    const bool is_tail = rb < R0;
     const int r = rb + lane;
-    const bool valid = r < R1;
-    const int s = valid ? __ldg(pos + r) : 0;
-    const int e = valid ? __ldg(pos + r + 1) : 0;
-    const unsigned hub = __ballot_sync(0xffffffffu, valid && (e - s > SPMM_LONG));
-    const int nvalid = min(32, R1 - rb);
-    const int nshort = hub ? (__ffs(hub) - 1) : nvalid;   // a hub row is always the last row a slot owns
-    if (nshort > 0) {
-      const int a = __shfl_sync(0xffffffffu, s, 0);
-      const int b = __shfl_sync(0xffffffffu, e, nshort - 1);
-      spmm_walk<T, VEC, COLMAJOR, true>(crd, vals, B, C, rows, K, col, active, lane, a, b, rb, nshort, e);
+    const bool valid = !is_tail && r < R1;
+    int s = valid ? __ldg(pos + r) : 0;
+    int e = valid ? __ldg(pos + r + 1) : 0;
+    unsigned empty = __ballot_sync(0xffffffffu, valid && e == s);
+    unsigned full = __ballot_sync(0xffffffffu, valid && e > s);
+    int rowbase = rb;
+    if (is_tail) { s = lo; e = min(hi, tail_e); full = 1u; rowbase = R0 - 1; }
+    Frag<T, VEC> acc;
+#pragma unroll
+    for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+    while (empty) {
+      const int h = __ffs(empty) - 1;
+      empty &= empty - 1;
+      if (active) store_row<T, VEC, COLMAJOR>(C, rb + h, col, rows, K, acc, strm);
     }
-    if (hub) {
-      const int h = __ffs(hub) - 1;
-      const int hs = __shfl_sync(0xffffffffu, s, h), he = __shfl_sync(0xffffffffu, e, h);
-      spmm_walk<T, VEC, COLMAJOR, false>(crd, vals, B, C, rows, K, col, active, lane, hs, min(hi, he), rb + h, 1, 0);
+    while (full) {
+      const int h = __ffs(full) - 1;
+      full &= full - 1;
+      const int hs = __shfl_sync(0xffffffffu, s, h);
+      int he = __shfl_sync(0xffffffffu, e, h);
+      const bool hub = is_tail || he - hs > SPMM_LONG;
+      if (hub) he = min(hi, he);
+#pragma unroll
+      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+      spmm_accumulate<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane, keep, strm);
+      if (active) {
+        if (hub) red_row<T, VEC, COLMAJOR>(C, rowbase + h, col, rows, K, acc);
+        else store_row<T, VEC, COLMAJOR>(C, rowbase + h, col, rows, K, acc, strm);
+      }
     }
   }
+}
+
+// Launch variants: (gathers in flight per warp, warps per CTA).  TACO_B200_SPMM_VARIANT selects one for tuning runs.
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS>
+static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz, int nslots,
+                    const int* slot_rows) {
+  dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
+  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, nnz, nslots,
+                                                                                 slot_rows);
 }
 
 template <typename T, int VEC, bool COLMAJOR>
@@ -205,11 +235,16 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
   spmm_slot_rows_kernel<T, COLMAJOR><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rows, nnz, nslots, K,
                                                                                      (int*)slot_rows, C);
-  dim3 grid((nslots + SPMM_WARPS - 1) / SPMM_WARPS, (K + 32 * VEC - 1) / (32 * VEC));
+  static const int variant = getenv("TACO_B200_SPMM_VARIANT") ? atoi(getenv("TACO_B200_SPMM_VARIANT")) : 0;
   {
     ProfScope ps("spmm_csr");
-    spmm_csr_kernel<T, VEC, COLMAJOR><<<grid, SPMM_WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, nnz, nslots,
-                                                                              (const int*)slot_rows);
+    const int* sr = (const int*)slot_rows;
+    switch (variant) {
+      case 1: spmm_go<T, VEC, COLMAJOR, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 2: spmm_go<T, VEC, COLMAJOR, 4, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 3: spmm_go<T, VEC, COLMAJOR, 8, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      default: spmm_go<T, VEC, COLMAJOR, 4, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+    }
   }
   count_launch(2);
   scratch_free(slot_rows);
