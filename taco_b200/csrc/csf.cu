@@ -179,8 +179,8 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
   }
 }
 
-template <typename T, int U, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename T, int U, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
@@ -272,7 +272,7 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
           }
           if (q < cnt) {
             const int rem = cnt - q;
-            T cv[U - 1], dv[U - 1], vv[U - 1];
+            T cv[U > 1 ? U - 1 : 1], dv[U > 1 ? U - 1 : 1], vv[U > 1 ? U - 1 : 1];
 #pragma unroll
             for (int u = 0; u < U - 1; u++) {
               if (u < rem) {
@@ -337,9 +337,9 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
   return TACO_B200_OK;
 }
 
-template <typename T, int U, int WARPS>
+template <typename T, int U, int WARPS, int MINB>
 static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices) {
-  mttkrp_csf_kernel<T, U, WARPS><<<(nslots + WARPS - 1) / WARPS, WARPS * 32, 0, stream()>>>(
+  mttkrp_csf_kernel<T, U, WARPS, MINB><<<(nslots + WARPS - 1) / WARPS, WARPS * 32, 0, stream()>>>(
       cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D,
       A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
 }
@@ -363,10 +363,12 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
     ProfScope ps("mttkrp_csf");
     const int* ss = (const int*)slot_slices;
     switch (variant) {
-      case 1: mttkrp_go<T, 4, 8>(cc, C, D, A, R, nslots, ss); break;
-      case 2: mttkrp_go<T, 8, 4>(cc, C, D, A, R, nslots, ss); break;
-      case 3: mttkrp_go<T, 4, 4>(cc, C, D, A, R, nslots, ss); break;
-      default: mttkrp_go<T, 8, 8>(cc, C, D, A, R, nslots, ss); break;
+      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss); break;
+      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss); break;
+      case 3: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss); break;
+      case 4: mttkrp_go<T, 4, 8, 1>(cc, C, D, A, R, nslots, ss); break;
+      case 5: mttkrp_go<T, 4, 8, 5>(cc, C, D, A, R, nslots, ss); break;
+      default: mttkrp_go<T, 4, 8, 4>(cc, C, D, A, R, nslots, ss); break;
     }
   }
   count_launch(2);

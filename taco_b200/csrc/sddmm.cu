@@ -11,6 +11,7 @@
 //   assemble : the result structure is B's (append assembly of the reference yields exactly B's pos/crd,
 //              src/lower/lowerer_impl_imperative.cpp:3157-3308): two device copies.
 // Algorithmic bytes per launch: nnz*(4 + 2*sizeof T) + 4(n+1) + 2*sizeof T*n*K (+ 8*nnz+4(n+1) when assembling).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -96,6 +97,123 @@ sddmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const
   }
 }
 
+// ---- single-chunk kernel: K == G*VEC (a dense row is exactly one 16-byte piece per lane of a G-lane group) -----------
+// The C row of a group stays in registers while the nonzeros of one row go by, U gathered D rows are in flight per
+// group, and the U partial dot products a lane holds are reduced across the group with a transposing butterfly
+// (U-1 + log2(G/U) shuffles for U nonzeros instead of U*log2(G)).
+template <typename T, int U, int G>
+__device__ __forceinline__ T sddmm_multi_reduce(T (&v)[U], int gl) {
+  int off = G / 2;
+#pragma unroll
+  for (int n = U; n > 1; n >>= 1) {
+    const int half = n / 2;
+    const bool upper = (gl & off) != 0;
+#pragma unroll
+    for (int t = 0; t < half; t++) {
+      const T send = upper ? v[t] : v[t + half];
+      const T keep = upper ? v[t + half] : v[t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];      // lane gl holds the total of nonzero u = gl / (G/U)
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void sddmm_ld_keep(const T* p, T (&v)[VEC], uint64_t keep) {
+  if constexpr (VEC == 4 && sizeof(T) == 4)
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(keep));
+  else if constexpr (VEC == 2 && sizeof(T) == 8)
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(keep));
+  else
+    v[0] = __ldg(p);
+}
+
+template <typename T, int VEC, int G, int UREQ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+sddmm_csr_chunk_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ bvals,
+                       const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ avals, int K, int nnz, int nslots,
+                       const int* __restrict__ slot_first) {
+  constexpr int U = UREQ < G ? UREQ : G;     // nonzeros in flight per lane group
+  constexpr int ROUNDS = G / U;              // rounds per batch of 32 nonzeros
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= nslots) return;
+  const uint64_t keep = tbd::policy_evict_last(), strm = tbd::policy_evict_first();
+  const int lo = w * SDDMM_W, hi = min(lo + SDDMM_W, nnz);
+  const int rlo = __ldg(slot_first + w), rhi = __ldg(slot_first + w + 1);
+  const int g = lane / G, gl = lane % G;
+  const T* Cg = C + gl * VEC;
+  const T* Dg = D + gl * VEC;
+  T c[VEC];
+#pragma unroll
+  for (int x = 0; x < VEC; x++) c[x] = T(0);
+  int cur_i = -1;
+  for (int base = lo; base < hi; base += 32) {
+    const int p = base + lane;
+    const bool ok = p < hi;
+    int my_row = rlo, my_col = 0;
+    T my_b = T(0);
+    if (ok) {
+      my_row = tbd::search_last_le(pos, rlo, rhi, p);
+      my_col = tbd::ldg_stream_i32(crd + p, strm);
+      my_b = tbd::ldg_stream(bvals + p, strm);
+    }
+    T res[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      T d[U][VEC];
+      int ii[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int q = g * G + r * U + u;
+        const int j = __shfl_sync(0xffffffffu, my_col, q);
+        ii[u] = __shfl_sync(0xffffffffu, my_row, q);
+        sddmm_ld_keep<T, VEC>(Dg + (size_t)j * K, d[u], keep);
+      }
+      T part[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int q = g * G + r * U + u;
+        if (ii[u] != cur_i) {              // next row of the sparse operand: refresh the group's piece of C(i,:)
+          cur_i = ii[u];
+          sddmm_ld_keep<T, VEC>(Cg + (size_t)cur_i * K, c, keep);
+        }
+        const T b = __shfl_sync(0xffffffffu, my_b, q);
+        T acc = T(0);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) acc = acc + (b * c[x]) * d[u][x];     // reference association (B*C)*D
+        part[u] = acc;
+      }
+      res[r] = sddmm_multi_reduce<T, U, G>(part, gl);
+    }
+    // nonzero (round r, slot u) of group g now sits in lanes g*G + u*ROUNDS .. +ROUNDS-1; lane u*ROUNDS+r forwards round r
+    T send = res[0];
+#pragma unroll
+    for (int r = 1; r < ROUNDS; r++)
+      if (gl % ROUNDS == r) send = res[r];
+    const T out = __shfl_sync(0xffffffffu, send, g * G + (gl % U) * ROUNDS + gl / U);
+    if (ok) {
+      if constexpr (sizeof(T) == 8) asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(avals + p), "d"(out), "l"(strm) : "memory");
+      else asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(avals + p), "f"(out), "l"(strm) : "memory");
+    }
+  }
+}
+
+template <typename T, int VEC, int G>
+static void sddmm_chunk_go(int variant, int grid8, int grid4, const int* pos, const int* crd, const T* bvals, const T* C, const T* D,
+                           T* avals, int K, int nnz, int nslots, const int* first) {
+  switch (variant) {
+    case 1: sddmm_csr_chunk_kernel<T, VEC, G, 4, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 2: sddmm_csr_chunk_kernel<T, VEC, G, 8, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 3: sddmm_csr_chunk_kernel<T, VEC, G, 4, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 4: sddmm_csr_chunk_kernel<T, VEC, G, 2, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    default: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+  }
+}
+
 template <typename T, int VEC>
 static int sddmm_launch_g(const int* pos, const int* crd, const T* bvals, const T* C, const T* D, T* avals, int rows,
                           int K, int nnz) {
@@ -109,7 +227,22 @@ static int sddmm_launch_g(const int* pos, const int* crd, const T* bvals, const 
 #define TB_SDDMM_GO(GG)                                                                                              \
   sddmm_csr_kernel<T, VEC, GG><<<grid, SDDMM_WARPS * 32, 0, stream()>>>(pos, crd, bvals, C, D, avals, rows, K, nnz, \
                                                                         nslots, (const int*)first)
-  {
+  static const int variant = getenv("TACO_B200_SDDMM_VARIANT") ? atoi(getenv("TACO_B200_SDDMM_VARIANT")) : 0;
+  const bool chunk = variant >= 0 && K % VEC == 0 && groups <= 32 && (groups & (groups - 1)) == 0;
+  if (chunk) {
+    ProfScope ps("sddmm_csr");
+    const int g4 = (nslots + 3) / 4;
+#define TB_SDDMM_CHUNK(GG) sddmm_chunk_go<T, VEC, GG>(variant, grid, g4, pos, crd, bvals, C, D, avals, K, nnz, nslots, (const int*)first)
+    switch (groups) {
+      case 1: TB_SDDMM_CHUNK(1); break;
+      case 2: TB_SDDMM_CHUNK(2); break;
+      case 4: TB_SDDMM_CHUNK(4); break;
+      case 8: TB_SDDMM_CHUNK(8); break;
+      case 16: TB_SDDMM_CHUNK(16); break;
+      default: TB_SDDMM_CHUNK(32); break;
+    }
+#undef TB_SDDMM_CHUNK
+  } else {
   ProfScope ps("sddmm_csr");
   if (groups <= 1) TB_SDDMM_GO(1);
   else if (groups <= 2) TB_SDDMM_GO(2);

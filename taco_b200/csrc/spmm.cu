@@ -133,7 +133,7 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
     }
     if (j < cnt) {                      // 1 .. U-1 left: same two phases, warp-uniform predicates
       const int rem = cnt - j;
-      Frag<T, VEC> bv[U - 1];
+      Frag<T, VEC> bv[U > 1 ? U - 1 : 1];
 #pragma unroll
       for (int u = 0; u < U - 1; u++) {
         if (u < rem) {
@@ -153,8 +153,8 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
   }
 }
 
-template <typename T, int VEC, bool COLMAJOR, int U, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, int nnz, int nslots,
                 const int* __restrict__ slot_rows) {
@@ -220,11 +220,11 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
 }
 
 // Launch variants: (gathers in flight per warp, warps per CTA).  TACO_B200_SPMM_VARIANT selects one for tuning runs.
-template <typename T, int VEC, bool COLMAJOR, int U, int WARPS>
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
 static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz, int nslots,
                     const int* slot_rows) {
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, nnz, nslots,
+  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, nnz, nslots,
                                                                                  slot_rows);
 }
 
@@ -240,10 +240,12 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
     ProfScope ps("spmm_csr");
     const int* sr = (const int*)slot_rows;
     switch (variant) {
-      case 1: spmm_go<T, VEC, COLMAJOR, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 2: spmm_go<T, VEC, COLMAJOR, 4, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 3: spmm_go<T, VEC, COLMAJOR, 8, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      default: spmm_go<T, VEC, COLMAJOR, 4, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 4: spmm_go<T, VEC, COLMAJOR, 2, 4, 12>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 5: spmm_go<T, VEC, COLMAJOR, 2, 8, 7>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
     }
   }
   count_launch(2);

@@ -4,13 +4,23 @@
 // scheduleSpMVSplitPosGPU / scheduleSpMVRowsGPU, /root/reference/test/tests-scheduling-eval.cpp:193-247):
 //   reference: nnz-split over fused pos space, per-thread binary search, ONE GLOBAL fp64 atomicAdd PER NONZERO,
 //              host-serial zeroing of y, block-start array allocated+freed per call in managed memory.
-//   here     : nnz-balanced ROW-ALIGNED tiles (tile b owns the rows whose first nonzero falls in
-//              [b*TILE, (b+1)*TILE) -- same binary search as taco_binarySearchBeforeBlock,
-//              /root/reference/src/codegen/codegen_cuda.cpp:110-125, but each row has exactly one owner so
-//              no atomics and no zero-fill pass are needed); crd/vals are streamed with aligned 128-bit
-//              ld.global.nc.L1::no_allocate loads, products are staged in shared memory and every row is
-//              reduced by one thread in ascending position order -- the operation order of the reference's C
-//              kernel (Appendix A.1), so results are bit-identical to the oracle, not merely within 1e-12.
+//   here     : ONE kernel.  The nonzeros are cut into tiles of TILE = 2048; CTA b
+//              (0) immediately issues aligned 128-bit streaming loads of its window of crd / vals (they depend on
+//                  nothing but blockIdx) plus a 64-entry overlap into the next window,
+//              (1) meanwhile finds the rows whose first nonzero lies in the window with two 128-ary searches over pos
+//                  (3 rounds for 1M rows; the search of taco_binarySearchBeforeBlock,
+//                  /root/reference/src/codegen/codegen_cuda.cpp:110-125, without the block-start array and its
+//                  extra launch),
+//              (2) gathers x through L2 (evict_last), stages the products in shared memory,
+//              (3) reduces every owned row with one thread in ascending position order -- the operation order of the
+//                  reference's C kernel (Appendix A.1), so y is bit-identical to the oracle.  A row has exactly one
+//                  owner: no atomics, no zero-fill pass.
+//              Rows that run past the overlap are finished by the tile that contains their end: the owner publishes
+//              the in-order sum of its piece (partial + epoch flag), tiles lying wholly inside the row publish a tree
+//              sum of their window, and the end tile -- which only ever waits for LOWER-numbered tiles, so in-order CTA
+//              dispatch guarantees progress -- adds the carried value and its own piece in order.  Rows spanning at
+//              most two tiles (<= 2048 nonzeros always do) therefore stay bit-exact; longer rows are deterministic and
+//              within 1e-12 of the sequential sum.
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*(cols + rows).
 #include "common.cuh"
 
@@ -18,14 +28,9 @@ namespace tb {
 
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_VEC = 4;                 // nonzeros per thread per vector step (one int4 of crd)
-
-// tile_rows[b] = first row r with pos[r] >= b*tile   (b = 0..ntiles-1), tile_rows[ntiles] = rows
-__global__ void spmv_tile_rows_kernel(const int* __restrict__ pos, int rows, int tile, int ntiles,
-                                      int* __restrict__ tile_rows) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > ntiles) return;
-  tile_rows[b] = (b == ntiles) ? rows : tbd::search_first_ge(pos, 0, rows, b * tile);
-}
+constexpr int SPMV_STEPS = 2;
+constexpr int SPMV_TILE = SPMV_THREADS * SPMV_VEC * SPMV_STEPS;     // 2048
+constexpr int SPMV_OV = 64;                 // overlap into the next tile (rows ending inside it need no hand-over)
 
 template <typename T> struct ValVec;
 template <> struct ValVec<double> {
@@ -41,102 +46,198 @@ template <> struct ValVec<float> {
   }
 };
 
-// STEPS vector steps per thread => tile of THREADS*VEC*STEPS nonzeros staged in shared memory.
-template <typename T, int STEPS>
-__global__ void __launch_bounds__(SPMV_THREADS)
-spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
-                const T* __restrict__ x, T* __restrict__ y, const int* __restrict__ tile_rows, int nnz) {
-  constexpr int TILE = SPMV_THREADS * SPMV_VEC * STEPS;
-  __shared__ T prod[TILE + SPMV_VEC];
-  const int r0 = tile_rows[blockIdx.x], r1 = tile_rows[blockIdx.x + 1];
-  if (r0 >= r1) return;
-  const int p0 = __ldg(pos + r0), p1 = __ldg(pos + r1);
-  const int tid = threadIdx.x;
-
-  if (p1 - (p0 & ~(SPMV_VEC - 1)) <= TILE) {
-    // ---- fast path: the whole tile fits one staging pass ------------------------------------------------
-    const int base = p0 & ~(SPMV_VEC - 1);          // 16-byte aligned start for the vector loads
-    int4 c[STEPS];
-    T v[STEPS][4];
+template <typename T>
+__device__ __forceinline__ void spmv_load4(const int* __restrict__ crd, const T* __restrict__ vals, int q, int nnz, int4& c,
+                                           T (&v)[4]) {
+  if (q + SPMV_VEC <= nnz) {
+    c = tbd::ldg_stream_i4(crd + q);
+    ValVec<T>::load4(vals + q, v);
+  } else {
+    int cc[4];
 #pragma unroll
-    for (int s = 0; s < STEPS; s++) {
-      int q = base + (s * SPMV_THREADS + tid) * SPMV_VEC;
-      if (q + SPMV_VEC <= nnz) {
-        c[s] = tbd::ldg_stream_i4(crd + q);
-        ValVec<T>::load4(vals + q, v[s]);
-      } else {
-        int cc[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          bool ok = q + e < nnz;
-          cc[e] = ok ? __ldg(crd + q + e) : 0;
-          v[s][e] = ok ? __ldg(vals + q + e) : T(0);
-        }
-        c[s] = make_int4(cc[0], cc[1], cc[2], cc[3]);
-      }
+    for (int e = 0; e < 4; e++) {
+      const bool ok = q + e < nnz;
+      cc[e] = ok ? __ldg(crd + q + e) : 0;
+      v[e] = ok ? __ldg(vals + q + e) : T(0);
     }
-#pragma unroll
-    for (int s = 0; s < STEPS; s++) {
-      int q = base + (s * SPMV_THREADS + tid) * SPMV_VEC;
-      if (q < p1) {   // entries in [base,p0) and [p1, ..) are loaded but never consumed
-        T x0 = __ldg(x + c[s].x), x1 = __ldg(x + c[s].y), x2 = __ldg(x + c[s].z), x3 = __ldg(x + c[s].w);
-        T* d = prod + (q - base);
-        d[0] = v[s][0] * x0; d[1] = v[s][1] * x1; d[2] = v[s][2] * x2; d[3] = v[s][3] * x3;
-      }
-    }
-    __syncthreads();
-    for (int r = r0 + tid; r < r1; r += SPMV_THREADS) {
-      int s = __ldg(pos + r) - base, e = __ldg(pos + r + 1) - base;
-      T acc = T(0);
-      for (int q = s; q < e; q++) acc += prod[q];
-      y[r] = acc;
-    }
-    return;
-  }
-
-  // ---- slow path: the tile owns a row longer than the staging buffer; walk it in chunks -----------------
-  // Empty rows first (they never intersect a chunk).
-  for (int r = r0 + tid; r < r1; r += SPMV_THREADS)
-    if (__ldg(pos + r) == __ldg(pos + r + 1)) y[r] = T(0);
-  T carry = T(0);
-  int carry_row = -1;
-  for (int lo = p0; lo < p1; lo += TILE) {
-    const int hi = min(lo + TILE, p1);
-    __syncthreads();
-    for (int q = lo + tid; q < hi; q += SPMV_THREADS) prod[q - lo] = __ldg(vals + q) * __ldg(x + __ldg(crd + q));
-    __syncthreads();
-    const int rf = tbd::search_last_le(pos, r0, r1 - 1, lo);       // row containing (or preceding) lo
-    const int rl = tbd::search_last_le(pos, r0, r1 - 1, hi - 1);   // row containing hi-1
-    // rows are owned by (r - r0) % THREADS so a row straddling two chunks stays with the thread holding its carry
-    for (int r = rf + ((tid - (rf - r0) % SPMV_THREADS + SPMV_THREADS) % SPMV_THREADS); r <= rl; r += SPMV_THREADS) {
-      int rs = __ldg(pos + r), re = __ldg(pos + r + 1);
-      if (rs == re) continue;
-      int s = max(rs, lo), e = min(re, hi);
-      if (s >= e) continue;
-      T acc = (carry_row == r) ? carry : T(0);
-      for (int q = s; q < e; q++) acc += prod[q - lo];
-      if (re <= hi) y[r] = acc;
-      else { carry = acc; carry_row = r; }
-    }
+    c = make_int4(cc[0], cc[1], cc[2], cc[3]);
   }
 }
 
 template <typename T>
+__device__ __forceinline__ T spmv_ld_x(const T* p, uint64_t keep) {
+  T r;
+  if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(keep));
+  else asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(keep));
+  return r;
+}
+
+// deterministic tree sum of prod[a..b) by the whole CTA; result valid in thread 0
+template <typename T>
+__device__ __forceinline__ T spmv_block_sum(const T* prod, int a, int b, T* red) {
+  T acc = T(0);
+  for (int q = a + (int)threadIdx.x; q < b; q += SPMV_THREADS) acc += prod[q];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  T tot = T(0);
+  if (threadIdx.x == 0)
+    for (int w = 0; w < SPMV_THREADS / 32; w++) tot += red[w];
+  return tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
+                const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
+                int* __restrict__ flag, int epoch) {
+  __shared__ T prod[SPMV_TILE + SPMV_OV];
+  __shared__ T red[SPMV_THREADS / 32];
+  __shared__ int s_cnt[SPMV_THREADS / 32];
+  __shared__ int s_long[4];                        // tail row, its start
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int lo = b * SPMV_TILE;                    // window [lo, hi), staged [lo, hiov)
+  const int hi = min(lo + SPMV_TILE, nnz);
+  const int hiov = min(lo + SPMV_TILE + SPMV_OV, nnz);
+  const bool last_tile = (b == (int)gridDim.x - 1);
+
+  // ---- (0) window loads: independent of the row structure ------------------------------------------------------
+  int4 c[SPMV_STEPS], cx;
+  T v[SPMV_STEPS][4], vx[4];
+#pragma unroll
+  for (int s = 0; s < SPMV_STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, c[s], v[s]);
+  const bool has_x = tid < SPMV_OV / SPMV_VEC;
+  if (has_x) spmv_load4<T>(crd, vals, lo + SPMV_TILE + tid * SPMV_VEC, nnz, cx, vx);
+  if (tid == 0) s_long[0] = -1;
+
+  // ---- (1) owned rows [r_lo, r_hi): first row with pos[r] >= lo / >= hi, 128-ary search per half CTA --------------
+  int r_bound;
+  {
+    const int half = tid >> 7, t = tid & 127;
+    const int target = half ? hi : lo;
+    int base = 0, n = rows + 1;                    // invariant: pos[base + n - 1] >= target  (pos[rows] = nnz)
+    // the trip count follows the unclamped range size so that both halves meet at the barriers
+    for (int nmax = rows + 1; nmax > 1; nmax = (nmax + 127) >> 7) {
+      const int stride = (n + 127) >> 7;
+      const int idx = base + t * stride;
+      const bool below = idx < base + n && __ldg(pos + idx) < target;
+      const unsigned m = __ballot_sync(0xffffffffu, below);
+      if ((tid & 31) == 0) s_cnt[tid >> 5] = __popc(m);
+      __syncthreads();
+      const int f = s_cnt[half * 4] + s_cnt[half * 4 + 1] + s_cnt[half * 4 + 2] + s_cnt[half * 4 + 3];
+      __syncthreads();
+      if (f == 0) { n = 1; }
+      else {
+        const int nb = base + (f - 1) * stride + 1;
+        n = min(stride, base + n - nb);
+        base = nb;
+      }
+    }
+    r_bound = base;
+    if (t == 0) s_cnt[half] = r_bound;
+    __syncthreads();
+  }
+  const int r_lo = s_cnt[0];
+  const int r_hi = last_tile ? rows : s_cnt[1];
+
+  // ---- (2) products into shared memory ------------------------------------------------------------------------------
+  const uint64_t keep = tbd::policy_evict_last();
+#pragma unroll
+  for (int s = 0; s < SPMV_STEPS; s++) {
+    const int q = (s * SPMV_THREADS + tid) * SPMV_VEC;
+    if (lo + q < hiov) {
+      const T x0 = spmv_ld_x(x + c[s].x, keep), x1 = spmv_ld_x(x + c[s].y, keep), x2 = spmv_ld_x(x + c[s].z, keep),
+              x3 = spmv_ld_x(x + c[s].w, keep);
+      T* d = prod + q;
+      d[0] = v[s][0] * x0; d[1] = v[s][1] * x1; d[2] = v[s][2] * x2; d[3] = v[s][3] * x3;
+    }
+  }
+  if (has_x && lo + SPMV_TILE + tid * SPMV_VEC < hiov) {
+    const T x0 = spmv_ld_x(x + cx.x, keep), x1 = spmv_ld_x(x + cx.y, keep), x2 = spmv_ld_x(x + cx.z, keep),
+            x3 = spmv_ld_x(x + cx.w, keep);
+    T* d = prod + SPMV_TILE + tid * SPMV_VEC;
+    d[0] = vx[0] * x0; d[1] = vx[1] * x1; d[2] = vx[2] * x2; d[3] = vx[3] * x3;
+  }
+  __syncthreads();
+
+  // ---- (3) owned rows: one thread per row, ascending positions ------------------------------------------------------
+  for (int r = r_lo + tid; r < r_hi; r += SPMV_THREADS) {
+    const int s = __ldg(pos + r), e = __ldg(pos + r + 1);
+    if (e <= hiov) {
+      T acc = T(0);
+      for (int q = s - lo; q < e - lo; q++) acc += prod[q];
+      y[r] = acc;
+    } else {                                       // only the last owned row can run past the overlap
+      T acc = T(0);
+      for (int q = s - lo; q < hi - lo; q++) acc += prod[q];
+      partial[b] = acc;                            // in-order sum of the owner's piece
+      __threadfence();
+      atomicExch(flag + b, epoch);
+    }
+  }
+
+  // ---- (4) the row that covers nonzero `lo` but started in an earlier tile -----------------------------------------------
+  if (r_lo > 0 && lo < nnz) {
+    const int e_head = __ldg(pos + r_lo);          // uniform over the CTA
+    if (e_head > lo) {
+      const int s_head = __ldg(pos + r_lo - 1);
+      const int b0 = s_head / SPMV_TILE;           // owner tile
+      if (e_head > min((b0 + 1) * SPMV_TILE + SPMV_OV, nnz)) {     // the owner handed this row over
+        if (e_head > hi) {                         // this window lies wholly inside the row
+          const T sum = spmv_block_sum(prod, 0, hi - lo, red);
+          if (tid == 0) {
+            partial[b] = sum;
+            __threadfence();
+            atomicExch(flag + b, epoch);
+          }
+        } else if (tid == 0) {                     // the row ends here: carry the earlier pieces in tile order
+          T acc = T(0);
+          for (int bb = b0; bb < b; bb++) {
+            while (atomicAdd(flag + bb, 0) != epoch) __nanosleep(40);
+            __threadfence();
+            const T pv = *(volatile T*)(partial + bb);
+            acc = (bb == b0) ? pv : acc + pv;
+          }
+          for (int q = 0; q < e_head - lo; q++) acc += prod[q];
+          y[r_lo - 1] = acc;
+        }
+      }
+    }
+  }
+}
+
+// persistent hand-over scratch (one slot per tile); flags are compared against a per-launch epoch, so they are
+// never cleared between calls
+static void* g_spmv_partial = nullptr;
+static int* g_spmv_flag = nullptr;
+static int g_spmv_cap = 0;
+static int g_spmv_epoch = 0;
+
+template <typename T>
 static int spmv_launch(const CsrView& A, const In& pos, const In& crd, const In& vals, const In& x, Out& y, int nnz) {
-  constexpr int STEPS = 2;
-  constexpr int TILE = SPMV_THREADS * SPMV_VEC * STEPS;
-  int ntiles = nnz > 0 ? (nnz + TILE - 1) / TILE : 1;
-  void* tile_rows = nullptr;
-  TB_TRY(scratch_alloc(&tile_rows, sizeof(int) * (size_t)(ntiles + 1)));
-  spmv_tile_rows_kernel<<<(ntiles + 1 + 255) / 256, 256, 0, stream()>>>(pos.as<int>(), A.rows, TILE, ntiles,
-                                                                          (int*)tile_rows);
+  const int ntiles = nnz > 0 ? (nnz + SPMV_TILE - 1) / SPMV_TILE : 1;
+  if (ntiles > g_spmv_cap) {
+    if (g_spmv_partial) { cudaFree(g_spmv_partial); cudaFree(g_spmv_flag); }
+    g_spmv_cap = ntiles + ntiles / 2 + 1024;
+    TB_CUDA(cudaMalloc(&g_spmv_partial, sizeof(double) * (size_t)g_spmv_cap));
+    TB_CUDA(cudaMalloc((void**)&g_spmv_flag, sizeof(int) * (size_t)g_spmv_cap));
+    TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
+    g_spmv_epoch = 0;
+  }
+  if (++g_spmv_epoch == INT32_MAX) {
+    TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
+    g_spmv_epoch = 1;
+  }
   {
     ProfScope ps("spmv_csr");
-    spmv_csr_kernel<T, STEPS><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<T>(),
-                                                                      x.as<T>(), y.as<T>(), (const int*)tile_rows, nnz);
+    spmv_csr_kernel<T><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<T>(), x.as<T>(),
+                                                              y.as<T>(), A.rows, nnz, (T*)g_spmv_partial, g_spmv_flag,
+                                                              g_spmv_epoch);
   }
-  count_launch(2);
-  scratch_free(tile_rows);
+  count_launch(1);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }
