@@ -68,11 +68,121 @@ spadd_fill_kernel(int n, const int* __restrict__ Apos, const int* __restrict__ A
   for (; b < be; b++, p++) { if (CRD) Ccrd[p] = __ldg(Bcrd + b); if (VALS) Cv[p] = __ldg(Bv + b); }
 }
 
+// Row-block kernels: a CTA owns `rb` consecutive rows.  Their segments of A and B (and of C) are contiguous, so they
+// are moved between HBM and shared memory with fully coalesced accesses and the per-row two-finger merges run out of
+// shared memory.  MODE: 0 = count (symbolic), 1 = crd only (assemble), 2 = vals only (compute), 3 = crd + vals
+// (evaluate).  A row block whose segments exceed the staging capacity takes the direct path below.
+constexpr int SPADD_THREADS = 256;     // staging threads; the first rb of them also merge one row each
+constexpr int SPADD_CAP = 2048;       // staged entries per operand per CTA
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(SPADD_THREADS)
+spadd_block_kernel(int n, int rb, const int* __restrict__ Apos, const int* __restrict__ Acrd, const T* __restrict__ Av,
+                   const int* __restrict__ Bpos, const int* __restrict__ Bcrd, const T* __restrict__ Bv,
+                   const int* __restrict__ Cpos, int* __restrict__ Ccrd, T* __restrict__ Cv, int* __restrict__ counts) {
+  constexpr bool CRD = (MODE & 1) != 0, VALS = (MODE & 2) != 0, COUNT = MODE == 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [A crd | B crd | C crd (if CRD)] ints, then [A vals | B vals | C vals] (if VALS)
+  int* sAc = (int*)smem_raw;
+  int* sBc = sAc + SPADD_CAP;
+  int* sCc = sBc + SPADD_CAP;
+  T* sAv = (T*)(sCc + (CRD ? 2 * SPADD_CAP : 0));
+  T* sBv = sAv + SPADD_CAP;
+  T* sCv = sBv + SPADD_CAP;
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * rb, r1 = min(r0 + rb, n);
+  if (COUNT && blockIdx.x == gridDim.x - 1 && tid == 0) counts[n] = 0;
+  const int a0 = __ldg(Apos + r0), a1 = __ldg(Apos + r1), b0 = __ldg(Bpos + r0), b1 = __ldg(Bpos + r1);
+  const int r = r0 + tid;
+  const bool mine = tid < rb && r < r1;
+  if (a1 - a0 <= SPADD_CAP && b1 - b0 <= SPADD_CAP) {
+#pragma unroll 4
+    for (int q = tid; q < a1 - a0; q += SPADD_THREADS) { sAc[q] = tbd::ldg_stream_i32(Acrd + a0 + q); if (VALS) sAv[q] = __ldg(Av + a0 + q); }
+#pragma unroll 4
+    for (int q = tid; q < b1 - b0; q += SPADD_THREADS) { sBc[q] = tbd::ldg_stream_i32(Bcrd + b0 + q); if (VALS) sBv[q] = __ldg(Bv + b0 + q); }
+    const int c0 = COUNT ? 0 : __ldg(Cpos + r0), c1 = COUNT ? 0 : __ldg(Cpos + r1);
+    int a = 0, ae = 0, b = 0, be = 0, p = 0;
+    if (mine) {
+      a = __ldg(Apos + r) - a0; ae = __ldg(Apos + r + 1) - a0; b = __ldg(Bpos + r) - b0; be = __ldg(Bpos + r + 1) - b0;
+      if (!COUNT) p = __ldg(Cpos + r) - c0;
+    }
+    __syncthreads();
+    if (mine) {
+      int cnt = 0;
+      while (a < ae && b < be) {
+        const int ja = sAc[a], jb = sBc[b], j = min(ja, jb);
+        if (COUNT) cnt++;
+        else {
+          if (CRD) sCc[p] = j;
+          if (VALS) sCv[p] = (ja == j && jb == j) ? (sAv[a] + sBv[b]) : (ja == j ? sAv[a] : sBv[b]);
+          p++;
+        }
+        a += (ja == j);
+        b += (jb == j);
+      }
+      if (COUNT) counts[r] = cnt + (ae - a) + (be - b);
+      else {
+        for (; a < ae; a++, p++) { if (CRD) sCc[p] = sAc[a]; if (VALS) sCv[p] = sAv[a]; }
+        for (; b < be; b++, p++) { if (CRD) sCc[p] = sBc[b]; if (VALS) sCv[p] = sBv[b]; }
+      }
+    }
+    if (!COUNT) {
+      __syncthreads();
+#pragma unroll 4
+      for (int q = tid; q < c1 - c0; q += SPADD_THREADS) { if (CRD) Ccrd[c0 + q] = sCc[q]; if (VALS) Cv[c0 + q] = sCv[q]; }
+    }
+    return;
+  }
+  // ---- direct path: segments too long to stage ----------------------------------------------------------------------
+  if (!mine) return;
+  int a = __ldg(Apos + r), ae = __ldg(Apos + r + 1), b = __ldg(Bpos + r), be = __ldg(Bpos + r + 1);
+  int p = COUNT ? 0 : __ldg(Cpos + r), cnt = 0;
+  while (a < ae && b < be) {
+    const int ja = __ldg(Acrd + a), jb = __ldg(Bcrd + b), j = min(ja, jb);
+    if (COUNT) cnt++;
+    else {
+      if (CRD) Ccrd[p] = j;
+      if (VALS) Cv[p] = (ja == j && jb == j) ? (__ldg(Av + a) + __ldg(Bv + b)) : (ja == j ? __ldg(Av + a) : __ldg(Bv + b));
+      p++;
+    }
+    a += (ja == j);
+    b += (jb == j);
+  }
+  if (COUNT) counts[r] = cnt + (ae - a) + (be - b);
+  else {
+    for (; a < ae; a++, p++) { if (CRD) Ccrd[p] = __ldg(Acrd + a); if (VALS) Cv[p] = __ldg(Av + a); }
+    for (; b < be; b++, p++) { if (CRD) Ccrd[p] = __ldg(Bcrd + b); if (VALS) Cv[p] = __ldg(Bv + b); }
+  }
+}
+
+template <typename T, int MODE>
+static int spadd_block_launch(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
+                              const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
+  constexpr bool CRD = (MODE & 1) != 0, VALS = (MODE & 2) != 0;
+  const size_t smem = sizeof(int) * SPADD_CAP * (2 + (CRD ? 2 : 0)) + (VALS ? sizeof(T) * SPADD_CAP * 4 : 0);
+  static bool configured = false;
+  if (!configured) {
+    TB_CUDA(cudaFuncSetAttribute(spadd_block_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  // rows per CTA: as many as keep an average segment at ~70% of the staging capacity
+  const double avg = (double)(nnzA > nnzB ? nnzA : nnzB) / (n > 0 ? n : 1);
+  int rb = avg > 0 ? (int)(0.7 * SPADD_CAP / avg) : SPADD_THREADS;
+  rb = rb > 128 ? 128 : (rb < 4 ? 4 : rb);
+  const int grid = (n + rb - 1) / rb;
+  spadd_block_kernel<T, MODE><<<grid, SPADD_THREADS, smem, stream()>>>(n, rb, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd, Cv,
+                                                                       counts);
+  count_launch(1);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
 // =========================================================================================================
 // SpGEMM
 // =========================================================================================================
 constexpr int SG_WARP_CAP = 256;     // products per row handled by a warp team in shared memory
 constexpr int SG_CTA_CAP = 8192;     // products per row handled by a CTA team in shared memory
+constexpr int SG_BINS = 5;           // 0: <=64, 1: <=128, 2: <=256 products (warp, registers), 3: <=8192 (CTA), 4: bitmap
 
 // upper bound of the row pattern = number of products; rows are binned by it
 __global__ void __launch_bounds__(256)
@@ -85,10 +195,185 @@ spgemm_bound_kernel(int n, const int* __restrict__ Apos, const int* __restrict__
     int j = __ldg(Acrd + p);
     ub += __ldg(Bpos + j + 1) - __ldg(Bpos + j);
   }
-  if (ub == 0) { counts[i] = 0; return; }
-  int bin = ub <= SG_WARP_CAP ? 0 : (ub <= SG_CTA_CAP ? 1 : 2);
-  int slot = atomicAdd(bin_count + bin, 1);
-  bin_rows[(size_t)bin * n + slot] = i;
+  if (ub == 0) { if (counts) counts[i] = 0; return; }
+  int bin = ub <= 64 ? 0 : (ub <= 128 ? 1 : (ub <= 256 ? 2 : (ub <= SG_CTA_CAP ? 3 : 4)));
+  // warp-aggregated append: one atomic per (warp, bin)
+  for (int b = 0; b < SG_BINS; b++) {
+    const unsigned m = __ballot_sync(__activemask(), bin == b);
+    if (bin == b) {
+      const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(bin_count + b, __popc(m));
+      base = __shfl_sync(m, base, leader);
+      bin_rows[(size_t)b * n + base + __popc(m & ((1u << lane) - 1))] = i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Rows with at most EPL*32 products: one warp per row, everything in registers / per-warp shared memory.
+// ---------------------------------------------------------------------------------------------------------
+// Expansion shared by the count and the fill kernel: visit every product (t, k, a*b) of row i in generation order
+// t = 0,1,.. (A entries ascending, then the B row in order -- the order of the reference's workspace loop, Appendix
+// A.5).  G lanes share one A entry, so short B rows still fill the warp.
+template <typename T, bool VALS, typename F>
+__device__ __forceinline__ int spgemm_expand(int i, int G, const int* __restrict__ Apos, const int* __restrict__ Acrd,
+                                             const T* __restrict__ Av, const int* __restrict__ Bpos,
+                                             const int* __restrict__ Bcrd, const T* __restrict__ Bv, F&& visit) {
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G, gl = lane % G, NG = 32 / G;
+  const int a0 = __ldg(Apos + i), a1 = __ldg(Apos + i + 1);
+  int total = 0;
+  for (int ab = a0; ab < a1; ab += 32) {
+    int bs = 0, len = 0;
+    T av = T(0);
+    if (ab + lane < a1) {
+      const int j = __ldg(Acrd + ab + lane);
+      if (VALS) av = __ldg(Av + ab + lane);
+      bs = __ldg(Bpos + j);
+      len = __ldg(Bpos + j + 1) - bs;
+    }
+    int incl = len;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const int off = total + incl - len;
+    const int cnt = min(32, a1 - ab);
+    for (int q0 = 0; q0 < cnt; q0 += NG) {
+      const int q = min(q0 + grp, 31);
+      const int qbs = __shfl_sync(0xffffffffu, bs, q);
+      int qlen = __shfl_sync(0xffffffffu, len, q);
+      if (q0 + grp >= cnt) qlen = 0;
+      const int qoff = __shfl_sync(0xffffffffu, off, q);
+      const T qa = __shfl_sync(0xffffffffu, av, q);
+      for (int l = gl; l < qlen; l += G) {
+        const int k = __ldg(Bcrd + qbs + l);
+        T prod = T(0);
+        if (VALS) prod = qa * __ldg(Bv + qbs + l);
+        visit(qoff + l, k, prod);
+      }
+    }
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  return total;
+}
+
+// symbolic count: distinct columns among the products of a row, with a per-warp open-addressing hash set
+template <int EPL>
+__global__ void __launch_bounds__(256)
+spgemm_count_warp_kernel(const int* __restrict__ rows_list, int nrows_bin, int G, const int* __restrict__ Apos,
+                         const int* __restrict__ Acrd, const int* __restrict__ Bpos, const int* __restrict__ Bcrd,
+                         int* __restrict__ counts) {
+  constexpr int SLOTS = EPL * 64;                 // 2x the product capacity
+  __shared__ int table_all[8][SLOTS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ridx = blockIdx.x * 8 + wid;
+  if (ridx >= nrows_bin) return;
+  int* table = table_all[wid];
+#pragma unroll
+  for (int t = 0; t < SLOTS / 32; t++) table[t * 32 + lane] = -1;
+  __syncwarp();
+  const int i = __ldg(rows_list + ridx);
+  int mine = 0;
+  spgemm_expand<float, false>(i, G, Apos, Acrd, (const float*)nullptr, Bpos, Bcrd, (const float*)nullptr,
+                              [&](int, int k, float) {
+                                unsigned h = ((unsigned)k * 2654435761u) >> 7;
+                                while (true) {
+                                  h &= SLOTS - 1;
+                                  const int old = atomicCAS(table + h, -1, k);
+                                  if (old == -1) { mine++; break; }
+                                  if (old == k) break;
+                                  h++;
+                                }
+                              });
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if (lane == 0) counts[i] = mine;
+}
+
+// fill: expand (column<<8 | t) keys, bitonic-sort them in registers (EPL per lane, blocked layout: distances < EPL are
+// in-lane, the rest are shuffles), then every run of equal columns is summed IN GENERATION ORDER by the lane that holds
+// its head -- the first product is stored, later ones added, like the reference's `w[k] = a*b` / `w[k] += a*b`.
+template <typename T, typename KEY, int EPL, bool CRD, bool VALS>
+__global__ void __launch_bounds__(256)
+spgemm_fill_warp_kernel(const int* __restrict__ rows_list, int nrows_bin, int G, const int* __restrict__ Apos,
+                        const int* __restrict__ Acrd, const T* __restrict__ Av, const int* __restrict__ Bpos,
+                        const int* __restrict__ Bcrd, const T* __restrict__ Bv, const int* __restrict__ Cpos,
+                        int* __restrict__ Ccrd, T* __restrict__ Cv) {
+  constexpr int N = EPL * 32;
+  __shared__ __align__(16) KEY skey_all[8][N];
+  __shared__ __align__(16) T sval_all[8][VALS ? N : 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ridx = blockIdx.x * 8 + wid;
+  if (ridx >= nrows_bin) return;
+  KEY* skey = skey_all[wid];
+  T* sval = sval_all[wid];
+  const int i = __ldg(rows_list + ridx);
+  const int total = spgemm_expand<T, VALS>(i, G, Apos, Acrd, Av, Bpos, Bcrd, Bv, [&](int t, int k, T prod) {
+    skey[t] = ((KEY)(unsigned)k << 8) | (KEY)t;
+    if (VALS) sval[t] = prod;
+  });
+  for (int t = total + lane; t < N; t += 32) skey[t] = ~(KEY)0;
+  __syncwarp();
+  KEY key[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; e++) key[e] = skey[lane * EPL + e];
+  // bitonic sort, ascending over x = lane*EPL + e
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= EPL) {
+        const int lj = j / EPL;
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          const int x = lane * EPL + e;
+          const KEY other = __shfl_xor_sync(0xffffffffu, key[e], lj);
+          const bool keep_min = ((x & k) == 0) == ((lane & lj) == 0);
+          const KEY lo_ = key[e] < other ? key[e] : other, hi_ = key[e] < other ? other : key[e];
+          key[e] = keep_min ? lo_ : hi_;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+          if ((e & j) == 0) {
+            const int x = lane * EPL + e;
+            const bool asc = (x & k) == 0;
+            const KEY a = key[e], b = key[e | j];
+            const bool sw = asc ? (a > b) : (a < b);
+            key[e] = sw ? b : a;
+            key[e | j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < EPL; e++) skey[lane * EPL + e] = key[e];
+  __syncwarp();
+  // run heads (striped positions p = e*32 + lane so that output writes are coalesced)
+  const int c0 = __ldg(Cpos + i);
+  int before = 0;
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const int p = e * 32 + lane;
+    const KEY kp = skey[p];
+    const bool head = p < total && (p == 0 || (skey[p - 1] >> 8) != (kp >> 8));
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int rank = before + __popc(m & ((1u << lane) - 1));
+      if (CRD) Ccrd[c0 + rank] = (int)(kp >> 8);
+      if (VALS) {
+        T acc = sval[(int)(kp & 255)];
+        for (int pp = p + 1; pp < total && (skey[pp] >> 8) == (kp >> 8); pp++) acc = acc + sval[(int)(skey[pp] & 255)];
+        Cv[c0 + rank] = acc;
+      }
+    }
+    before += __popc(m);
+  }
 }
 
 // Team-cooperative symbolic phase: expand the columns of all products of a row into shared memory, bitonic-sort them,
@@ -235,13 +520,14 @@ spgemm_symbolic_bitmap_kernel(const int* __restrict__ rows_list, int nrows_bin, 
 // add, exactly as the reference's workspace does (w[k] = a*b | w[k] = w[k] + a*b).
 template <typename T, int TEAM>
 __global__ void __launch_bounds__(256)
-spgemm_numeric_kernel(int n, const int* __restrict__ Apos, const int* __restrict__ Acrd, const T* __restrict__ Av,
-                      const int* __restrict__ Bpos, const int* __restrict__ Bcrd, const T* __restrict__ Bv,
-                      const int* __restrict__ Cpos, const int* __restrict__ Ccrd, T* Cv) {
+spgemm_numeric_kernel(const int* __restrict__ rows_list, int n, const int* __restrict__ Apos, const int* __restrict__ Acrd,
+                      const T* __restrict__ Av, const int* __restrict__ Bpos, const int* __restrict__ Bcrd,
+                      const T* __restrict__ Bv, const int* __restrict__ Cpos, const int* __restrict__ Ccrd, T* Cv) {
   const int gt = blockIdx.x * 256 + threadIdx.x;
-  const int i = gt / TEAM, tl = gt % TEAM;
+  const int ridx = gt / TEAM, tl = gt % TEAM;
   const unsigned mask = TEAM == 32 ? 0xffffffffu : (((1u << TEAM) - 1u) << ((threadIdx.x & 31) / TEAM * TEAM));
-  if (i >= n) return;
+  if (ridx >= n) return;
+  const int i = rows_list ? __ldg(rows_list + ridx) : ridx;
   const int c0 = __ldg(Cpos + i), c1 = __ldg(Cpos + i + 1);
   for (int t = c0 + tl; t < c1; t += TEAM) Cv[t] = T(0);
   __syncwarp(mask);
@@ -300,11 +586,11 @@ static int csr3_prepare(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B, bo
   return TACO_B200_OK;
 }
 
-// hand freshly built device pos / crd to the caller in the configured result space
-static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int32_t nnzC, size_t esize) {
+// hand freshly built device pos / crd (and, after a fused evaluate, vals) to the caller in the configured result space
+static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int32_t nnzC, size_t esize, void* dvals = nullptr) {
   if (result_space() == TACO_B200_SPACE_DEVICE) {
-    void* vals = result_alloc(esize * (size_t)nnzC);
-    if (!vals) return fail(TACO_B200_ERR_ALLOC, "cannot allocate result values");
+    void* vals = dvals;
+    if (!vals) TB_TRY(device_result_alloc(&vals, esize * (size_t)(nnzC > 0 ? nnzC : 1)));
     C->indices[1][0] = (uint8_t*)dpos;
     C->indices[1][1] = (uint8_t*)dcrd;
     C->vals = (uint8_t*)vals;
@@ -315,9 +601,11 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
     if (!hpos || !hcrd || !vals) return fail(TACO_B200_ERR_ALLOC, "cannot allocate host result arrays");
     TB_CUDA(cudaMemcpyAsync(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, stream()));
     if (nnzC) TB_CUDA(cudaMemcpyAsync(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC, cudaMemcpyDeviceToHost, stream()));
+    if (nnzC && dvals) TB_CUDA(cudaMemcpyAsync(vals, dvals, esize * (size_t)nnzC, cudaMemcpyDeviceToHost, stream()));
     TB_CUDA(cudaStreamSynchronize(stream()));
     device_result_free(dpos);
     device_result_free(dcrd);
+    device_result_free(dvals);
     C->indices[1][0] = (uint8_t*)hpos;
     C->indices[1][1] = (uint8_t*)hcrd;
     C->vals = (uint8_t*)vals;
@@ -326,28 +614,39 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
   return TACO_B200_OK;
 }
 
-static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s) {
+// symbolic count -> scan -> (host learns nnz) -> fill.  with_vals: the fill also writes the values (evaluate), so the
+// operands are merged twice instead of three times.
+template <typename T>
+static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* bv) {
   const int n = s.A.rows;
+  const bool with_vals = av != nullptr;
   int* dpos = nullptr;
   TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
-  {
+  if (n > 0) {
     ProfScope ps("spadd_symbolic");
-    spadd_count_kernel<<<(n + 1 + 255) / 256, 256, 0, stream()>>>(n, s.apos.as<int>(), s.acrd.as<int>(), s.bpos.as<int>(),
-                                                                 s.bcrd.as<int>(), dpos);
+    TB_TRY((spadd_block_launch<T, 0>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), nullptr, s.bpos.as<int>(),
+                                     s.bcrd.as<int>(), nullptr, nullptr, nullptr, nullptr, dpos)));
+  } else {
+    TB_CUDA(cudaMemsetAsync(dpos, 0, sizeof(int), stream()));
   }
-  count_launch(1);
   TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
   int32_t nnzC = 0;
   TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
   int* dcrd = nullptr;
   TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
-  if (n > 0) {
-    spadd_fill_kernel<double, true, false><<<(n + 255) / 256, 256, 0, stream()>>>(
-        n, s.apos.as<int>(), s.acrd.as<int>(), nullptr, s.bpos.as<int>(), s.bcrd.as<int>(), nullptr, dpos, dcrd, nullptr);
-    count_launch(1);
+  void* dvals = nullptr;
+  if (with_vals) TB_TRY(device_result_alloc(&dvals, sizeof(T) * (size_t)(nnzC > 0 ? nnzC : 1)));
+  if (n > 0 && nnzC > 0) {
+    if (with_vals) {
+      ProfScope ps("spadd_numeric");
+      TB_TRY((spadd_block_launch<T, 3>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), av, s.bpos.as<int>(), s.bcrd.as<int>(),
+                                       bv, dpos, dcrd, (T*)dvals, nullptr)));
+    } else {
+      TB_TRY((spadd_block_launch<T, 1>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), nullptr, s.bpos.as<int>(),
+                                       s.bcrd.as<int>(), nullptr, dpos, dcrd, nullptr, nullptr)));
+    }
   }
-  TB_CUDA(cudaGetLastError());
-  return publish_structure(C, n, dpos, dcrd, nnzC, dsize(s.A.dt));
+  return publish_structure(C, n, dpos, dcrd, nnzC, sizeof(T), dvals);
 }
 
 template <typename T>
@@ -355,94 +654,162 @@ static int spadd_numeric(Csr3& s, const In& av, const In& bv, const In& cpos, Ou
   const int n = s.A.rows;
   if (n > 0) {
     ProfScope ps("spadd_numeric");
-    spadd_fill_kernel<T, false, true><<<(n + 255) / 256, 256, 0, stream()>>>(
-        n, s.apos.as<int>(), s.acrd.as<int>(), av.as<T>(), s.bpos.as<int>(), s.bcrd.as<int>(), bv.as<T>(), cpos.as<int>(),
-        nullptr, cv.as<T>());
-    count_launch(1);
+    TB_TRY((spadd_block_launch<T, 2>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), av.as<T>(), s.bpos.as<int>(),
+                                     s.bcrd.as<int>(), bv.as<T>(), cpos.as<int>(), nullptr, cv.as<T>(), nullptr)));
   }
-  TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }
 
-static int spgemm_assemble_impl(taco_tensor_t* C, Csr3& s) {
-  const int n = s.A.rows, ncols = s.B.cols;
-  int* dpos = nullptr;
-  TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
-  void *bin_count = nullptr, *bin_rows = nullptr, *bitmaps = nullptr;
-  TB_TRY(scratch_alloc(&bin_count, sizeof(int) * 4));
-  TB_TRY(scratch_alloc(&bin_rows, sizeof(int) * 3 * (size_t)(n > 0 ? n : 1)));
-  TB_CUDA(cudaMemsetAsync(bin_count, 0, sizeof(int) * 4, stream()));
-  TB_CUDA(cudaMemsetAsync(dpos + n, 0, sizeof(int), stream()));
-  int hbin[4] = {0, 0, 0, 0};
+// ---- SpGEMM host side ---------------------------------------------------------------------------------------------
+struct SgBins {
+  void* bin_count = nullptr;
+  void* bin_rows = nullptr;
+  void* bitmaps = nullptr;
+  int h[SG_BINS] = {0, 0, 0, 0, 0};
+  int big_grid = 0;
+  const int* rows(int b, int n) const { return (const int*)bin_rows + (size_t)b * n; }
+  ~SgBins() { scratch_free(bin_count); scratch_free(bin_rows); scratch_free(bitmaps); }
+};
+
+// bin the rows by their number of products (and store 0 into counts[] for rows without any, if counts != nullptr)
+static int spgemm_make_bins(Csr3& s, int* counts, SgBins* b) {
+  const int n = s.A.rows;
+  TB_TRY(scratch_alloc(&b->bin_count, sizeof(int) * 8));
+  TB_TRY(scratch_alloc(&b->bin_rows, sizeof(int) * SG_BINS * (size_t)(n > 0 ? n : 1)));
+  TB_CUDA(cudaMemsetAsync(b->bin_count, 0, sizeof(int) * 8, stream()));
   if (n > 0) {
     spgemm_bound_kernel<<<(n + 255) / 256, 256, 0, stream()>>>(n, s.apos.as<int>(), s.acrd.as<int>(), s.bpos.as<int>(),
-                                                              (int*)bin_count, (int*)bin_rows, dpos);
+                                                              (int*)b->bin_count, (int*)b->bin_rows, counts);
     count_launch(1);
-    TB_TRY(read_back(hbin, bin_count, sizeof(int) * 4));
+    TB_TRY(read_back(b->h, b->bin_count, sizeof(int) * SG_BINS));
   }
-  const int* rows0 = (const int*)bin_rows;
-  const int* rows1 = rows0 + n;
-  const int* rows2 = rows1 + n;
-  int big_grid = 0;
-  if (hbin[2] > 0) {
-    big_grid = hbin[2] < 2 * num_sms() ? hbin[2] : 2 * num_sms();
-    TB_TRY(scratch_alloc(&bitmaps, sizeof(unsigned) * (size_t)big_grid * ((ncols + 31) / 32)));
-  }
-  for (int pass = 0; pass < 2; pass++) {
-    int* dcrd = nullptr;
-    int32_t nnzC = 0;
-    if (pass == 1) {
-      TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
-      TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
-      TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
-    }
-#define TB_SG_ARGS s.apos.as<int>(), s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), dpos, dpos, dcrd
-    ProfScope ps("spgemm_symbolic");
-    if (hbin[0] > 0) {
-      int grid = (hbin[0] + 7) / 8;
-      if (pass == 0) spgemm_symbolic_kernel<32, SG_WARP_CAP, false><<<grid, 256, 0, stream()>>>(rows0, hbin[0], TB_SG_ARGS);
-      else spgemm_symbolic_kernel<32, SG_WARP_CAP, true><<<grid, 256, 0, stream()>>>(rows0, hbin[0], TB_SG_ARGS);
-      count_launch(1);
-    }
-    if (hbin[1] > 0) {
-      if (pass == 0) spgemm_symbolic_kernel<256, SG_CTA_CAP, false><<<hbin[1], 256, 0, stream()>>>(rows1, hbin[1], TB_SG_ARGS);
-      else spgemm_symbolic_kernel<256, SG_CTA_CAP, true><<<hbin[1], 256, 0, stream()>>>(rows1, hbin[1], TB_SG_ARGS);
-      count_launch(1);
-    }
-#undef TB_SG_ARGS
-    if (hbin[2] > 0) {
-      if (pass == 0)
-        spgemm_symbolic_bitmap_kernel<false><<<big_grid, 256, 0, stream()>>>(rows2, hbin[2], ncols, s.apos.as<int>(),
-            s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), (unsigned*)bitmaps, dpos, dpos, dcrd);
-      else
-        spgemm_symbolic_bitmap_kernel<true><<<big_grid, 256, 0, stream()>>>(rows2, hbin[2], ncols, s.apos.as<int>(),
-            s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), (unsigned*)bitmaps, dpos, dpos, dcrd);
-      count_launch(1);
-    }
-    TB_CUDA(cudaGetLastError());
-    if (pass == 1) {
-      scratch_free(bin_count); scratch_free(bin_rows); scratch_free(bitmaps);
-      return publish_structure(C, n, dpos, dcrd, nnzC, dsize(s.A.dt));
-    }
+  if (b->h[4] > 0) {
+    b->big_grid = b->h[4] < 2 * num_sms() ? b->h[4] : 2 * num_sms();
+    TB_TRY(scratch_alloc(&b->bitmaps, sizeof(unsigned) * (size_t)b->big_grid * ((s.B.cols + 31) / 32)));
   }
   return TACO_B200_OK;
+}
+
+static int spgemm_group_lanes(const Csr3& s) {   // lanes that share one A entry in the warp kernels
+  const double avg = s.B.rows > 0 ? (double)s.nnzB / s.B.rows : 0.0;
+  return avg <= 8.0 ? 8 : (avg <= 16.0 ? 16 : 32);
+}
+
+template <typename T, typename KEY, bool CRD, bool VALS>
+static void spgemm_fill_warp_bins(const SgBins& b, Csr3& s, const T* av, const T* bv, const int* dpos, int* dcrd, T* dvals) {
+  const int n = s.A.rows, G = spgemm_group_lanes(s);
+#define TB_SG_FILL(BIN, EPL)                                                                                            \
+  if (b.h[BIN] > 0) {                                                                                                   \
+    spgemm_fill_warp_kernel<T, KEY, EPL, CRD, VALS><<<(b.h[BIN] + 7) / 8, 256, 0, stream()>>>(                          \
+        b.rows(BIN, n), b.h[BIN], G, s.apos.as<int>(), s.acrd.as<int>(), av, s.bpos.as<int>(), s.bcrd.as<int>(), bv, dpos, dcrd, \
+        dvals);                                                                                                         \
+    count_launch(1);                                                                                                    \
+  }
+  TB_SG_FILL(0, 2)
+  TB_SG_FILL(1, 4)
+  TB_SG_FILL(2, 8)
+#undef TB_SG_FILL
 }
 
 template <typename T>
-static int spgemm_numeric(Csr3& s, const In& av, const In& bv, const In& cpos, const In& ccrd, Out& cv) {
-  const int n = s.A.rows;
-  if (n == 0) return TACO_B200_OK;
-  double avg = s.B.rows > 0 ? (double)s.nnzB / s.B.rows : 0.0;
-#define TB_SGN(TEAM)                                                                                               \
-  spgemm_numeric_kernel<T, TEAM><<<(unsigned)(((long long)n * TEAM + 255) / 256), 256, 0, stream()>>>(              \
-      n, s.apos.as<int>(), s.acrd.as<int>(), av.as<T>(), s.bpos.as<int>(), s.bcrd.as<int>(), bv.as<T>(), cpos.as<int>(), \
-      ccrd.as<int>(), cv.as<T>())
-  ProfScope ps("spgemm_numeric");
+static void spgemm_numeric_rows(const int* rows_list, int nrows, Csr3& s, const T* av, const T* bv, const int* cpos,
+                                const int* ccrd, T* cv) {
+  if (nrows <= 0) return;
+  const double avg = s.B.rows > 0 ? (double)s.nnzB / s.B.rows : 0.0;
+#define TB_SGN(TEAM)                                                                                                   \
+  spgemm_numeric_kernel<T, TEAM><<<(unsigned)(((long long)nrows * TEAM + 255) / 256), 256, 0, stream()>>>(              \
+      rows_list, nrows, s.apos.as<int>(), s.acrd.as<int>(), av, s.bpos.as<int>(), s.bcrd.as<int>(), bv, cpos, ccrd, cv)
   if (avg <= 12.0) TB_SGN(8);
   else if (avg <= 24.0) TB_SGN(16);
   else TB_SGN(32);
 #undef TB_SGN
   count_launch(1);
+}
+
+// symbolic count -> scan -> (host learns nnz) -> fill.  av != nullptr: the fill also computes the values (evaluate).
+template <typename T>
+static int spgemm_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* bv) {
+  const int n = s.A.rows, ncols = s.B.cols;
+  const bool with_vals = av != nullptr;
+  const bool key32 = ncols <= (1 << 24);
+  int* dpos = nullptr;
+  TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
+  TB_CUDA(cudaMemsetAsync(dpos + n, 0, sizeof(int), stream()));
+  SgBins b;
+  TB_TRY(spgemm_make_bins(s, dpos, &b));
+  const int G = spgemm_group_lanes(s);
+  {
+    ProfScope ps("spgemm_symbolic");
+#define TB_SG_COUNT(BIN, EPL)                                                                                            \
+    if (b.h[BIN] > 0) {                                                                                                  \
+      spgemm_count_warp_kernel<EPL><<<(b.h[BIN] + 7) / 8, 256, 0, stream()>>>(b.rows(BIN, n), b.h[BIN], G, s.apos.as<int>(), \
+          s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), dpos);                                                   \
+      count_launch(1);                                                                                                   \
+    }
+    TB_SG_COUNT(0, 2)
+    TB_SG_COUNT(1, 4)
+    TB_SG_COUNT(2, 8)
+#undef TB_SG_COUNT
+    if (b.h[3] > 0) {
+      spgemm_symbolic_kernel<256, SG_CTA_CAP, false><<<b.h[3], 256, 0, stream()>>>(b.rows(3, n), b.h[3], s.apos.as<int>(),
+          s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), dpos, dpos, nullptr);
+      count_launch(1);
+    }
+    if (b.h[4] > 0) {
+      spgemm_symbolic_bitmap_kernel<false><<<b.big_grid, 256, 0, stream()>>>(b.rows(4, n), b.h[4], ncols, s.apos.as<int>(),
+          s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), (unsigned*)b.bitmaps, dpos, dpos, nullptr);
+      count_launch(1);
+    }
+  }
+  TB_CUDA(cudaGetLastError());
+  TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
+  int32_t nnzC = 0;
+  TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
+  int* dcrd = nullptr;
+  TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
+  void* dvals = nullptr;
+  if (with_vals) TB_TRY(device_result_alloc(&dvals, sizeof(T) * (size_t)(nnzC > 0 ? nnzC : 1)));
+  {
+    ProfScope ps("spgemm_numeric");
+    if (with_vals) {
+      if (key32) spgemm_fill_warp_bins<T, uint32_t, true, true>(b, s, av, bv, dpos, dcrd, (T*)dvals);
+      else spgemm_fill_warp_bins<T, uint64_t, true, true>(b, s, av, bv, dpos, dcrd, (T*)dvals);
+    } else {
+      if (key32) spgemm_fill_warp_bins<T, uint32_t, true, false>(b, s, av, bv, dpos, dcrd, (T*)dvals);
+      else spgemm_fill_warp_bins<T, uint64_t, true, false>(b, s, av, bv, dpos, dcrd, (T*)dvals);
+    }
+    if (b.h[3] > 0) {
+      spgemm_symbolic_kernel<256, SG_CTA_CAP, true><<<b.h[3], 256, 0, stream()>>>(b.rows(3, n), b.h[3], s.apos.as<int>(),
+          s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), dpos, dpos, dcrd);
+      count_launch(1);
+      if (with_vals) spgemm_numeric_rows<T>(b.rows(3, n), b.h[3], s, av, bv, dpos, dcrd, (T*)dvals);
+    }
+    if (b.h[4] > 0) {
+      spgemm_symbolic_bitmap_kernel<true><<<b.big_grid, 256, 0, stream()>>>(b.rows(4, n), b.h[4], ncols, s.apos.as<int>(),
+          s.acrd.as<int>(), s.bpos.as<int>(), s.bcrd.as<int>(), (unsigned*)b.bitmaps, dpos, dpos, dcrd);
+      count_launch(1);
+      if (with_vals) spgemm_numeric_rows<T>(b.rows(4, n), b.h[4], s, av, bv, dpos, dcrd, (T*)dvals);
+    }
+  }
+  TB_CUDA(cudaGetLastError());
+  return publish_structure(C, n, dpos, dcrd, nnzC, sizeof(T), dvals);
+}
+
+// compute() on an assembled result: rows with few products re-derive their sorted order in registers and write only
+// the values; long rows locate each product in the row's crd by binary search.
+template <typename T>
+static int spgemm_numeric(Csr3& s, const In& av, const In& bv, const In& cpos, const In& ccrd, Out& cv) {
+  const int n = s.A.rows;
+  if (n == 0) return TACO_B200_OK;
+  SgBins b;
+  TB_TRY(spgemm_make_bins(s, nullptr, &b));
+  ProfScope ps("spgemm_numeric");
+  if (s.B.cols <= (1 << 24))
+    spgemm_fill_warp_bins<T, uint32_t, false, true>(b, s, av.as<T>(), bv.as<T>(), cpos.as<int>(), nullptr, cv.as<T>());
+  else
+    spgemm_fill_warp_bins<T, uint64_t, false, true>(b, s, av.as<T>(), bv.as<T>(), cpos.as<int>(), nullptr, cv.as<T>());
+  spgemm_numeric_rows<T>(b.rows(3, n), b.h[3], s, av.as<T>(), bv.as<T>(), cpos.as<int>(), ccrd.as<int>(), cv.as<T>());
+  spgemm_numeric_rows<T>(b.rows(4, n), b.h[4], s, av.as<T>(), bv.as<T>(), cpos.as<int>(), ccrd.as<int>(), cv.as<T>());
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }
@@ -482,23 +849,41 @@ extern "C" {
 int taco_b200_spadd_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
   Csr3 s;
   TB_TRY(csr3_prepare(C, A, B, false, &s));
-  return spadd_assemble_impl(C, s);
+  if (s.A.dt == DType::F64) return spadd_assemble_impl<double>(C, s, nullptr, nullptr);
+  return spadd_assemble_impl<float>(C, s, nullptr, nullptr);
 }
 int taco_b200_spadd_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) { return sparse_compute(C, A, B, false); }
+// evaluate = assemble + compute with the value fill fused into the structure fill (one merge pass less)
 int taco_b200_spadd_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
-  TB_TRY(taco_b200_spadd_assemble(C, A, B));
-  return taco_b200_spadd_compute(C, A, B);
+  Csr3 s;
+  TB_TRY(csr3_prepare(C, A, B, false, &s));
+  const size_t es = dsize(s.A.dt);
+  In av, bv;
+  TB_TRY(av.acquire(s.A.vals ? s.A.vals : (void*)s.A.pos, es * (size_t)s.nnzA));
+  TB_TRY(bv.acquire(s.B.vals ? s.B.vals : (void*)s.B.pos, es * (size_t)s.nnzB));
+  if (s.A.dt == DType::F64) TB_TRY(spadd_assemble_impl<double>(C, s, av.as<double>(), bv.as<double>()));
+  else TB_TRY(spadd_assemble_impl<float>(C, s, av.as<float>(), bv.as<float>()));
+  return finish_call();
 }
 
 int taco_b200_spgemm_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
   Csr3 s;
   TB_TRY(csr3_prepare(C, A, B, true, &s));
-  return spgemm_assemble_impl(C, s);
+  if (s.A.dt == DType::F64) return spgemm_assemble_impl<double>(C, s, nullptr, nullptr);
+  return spgemm_assemble_impl<float>(C, s, nullptr, nullptr);
 }
 int taco_b200_spgemm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) { return sparse_compute(C, A, B, true); }
+// evaluate = assemble + compute with the values produced by the same sort that orders the columns
 int taco_b200_spgemm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
-  TB_TRY(taco_b200_spgemm_assemble(C, A, B));
-  return taco_b200_spgemm_compute(C, A, B);
+  Csr3 s;
+  TB_TRY(csr3_prepare(C, A, B, true, &s));
+  const size_t es = dsize(s.A.dt);
+  In av, bv;
+  TB_TRY(av.acquire(s.A.vals ? s.A.vals : (void*)s.A.pos, es * (size_t)s.nnzA));
+  TB_TRY(bv.acquire(s.B.vals ? s.B.vals : (void*)s.B.pos, es * (size_t)s.nnzB));
+  if (s.A.dt == DType::F64) TB_TRY(spgemm_assemble_impl<double>(C, s, av.as<double>(), bv.as<double>()));
+  else TB_TRY(spgemm_assemble_impl<float>(C, s, av.as<float>(), bv.as<float>()));
+  return finish_call();
 }
 
 }  // extern "C"

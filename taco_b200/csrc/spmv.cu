@@ -105,30 +105,24 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   const bool last_tile = (b == (int)gridDim.x - 1);
 
   // ---- (0) window loads: independent of the row structure ------------------------------------------------------
-  int4 c[SPMV_STEPS], cx;
-  T v[SPMV_STEPS][4], vx[4];
+  int4 c[SPMV_STEPS];
+  T v[SPMV_STEPS][4];
 #pragma unroll
   for (int s = 0; s < SPMV_STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, c[s], v[s]);
-  const bool has_x = tid < SPMV_OV / SPMV_VEC;
-  if (has_x) spmv_load4<T>(crd, vals, lo + SPMV_TILE + tid * SPMV_VEC, nnz, cx, vx);
   if (tid == 0) s_long[0] = -1;
 
-  // ---- (1) owned rows [r_lo, r_hi): first row with pos[r] >= lo / >= hi, 128-ary search per half CTA --------------
-  int r_bound;
-  {
-    const int half = tid >> 7, t = tid & 127;
+  // ---- (1) owned rows [r_lo, r_hi): first row with pos[r] >= lo / >= hi.  Warp 0 alone runs two 16-ary searches
+  //          (half a warp each, 5 rounds for 1M rows, no CTA barrier) while the other warps go on to the gathers.
+  if (tid < 32) {
+    const int half = tid >> 4, t = tid & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     const int target = half ? hi : lo;
     int base = 0, n = rows + 1;                    // invariant: pos[base + n - 1] >= target  (pos[rows] = nnz)
-    // the trip count follows the unclamped range size so that both halves meet at the barriers
-    for (int nmax = rows + 1; nmax > 1; nmax = (nmax + 127) >> 7) {
-      const int stride = (n + 127) >> 7;
+    for (int nmax = rows + 1; nmax > 1; nmax = (nmax + 15) >> 4) {   // same trip count for both halves
+      const int stride = (n + 15) >> 4;
       const int idx = base + t * stride;
       const bool below = idx < base + n && __ldg(pos + idx) < target;
-      const unsigned m = __ballot_sync(0xffffffffu, below);
-      if ((tid & 31) == 0) s_cnt[tid >> 5] = __popc(m);
-      __syncthreads();
-      const int f = s_cnt[half * 4] + s_cnt[half * 4 + 1] + s_cnt[half * 4 + 2] + s_cnt[half * 4 + 3];
-      __syncthreads();
+      const int f = __popc(__ballot_sync(0xffffffffu, below) & hmask);
       if (f == 0) { n = 1; }
       else {
         const int nb = base + (f - 1) * stride + 1;
@@ -136,12 +130,11 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
         base = nb;
       }
     }
-    r_bound = base;
-    if (t == 0) s_cnt[half] = r_bound;
-    __syncthreads();
+    if (t == 0) s_cnt[half] = base;
+    // pull the pos entries of the owned rows towards L2 while the gathers run (they are needed after the barrier)
+    const int p_lo = __shfl_sync(0xffffffffu, base, 0), p_hi = last_tile ? rows : __shfl_sync(0xffffffffu, base, 16);
+    if (p_lo + tid * 32 <= p_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(pos + p_lo + tid * 32));
   }
-  const int r_lo = s_cnt[0];
-  const int r_hi = last_tile ? rows : s_cnt[1];
 
   // ---- (2) products into shared memory ------------------------------------------------------------------------------
   const uint64_t keep = tbd::policy_evict_last();
@@ -155,13 +148,18 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
       d[0] = v[s][0] * x0; d[1] = v[s][1] * x1; d[2] = v[s][2] * x2; d[3] = v[s][3] * x3;
     }
   }
-  if (has_x && lo + SPMV_TILE + tid * SPMV_VEC < hiov) {
-    const T x0 = spmv_ld_x(x + cx.x, keep), x1 = spmv_ld_x(x + cx.y, keep), x2 = spmv_ld_x(x + cx.z, keep),
-            x3 = spmv_ld_x(x + cx.w, keep);
-    T* d = prod + SPMV_TILE + tid * SPMV_VEC;
-    d[0] = vx[0] * x0; d[1] = vx[1] * x1; d[2] = vx[2] * x2; d[3] = vx[3] * x3;
+  // the overlap into the next window: 16 threads of warp 1
+  if (tid >= 32 && tid < 32 + SPMV_OV / SPMV_VEC && lo + SPMV_TILE + (tid - 32) * SPMV_VEC < hiov) {
+    const int q = SPMV_TILE + (tid - 32) * SPMV_VEC;
+    spmv_load4<T>(crd, vals, lo + q, nnz, c[0], v[0]);
+    const T x0 = spmv_ld_x(x + c[0].x, keep), x1 = spmv_ld_x(x + c[0].y, keep), x2 = spmv_ld_x(x + c[0].z, keep),
+            x3 = spmv_ld_x(x + c[0].w, keep);
+    T* d = prod + q;
+    d[0] = v[0][0] * x0; d[1] = v[0][1] * x1; d[2] = v[0][2] * x2; d[3] = v[0][3] * x3;
   }
   __syncthreads();
+  const int r_lo = s_cnt[0];
+  const int r_hi = last_tile ? rows : s_cnt[1];
 
   // ---- (3) owned rows: one thread per row, ascending positions ------------------------------------------------------
   for (int r = r_lo + tid; r < r_hi; r += SPMV_THREADS) {
