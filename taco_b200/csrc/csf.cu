@@ -179,6 +179,8 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
   }
 }
 
+struct MkSlice { int f0, f1, l0, l1, row, zlo; };   // fibers, leaves, row of A, first row to zero before `row`
+
 template <typename T, int U, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
@@ -186,75 +188,72 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
                   int Idim, int nnz, int nslots, const int* __restrict__ slot_slices) {
   __shared__ MkLeaf<T> stage_all[WARPS][32];
+  __shared__ MkSlice meta_all[WARPS][32];
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
   MkLeaf<T>* stage = stage_all[threadIdx.x >> 5];
+  MkSlice* meta = meta_all[threadIdx.x >> 5];
   const int lo = w * MK_W, hi = min(lo + MK_W, nnz);
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(B3_crd + lo + lane * 32));
   else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bv + lo + (lane - 2) * (128 / (int)sizeof(T))));
-  const uint64_t keep = tbd::policy_evict_last(), strm = tbd::policy_evict_first();
   const int s_base = __ldg(B1_pos), nslices = __ldg(B1_pos + 1) - s_base;
   const int S0 = __ldg(slot_slices + w), S1 = __ldg(slot_slices + w + 1);
 
-  // the piece of a hub slice that started in an earlier slot and covers leaf `lo`
+  // group -1 (optional): the piece [lo, min(hi, end)) of a hub slice that started in an earlier slot (added atomically);
+  // groups 0..: the slices this slot owns, 32 at a time (metadata parked in shared memory, one broadcast read per slice)
   bool tail = false;
-  int t_f0 = 0, t_f1 = 0, t_l1 = 0;
   if (S0 > 0 && lo < nnz) {
-    t_f0 = __ldg(B2_pos + s_base + S0 - 1);
-    t_f1 = __ldg(B2_pos + s_base + S0);
-    const int l0 = __ldg(B3_pos + t_f0);
-    t_l1 = __ldg(B3_pos + t_f1);
-    tail = t_l1 > lo && t_l1 - l0 > MK_LONG;
+    const int f0 = __ldg(B2_pos + s_base + S0 - 1), f1 = __ldg(B2_pos + s_base + S0);
+    const int l0 = __ldg(B3_pos + f0), l1 = __ldg(B3_pos + f1);
+    tail = l1 > lo && l1 - l0 > MK_LONG;
+    if (tail && lane == 0) meta[0] = MkSlice{f0, f1, lo, min(hi, l1), __ldg(B1_crd + s_base + S0 - 1), -1};
   }
   for (int sb = tail ? S0 - 32 : S0; sb < S1; sb += 32) {
     const bool is_tail = sb < S0;
-    const int sl = sb + lane;
-    const bool valid = !is_tail && sl < S1;
-    int f0 = 0, f1 = 0, l0 = 0, l1 = 0, irow = 0, zlo = 0, zhi = 0;
-    if (valid) {
-      const int s = s_base + sl;
-      f0 = __ldg(B2_pos + s); f1 = __ldg(B2_pos + s + 1);
-      l0 = __ldg(B3_pos + f0); l1 = __ldg(B3_pos + f1);
-      irow = __ldg(B1_crd + s);
-      // rows of A without a slice are zeroed by the owner of the next occupied row (and the last owner zeroes the end)
-      zlo = (sl == 0) ? 0 : __ldg(B1_crd + s - 1) + 1;
-      zhi = (sl == nslices - 1) ? Idim : irow + 1;
+    int nwork = 1;
+    if (!is_tail) {
+      nwork = min(32, S1 - sb);
+      __syncwarp();
+      if (lane < nwork) {
+        const int sl = sb + lane, s = s_base + sl;
+        MkSlice m;
+        m.f0 = __ldg(B2_pos + s); m.f1 = __ldg(B2_pos + s + 1);
+        m.l0 = __ldg(B3_pos + m.f0); m.l1 = __ldg(B3_pos + m.f1);
+        m.row = __ldg(B1_crd + s);
+        // rows of A without a slice are zeroed by the owner of the next occupied row
+        m.zlo = (sl == 0) ? 0 : __ldg(B1_crd + s - 1) + 1;
+        meta[lane] = m;
+      }
     }
-    if (is_tail && lane == 0) { f0 = t_f0; f1 = t_f1; l0 = lo; l1 = min(hi, t_l1); irow = __ldg(B1_crd + s_base + S0 - 1); }
-    unsigned work = is_tail ? 1u : __ballot_sync(0xffffffffu, valid);
-    while (work) {
-      const int h = __ffs(work) - 1;
-      work &= work - 1;
-      const int hf0 = __shfl_sync(0xffffffffu, f0, h), hf1 = __shfl_sync(0xffffffffu, f1, h);
-      const int hl0 = __shfl_sync(0xffffffffu, l0, h);
-      int hl1 = __shfl_sync(0xffffffffu, l1, h);
-      const int hi_row = __shfl_sync(0xffffffffu, irow, h);
-      const int hzlo = __shfl_sync(0xffffffffu, zlo, h), hzhi = __shfl_sync(0xffffffffu, zhi, h);
-      const bool hub = is_tail || hl1 - hl0 > MK_LONG;
-      if (hub) hl1 = min(hi, hl1);
+    __syncwarp();
+    for (int h = 0; h < nwork; h++) {
+      const MkSlice m = meta[h];
+      const bool hub = is_tail || m.l1 - m.l0 > MK_LONG;
+      const int l1 = hub ? min(hi, m.l1) : m.l1;
       if (!is_tail) {
-        for (int r = hzlo; r < hzhi; r++) {
-          if (r == hi_row) continue;
-          for (int j = lane; j < R; j += 32) st_stream(A + (size_t)r * R + j, T(0), strm);
-        }
+        for (int r = m.zlo; r < m.row; r++)
+          for (int j = lane; j < R; j += 32) A[(size_t)r * R + j] = T(0);
+        if (sb + h == nslices - 1)                       // the last slice also owns the rows after it
+          for (int r = m.row + 1; r < Idim; r++)
+            for (int j = lane; j < R; j += 32) A[(size_t)r * R + j] = T(0);
       }
       for (int j0 = 0; j0 < R; j0 += 32) {
         const bool active = j0 + lane < R;
         const T* Cj = C + (active ? j0 + lane : 0);
         const T* Dj = D + (active ? j0 + lane : 0);
         T acc = T(0);
-        for (int pb = hl0; pb < hl1; pb += 32) {
-          const int cnt = min(32, hl1 - pb);
+        for (int pb = m.l0; pb < l1; pb += 32) {
+          const int cnt = min(32, l1 - pb);
           if (lane < cnt) {
             const int p = pb + lane;
-            MkLeaf<T> m;
-            m.l = tbd::ldg_stream_i32(B3_crd + p, strm);
-            m.v = tbd::ldg_stream(Bv + p, strm);
-            int f = min(hf0 + (p - hl0), hf1 - 1);          // exact when every fiber of the slice is a singleton
-            if (!(__ldg(B3_pos + f) <= p && __ldg(B3_pos + f + 1) > p)) f = tbd::search_last_le(B3_pos, hf0, hf1 - 1, p);
-            m.k = __ldg(B2_crd + f);
-            stage[lane] = m;
+            MkLeaf<T> e;
+            e.l = tbd::ldg_stream_i32(B3_crd + p);
+            e.v = __ldg(Bv + p);
+            int f = min(m.f0 + (p - m.l0), m.f1 - 1);         // exact when every fiber of the slice is a singleton
+            if (!(__ldg(B3_pos + f) <= p && __ldg(B3_pos + f + 1) > p)) f = tbd::search_last_le(B3_pos, m.f0, m.f1 - 1, p);
+            e.k = __ldg(B2_crd + f);
+            stage[lane] = e;
           }
           __syncwarp();
           int q = 0;
@@ -262,36 +261,24 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
             T cv[U], dv[U], vv[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-              const MkLeaf<T> m = stage[q + u];
-              vv[u] = m.v;
-              cv[u] = ld_keep(Cj + (size_t)m.k * R, keep);
-              dv[u] = ld_keep(Dj + (size_t)m.l * R, keep);
+              const MkLeaf<T> e = stage[q + u];
+              vv[u] = e.v;
+              cv[u] = __ldg(Cj + (size_t)e.k * R);
+              dv[u] = __ldg(Dj + (size_t)e.l * R);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) acc = acc + (vv[u] * cv[u]) * dv[u];
           }
-          if (q < cnt) {
-            const int rem = cnt - q;
-            T cv[U > 1 ? U - 1 : 1], dv[U > 1 ? U - 1 : 1], vv[U > 1 ? U - 1 : 1];
-#pragma unroll
-            for (int u = 0; u < U - 1; u++) {
-              if (u < rem) {
-                const MkLeaf<T> m = stage[q + u];
-                vv[u] = m.v;
-                cv[u] = ld_keep(Cj + (size_t)m.k * R, keep);
-                dv[u] = ld_keep(Dj + (size_t)m.l * R, keep);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < U - 1; u++)
-              if (u < rem) acc = acc + (vv[u] * cv[u]) * dv[u];
+          for (; q < cnt; q++) {
+            const MkLeaf<T> e = stage[q];
+            acc = acc + (e.v * __ldg(Cj + (size_t)e.k * R)) * __ldg(Dj + (size_t)e.l * R);
           }
           __syncwarp();
         }
         if (active) {
-          T* dst = A + (size_t)hi_row * R + j0 + lane;
+          T* dst = A + (size_t)m.row * R + j0 + lane;
           if (hub) atomicAdd(dst, acc);
-          else st_stream(dst, acc, strm);
+          else *dst = acc;
         }
       }
     }
@@ -365,10 +352,10 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
     switch (variant) {
       case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss); break;
       case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss); break;
-      case 3: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss); break;
-      case 4: mttkrp_go<T, 4, 8, 1>(cc, C, D, A, R, nslots, ss); break;
-      case 5: mttkrp_go<T, 4, 8, 5>(cc, C, D, A, R, nslots, ss); break;
-      default: mttkrp_go<T, 4, 8, 4>(cc, C, D, A, R, nslots, ss); break;
+      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss); break;
+      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss); break;
+      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss); break;
+      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss); break;
     }
   }
   count_launch(2);

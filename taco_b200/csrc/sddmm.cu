@@ -209,8 +209,8 @@ static void sddmm_chunk_go(int variant, int grid8, int grid4, const int* pos, co
     case 1: sddmm_csr_chunk_kernel<T, VEC, G, 4, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
     case 2: sddmm_csr_chunk_kernel<T, VEC, G, 8, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
     case 3: sddmm_csr_chunk_kernel<T, VEC, G, 4, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    case 4: sddmm_csr_chunk_kernel<T, VEC, G, 2, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    default: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 4: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    default: sddmm_csr_chunk_kernel<T, VEC, G, 2, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
   }
 }
 

@@ -242,10 +242,10 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
     switch (variant) {
       case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
       case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
       case 4: spmm_go<T, VEC, COLMAJOR, 2, 4, 12>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
       case 5: spmm_go<T, VEC, COLMAJOR, 2, 8, 7>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
     }
   }
   count_launch(2);

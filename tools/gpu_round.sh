@@ -7,8 +7,9 @@ nvidia-smi > gpurun_out/smi.txt 2>&1; nproc >> gpurun_out/smi.txt; free -g >> gp
 for wl in ${WORKLOADS:-spmm spmv sddmm mttkrp spadd spgemm}; do
   ( time timeout 900 python bench.py --workload $wl ) > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
 done
+OURS='regex:^(spmm|spmv|sddmm|csf3|spadd|spgemm|slot_first|scan_|partition|mttkrp)'
 for wl in ${NCU_WORKLOADS:-spmm}; do
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -c 400 --csv \
      --log-file gpurun_out/launches_$wl.csv python bench.py --workload $wl --steps 2 --warmup 3 --no-e2e --no-cpu \
      > gpurun_out/ncu_$wl.log 2>&1
 done
