@@ -50,6 +50,7 @@ struct Context {
   int sms = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t cur_stream = nullptr;
+  cudaStream_t aux[2] = {nullptr, nullptr};   // upload / download streams of the host-operand pipelines
   int space = TACO_B200_SPACE_HOST;
   long launches = 0;
   std::unordered_map<const void*, Resident> resident;
@@ -103,6 +104,16 @@ int ensure_init() {
 }
 
 cudaStream_t stream() { return g.cur_stream; }
+cudaStream_t aux_stream(int i) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!g.aux[i]) cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking);
+  return g.aux[i];
+}
+bool is_resident(const void* host_ptr, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  auto it = g.resident.find(host_ptr);
+  return it != g.resident.end() && it->second.bytes >= bytes;
+}
 int num_sms() { return g.sms; }
 void count_launch(int n) { g.launches += n; }
 int result_space() { return g.space; }

@@ -81,18 +81,22 @@ __device__ __forceinline__ void red_row(T* __restrict__ C, int row, int col, int
   }
 }
 
-// Pre-pass: slot_rows[w] = first row whose first nonzero is at or after w*W; slot_rows[nslots] = rows.
+// A launch covers the row range [r0, r1) = nonzeros [p0, p1) (the whole matrix, or one row chunk of the host-operand
+// pipeline below).
+struct SpmmRange { int r0, r1, p0, p1; };
+
+// Pre-pass: slot_rows[w] = first row whose first nonzero is at or after p0 + w*W; slot_rows[nslots] = r1.
 // Also zeroes the C row of every hub row (done by the slot in which the hub row's first slot boundary falls).
 template <typename T, bool COLMAJOR>
-__global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, int rows, int nnz, int nslots, int K,
+__global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg, int rows, int nslots, int K,
                                       int* __restrict__ slot_rows, T* __restrict__ C) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > nslots) return;
-  if (w == nslots) { slot_rows[w] = rows; return; }
-  int lo = w * SPMM_W;
-  slot_rows[w] = tbd::search_first_ge(pos, 0, rows, lo);
-  if (lo < nnz) {
-    int i = tbd::search_last_le(pos, 0, rows, lo);      // the row that contains nonzero `lo`
+  if (w == nslots) { slot_rows[w] = rg.r1; return; }
+  int lo = rg.p0 + w * SPMM_W;
+  slot_rows[w] = tbd::search_first_ge(pos, rg.r0, rg.r1, lo);
+  if (lo < rg.p1) {
+    int i = tbd::search_last_le(pos, rg.r0, rg.r1, lo);      // the row that contains nonzero `lo`
     int s = __ldg(pos + i), e = __ldg(pos + i + 1);
     if (e - s > SPMM_LONG && lo - s < SPMM_W) {
       if constexpr (COLMAJOR) { for (int k = 0; k < K; k++) C[(size_t)k * rows + i] = T(0); }
@@ -156,12 +160,13 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
-                const T* __restrict__ B, T* __restrict__ C, int rows, int K, int nnz, int nslots,
+                const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
                 const int* __restrict__ slot_rows) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
-  const int lo = w * SPMM_W, hi = min(lo + SPMM_W, nnz);
+  const int nnz = rg.p1;
+  const int lo = rg.p0 + w * SPMM_W, hi = min(lo + SPMM_W, nnz);
   // the slot's own window of crd / vals is needed a few dependent loads from now: pull it into L2 meanwhile
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
   else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
@@ -178,7 +183,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   //   atomically into the row the pre-pass zeroed.
   int tail_e = 0;
   bool tail = false;
-  if (R0 > 0 && lo < nnz) {
+  if (R0 > rg.r0 && lo < nnz) {
     const int s = __ldg(pos + R0 - 1);
     tail_e = __ldg(pos + R0);
     tail = tail_e > lo && tail_e - s > SPMM_LONG;
@@ -219,33 +224,34 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   }
 }
 
-// Launch variants: (gathers in flight per warp, warps per CTA).  TACO_B200_SPMM_VARIANT selects one for tuning runs.
+// Launch variants: (gathers in flight per warp, warps per CTA, min CTAs per SM).  TACO_B200_SPMM_VARIANT selects one
+// for tuning runs; the default is the measured best at config C2 (profiles/).
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
-static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz, int nslots,
-                    const int* slot_rows) {
+static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
+                    const int* slot_rows, cudaStream_t st) {
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, nnz, nslots,
+  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
                                                                                  slot_rows);
 }
 
 template <typename T, int VEC, bool COLMAJOR>
-static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz) {
+static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg) {
+  const int nnz = rg.p1 - rg.p0;
   int nslots = nnz > 0 ? (nnz + SPMM_W - 1) / SPMM_W : 1;
   void* slot_rows = nullptr;
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
-  spmm_slot_rows_kernel<T, COLMAJOR><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rows, nnz, nslots, K,
+  spmm_slot_rows_kernel<T, COLMAJOR><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rg, rows, nslots, K,
                                                                                      (int*)slot_rows, C);
   static const int variant = getenv("TACO_B200_SPMM_VARIANT") ? atoi(getenv("TACO_B200_SPMM_VARIANT")) : 0;
   {
     ProfScope ps("spmm_csr");
     const int* sr = (const int*)slot_rows;
+    cudaStream_t st = stream();
     switch (variant) {
-      case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 4: spmm_go<T, VEC, COLMAJOR, 2, 4, 12>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      case 5: spmm_go<T, VEC, COLMAJOR, 2, 8, 7>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
-      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, nnz, nslots, sr); break;
+      case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
+      case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
+      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
+      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
     }
   }
   count_launch(2);
@@ -255,16 +261,16 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
 }
 
 template <typename T>
-static int spmm_launch(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz,
+static int spmm_launch(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg,
                        bool colmajor) {
   constexpr int V = 16 / sizeof(T);
   bool vec_ok = (K % V == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)C & 15) == 0);
   if (colmajor) {
-    if (vec_ok) return spmm_launch_impl<T, V, true>(pos, crd, vals, B, C, rows, K, nnz);
-    return spmm_launch_impl<T, 1, true>(pos, crd, vals, B, C, rows, K, nnz);
+    if (vec_ok) return spmm_launch_impl<T, V, true>(pos, crd, vals, B, C, rows, K, rg);
+    return spmm_launch_impl<T, 1, true>(pos, crd, vals, B, C, rows, K, rg);
   }
-  if (vec_ok) return spmm_launch_impl<T, V, false>(pos, crd, vals, B, C, rows, K, nnz);
-  return spmm_launch_impl<T, 1, false>(pos, crd, vals, B, C, rows, K, nnz);
+  if (vec_ok) return spmm_launch_impl<T, V, false>(pos, crd, vals, B, C, rows, K, rg);
+  return spmm_launch_impl<T, 1, false>(pos, crd, vals, B, C, rows, K, rg);
 }
 
 int csr_nnz(const CsrView& A, int32_t vals_size_hint, int32_t* nnz);   // spmv.cu
@@ -284,6 +290,88 @@ static int spmm_views(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B, Dens
     return fail(TACO_B200_ERR_ARG, "spmm: dimension mismatch C[%d x %d] = A[%d x %d] * B[%d x %d]", Cv->dim[0],
                 Cv->dim[1], Av->rows, Av->cols, Bv->dim[0], Bv->dim[1]);
   if (Cv->dt != Av->dt || Bv->dt != Av->dt) return fail(TACO_B200_ERR_FORMAT, "spmm: mixed component types");
+  return TACO_B200_OK;
+}
+
+// TACO_B200_PIPELINE_MIN_BYTES: smallest (result + nonzero) volume that takes the chunked path (default 64 MiB;
+// 0 forces it, a huge value disables it)
+static size_t pipeline_min_bytes() {
+  const char* e = getenv("TACO_B200_PIPELINE_MIN_BYTES");
+  return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)64 << 20);
+}
+
+// Host-operand pipeline.  When A and C live in host memory the call is PCIe-bound, so it is cut into row chunks:
+//   upload stream : pos, B (unless device resident), then crd/vals of chunk 0, 1, ...
+//   compute stream: kernel of chunk c as soon as its nonzeros have landed
+//   download stream: rows of C of chunk c as soon as its kernel is done
+// Uploads of later chunks overlap the downloads of earlier ones (PCIe is full duplex), and the kernels hide under both.
+template <typename T>
+static int spmm_compute_pipelined(const CsrView& Av, const DenseView& Bv, const DenseView& Cv, int K, int32_t nnz) {
+  const int rows = Av.rows;
+  const size_t es = sizeof(T);
+  cudaStream_t main = stream(), up = aux_stream(0), down = aux_stream(1);
+  void *dpos = nullptr, *dcrd = nullptr, *dvals = nullptr, *dC = nullptr;
+  In bin;                                           // device-resident / registered B is used in place
+  const bool b_host = classify(Bv.vals) != Mem::Device && !is_resident(Bv.vals, es * (size_t)Av.cols * K);
+  void* dB = nullptr;
+  TB_TRY(scratch_alloc(&dpos, sizeof(int) * ((size_t)rows + 1)));
+  TB_TRY(scratch_alloc(&dcrd, sizeof(int) * (size_t)nnz));
+  TB_TRY(scratch_alloc(&dvals, es * (size_t)nnz));
+  TB_TRY(scratch_alloc(&dC, es * (size_t)rows * K));
+  if (b_host) TB_TRY(scratch_alloc(&dB, es * (size_t)Av.cols * K));
+  else { TB_TRY(bin.acquire(Bv.vals, es * (size_t)Av.cols * K)); dB = (void*)bin.dptr; }
+  cudaEvent_t ready, done_all;
+  TB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  TB_CUDA(cudaEventCreateWithFlags(&done_all, cudaEventDisableTiming));
+  TB_CUDA(cudaEventRecord(ready, main));            // the pool allocations above are ordered on the compute stream
+  TB_CUDA(cudaStreamWaitEvent(up, ready, 0));
+  TB_CUDA(cudaStreamWaitEvent(down, ready, 0));
+  TB_CUDA(cudaMemcpyAsync(dpos, Av.pos, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice, up));
+  if (b_host) TB_CUDA(cudaMemcpyAsync(dB, Bv.vals, es * (size_t)Av.cols * K, cudaMemcpyHostToDevice, up));
+  // chunk boundaries: balanced by (nonzeros uploaded + result bytes downloaded)
+  const int nchunks = 16;
+  const double w_row = (double)K * es, w_nz = 4.0 + es, total = w_row * rows + w_nz * nnz;
+  int r0 = 0;
+  int rc = TACO_B200_OK;
+  for (int c = 0; c < nchunks && r0 < rows && rc == TACO_B200_OK; c++) {
+    int r1 = rows;
+    if (c < nchunks - 1) {
+      const double target = total * (c + 1) / nchunks;
+      int lo = r0 + 1, hi = rows;                   // smallest r1 with weight(r1) >= target
+      while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        if (w_row * mid + w_nz * Av.pos[mid] >= target) hi = mid; else lo = mid + 1;
+      }
+      r1 = lo;
+    }
+    const int p0 = Av.pos[r0], p1 = Av.pos[r1];
+    cudaEvent_t e_up, e_done;
+    TB_CUDA(cudaEventCreateWithFlags(&e_up, cudaEventDisableTiming));
+    TB_CUDA(cudaEventCreateWithFlags(&e_done, cudaEventDisableTiming));
+    if (p1 > p0) {
+      TB_CUDA(cudaMemcpyAsync((int*)dcrd + p0, Av.crd + p0, sizeof(int) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, up));
+      TB_CUDA(cudaMemcpyAsync((T*)dvals + p0, (const T*)Av.vals + p0, es * (size_t)(p1 - p0), cudaMemcpyHostToDevice, up));
+    }
+    TB_CUDA(cudaEventRecord(e_up, up));
+    TB_CUDA(cudaStreamWaitEvent(main, e_up, 0));
+    rc = spmm_launch<T>((const int*)dpos, (const int*)dcrd, (const T*)dvals, (const T*)dB, (T*)dC, rows, K,
+                        SpmmRange{r0, r1, p0, p1}, false);
+    TB_CUDA(cudaEventRecord(e_done, main));
+    TB_CUDA(cudaStreamWaitEvent(down, e_done, 0));
+    TB_CUDA(cudaMemcpyAsync((T*)Cv.vals + (size_t)r0 * K, (const T*)dC + (size_t)r0 * K, es * (size_t)(r1 - r0) * K,
+                            cudaMemcpyDeviceToHost, down));
+    cudaEventDestroy(e_up);
+    cudaEventDestroy(e_done);
+    r0 = r1;
+  }
+  TB_CUDA(cudaEventRecord(done_all, down));
+  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));  // frees below (and the caller's sync) are ordered after the downloads
+  cudaEventDestroy(ready);
+  cudaEventDestroy(done_all);
+  scratch_free(dpos); scratch_free(dcrd); scratch_free(dvals); scratch_free(dC);
+  if (b_host) scratch_free(dB);
+  TB_TRY(rc);
+  TB_CUDA(cudaStreamSynchronize(main));
   return TACO_B200_OK;
 }
 
@@ -310,6 +398,14 @@ int taco_b200_spmm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B)
   if (nnz < 0 || nnz > INT32_MAX - 65536) return fail(TACO_B200_ERR_ARG, "spmm: bad nnz %d", nnz);
   const int K = Bv.dim[1];
   size_t es = dsize(Av.dt);
+  if (!Cv.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  // host-described A and host C, large enough for chunking to pay: overlap upload / kernels / download
+  if (!cm && Av.rows > 0 && K > 0 && nnz > 0 && classify(Av.pos) != Mem::Device && classify(Av.crd) != Mem::Device &&
+      classify(Av.vals) != Mem::Device && classify(Cv.vals) != Mem::Device &&
+      es * (size_t)Av.rows * K + (4 + es) * (size_t)nnz >= pipeline_min_bytes()) {
+    if (Av.dt == DType::F32) return spmm_compute_pipelined<float>(Av, Bv, Cv, K, nnz);
+    return spmm_compute_pipelined<double>(Av, Bv, Cv, K, nnz);
+  }
   In pos, crd, vals, bin; Out cout;
   TB_TRY(pos.acquire(Av.pos, sizeof(int32_t) * ((size_t)Av.rows + 1)));
   TB_TRY(crd.acquire(Av.crd ? (void*)Av.crd : (void*)Av.pos, sizeof(int32_t) * (size_t)nnz));
@@ -317,12 +413,13 @@ int taco_b200_spmm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B)
   TB_TRY(bin.acquire(Bv.vals, es * (size_t)Av.cols * K));
   TB_TRY(cout.acquire(Cv.vals, es * (size_t)Av.rows * K));
   if (Av.rows > 0 && K > 0) {
+    const SpmmRange all{0, Av.rows, 0, nnz};
     if (Av.dt == DType::F32)
       TB_TRY(spmm_launch<float>(pos.as<int>(), crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(),
-                                Av.rows, K, nnz, cm));
+                                Av.rows, K, all, cm));
     else
       TB_TRY(spmm_launch<double>(pos.as<int>(), crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(),
-                                 Av.rows, K, nnz, cm));
+                                 Av.rows, K, all, cm));
   }
   TB_TRY(cout.commit());
   return finish_call();

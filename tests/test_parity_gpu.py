@@ -177,6 +177,36 @@ def test_oracle_spmm(space, K, dtype):
     assert hubs > 0, "the R-MAT case is meant to exercise the hub-row path"
 
 
+@pytest.mark.parametrize("K,dtype", [(128, "float32"), (48, "float64")])
+def test_oracle_spmm_host_pipeline(K, dtype, monkeypatch):
+    # host operands through the chunked upload / compute / download pipeline (forced for this small case); pinned and
+    # pageable buffers, plus B registered resident
+    monkeypatch.setenv("TACO_B200_PIPELINE_MIN_BYTES", "0")
+    w = synth.make("spmm", None, scale=13, K=K, dtype=dtype)
+    C = G.run("spmm", w)
+    _spmm_check(w, C, dtype)
+    wp = {}
+    for k, v in w.items():
+        if k == "dims":
+            wp[k] = v
+        else:
+            a = tb.pinned_empty(v.shape, v.dtype)
+            a[...] = v
+            wp[k] = a
+    C = G.run("spmm", wp)
+    _spmm_check(w, C, dtype)
+    from taco_b200 import _lib
+    _lib.check(_lib.lib.taco_b200_make_resident(wp["B"].ctypes.data, wp["B"].nbytes))
+    try:
+        C = G.run("spmm", wp)
+        _spmm_check(w, C, dtype)
+    finally:
+        _lib.lib.taco_b200_invalidate(wp["B"].ctypes.data)
+        for k, v in wp.items():
+            if k != "dims":
+                tb.pinned_free(v)
+
+
 @pytest.mark.parametrize("K,dtype", [(64, "float32"), (64, "float64"), (20, "float32"), (5, "float64"), (256, "float32")])
 def test_oracle_sddmm(K, dtype):
     w = synth.make("sddmm", None, n=30_011, deg=20, K=K, dtype=dtype)
