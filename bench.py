@@ -38,7 +38,7 @@ FLOPS = {   # per step, as the reference counts them
     "spgemm": lambda s: 2.0 * s["products"],
 }
 DOMINANT = {"spmv": "spmv_csr", "spmm": "spmm_csr", "sddmm": "sddmm_csr", "mttkrp": "mttkrp_csf",
-            "spadd": "spadd_numeric", "spgemm": "spgemm_symbolic"}
+            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric"}
 
 
 def algorithmic_bytes(wl, s):
@@ -54,8 +54,8 @@ def algorithmic_bytes(wl, s):
         return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * s["R"] * (s["Kd"] + s["Ld"] + s["I"])
     if wl == "spadd":      # numeric phase: both operands + result values, all pos arrays
         return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * e + 12 * (s["rows"] + 1)
-    if wl == "spgemm":     # symbolic phase (two passes): A structure + gathered B rows + result crd
-        return 2 * (4 * s["nnzA"] + 8 * s["rows"] + 4 * s["products"]) + 4 * s["nnzC"]
+    if wl == "spgemm":     # fill pass (sort + compress): A, the gathered B rows (crd + vals), the result, all pos arrays
+        return (4 + e) * (s["nnzA"] + s["products"] + s["nnzC"]) + 12 * (s["rows"] + 1)
     raise KeyError(wl)
 
 
@@ -111,6 +111,17 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
                 "reasons": reasons, "samples": len(self.samples)}
+
+
+def ncu_traffic(wl, kernel_name):
+    """dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture (profiles/traffic.json,
+    written by tools/make_profiles.py from one `ncu --set full` run of this same command)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(wl)
+        return (t["dram_bytes_per_launch"], t["round"]) if t else (None, None)
+    except Exception:
+        return None, None
 
 
 def measured_peak():
@@ -433,7 +444,9 @@ def main():
                            "sharding": "row shard per rank, dense operand replicated, no collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": DOMINANT[wl], "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                             "frac": (ach / peak) if ach else None, "traffic": ncu_traffic(wl, DOMINANT[wl])[0],
+                             "traffic_source": f"ncu --set full, profiles/{ncu_traffic(wl, DOMINANT[wl])[1]}_{wl}.md (full-size config)",
+                             "peak_source": peak_src,
                              "kernel_ms": kern_ms, "algorithmic_bytes": algorithmic_bytes(wl, stats)},
                 "cpu_baseline": cpu}
         print(json.dumps(line))
