@@ -166,6 +166,11 @@ int   taco_b200_module_num_args(const taco_b200_module_t* m);
 int   taco_b200_module_call_packed(taco_b200_module_t* m, const char* name, void** args);
 void* taco_b200_module_get_func_ptr(taco_b200_module_t* m, const char* name);  /* like Module::getFuncPtr */
 void  taco_b200_module_close(taco_b200_module_t* m);
+/* C source for the reference's own plug point TensorBase::compileSource(std::string) (src/tensor.cpp:905-930) and the
+ * CLI's -read-source= (tools/taco.cpp:1212-1259): defines assemble/compute/evaluate with the signatures taco's
+ * generated shims call (src/codegen/codegen_c.cpp:591-628) and forwards them to this library (dlopen of
+ * $TACO_B200_LIB, else "libtaco_b200.so").  With it an UNMODIFIED taco runs the statement on the GPU path. */
+const char* taco_b200_module_stub_source(taco_b200_module_t* m);
 
 /* _shim_ entry points with the reference's exact shim signature (codegen_cuda.cpp:1500-1540). */
 int _shim_taco_b200_spmv_assemble(void** p);   int _shim_taco_b200_spmv_compute(void** p);   int _shim_taco_b200_spmv_evaluate(void** p);

@@ -123,6 +123,7 @@ static void parse_formats(const char* formats, std::map<std::string, std::pair<s
 struct taco_b200_module {
   const tb::Family* fam;
   std::string key;
+  std::string stub;      // lazily built C source for TensorBase::compileSource()
 };
 
 using namespace tb;
@@ -202,6 +203,53 @@ int taco_b200_module_call_packed(taco_b200_module_t* m, const char* name, void**
 }
 
 void taco_b200_module_close(taco_b200_module_t*) { /* modules are cached for the process lifetime */ }
+
+// C source that the UNMODIFIED reference can take through its own plug point TensorBase::compileSource(std::string)
+// (/root/reference/src/tensor.cpp:905-930; CLI: -read-source, tools/taco.cpp:1212-1259): it defines `assemble`,
+// `compute` and `evaluate` with the signatures taco's generated shims call (CodeGen_C::generateShim,
+// src/codegen/codegen_c.cpp:591-628) and forwards them to this library, located through dlopen
+// ($TACO_B200_LIB, else "libtaco_b200.so" on the loader path).  taco compiles it with its normal `cc` JIT -- no nvcc, no
+// change to taco.
+const char* taco_b200_module_stub_source(taco_b200_module_t* m) {
+  if (!m) { fail(TACO_B200_ERR_ARG, "module_stub_source: NULL module"); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_mod_mu);
+  if (!m->stub.empty()) return m->stub.c_str();
+  const int n = m->fam->nargs;
+  std::string params, args, types;
+  for (int a = 0; a < n; a++) {
+    params += std::string(a ? ", " : "") + "taco_tensor_t* t" + std::to_string(a);
+    args += std::string(a ? ", " : "") + "t" + std::to_string(a);
+    types += std::string(a ? ", " : "") + "taco_tensor_t*";
+  }
+  std::string src =
+      "// generated by libtaco_b200 (taco_b200_module_stub_source): forwards taco's kernel entry points to the GPU path\n"
+      "#include <stdint.h>\n#include <stdio.h>\n#include <stdlib.h>\n#include <dlfcn.h>\n"
+      "#ifndef TACO_TENSOR_T_DEFINED\n#define TACO_TENSOR_T_DEFINED\n"
+      "typedef enum { taco_mode_dense, taco_mode_sparse } taco_mode_t;\n"
+      "typedef struct taco_tensor_t {\n  int32_t order; int32_t* dimensions; int32_t csize; int32_t* mode_ordering;\n"
+      "  taco_mode_t* mode_types; uint8_t*** indices; uint8_t* vals; uint8_t* fill_value; int32_t vals_size;\n"
+      "} taco_tensor_t;\n#endif\n"
+      "static void* taco_b200_sym(const char* name) {\n"
+      "  static void* lib = 0;\n"
+      "  if (!lib) {\n"
+      "    const char* path = getenv(\"TACO_B200_LIB\");\n"
+      "    lib = dlopen(path ? path : \"libtaco_b200.so\", RTLD_NOW | RTLD_GLOBAL);\n"
+      "    if (!lib) { fprintf(stderr, \"taco_b200: %s\\n\", dlerror()); abort(); }\n"
+      "  }\n"
+      "  void* f = dlsym(lib, name);\n"
+      "  if (!f) { fprintf(stderr, \"taco_b200: missing symbol %s\\n\", name); abort(); }\n"
+      "  return f;\n}\n"
+      "static int taco_b200_report(int rc) {\n"
+      "  if (rc) fprintf(stderr, \"taco_b200: %s\\n\", ((const char* (*)(void))taco_b200_sym(\"taco_b200_last_error\"))());\n"
+      "  return rc;\n}\n";
+  for (const char* ph : {"assemble", "compute", "evaluate"}) {
+    src += std::string("int ") + ph + "(" + params + ") {\n  typedef int (*fn_t)(" + types + ");\n  static fn_t fn = 0;\n" +
+           "  if (!fn) fn = (fn_t)taco_b200_sym(\"taco_b200_" + m->fam->name + "_" + ph + "\");\n" +
+           "  return taco_b200_report(fn(" + args + "));\n}\n";
+  }
+  m->stub = src;
+  return m->stub.c_str();
+}
 
 // ---- _shim_ entry points (positional void** pack, /root/reference/src/codegen/codegen_cuda.cpp:1500-1540) -------
 #define TB_SHIM3(n, ph)                                                                                     \

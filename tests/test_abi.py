@@ -110,3 +110,25 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(tb.TacoError) as ei:
         k(y, A, x)
     assert ei.value.code == 1 and "no CPU fallback" in str(ei.value)
+
+
+def test_stub_source_for_compileSource_is_valid_c(tmp_path):
+    """taco_b200_module_stub_source: the text handed to the reference's TensorBase::compileSource must define
+    assemble/compute/evaluate with one taco_tensor_t* per tensor and compile as plain C (the reference JITs it with cc)."""
+    import ctypes
+    import subprocess
+    from taco_b200 import _lib
+    _lib.lib.taco_b200_module_stub_source.restype = ctypes.c_char_p
+    _lib.lib.taco_b200_module_stub_source.argtypes = [ctypes.c_void_p]
+    for expr, fm, fam, n in [("y(i) = A(i,j) * x(j)", "y:d,A:ds,x:d", "spmv", 3),
+                             ("A(i,j) = B(i,k,l) * C(k,j) * D(l,j)", "A:dd,B:sss,C:dd,D:dd", "mttkrp", 4)]:
+        m = _lib.lib.taco_b200_module_open(expr.encode(), fm.encode(), b"f64")
+        assert m
+        src = _lib.lib.taco_b200_module_stub_source(m).decode()
+        for ph in ("assemble", "compute", "evaluate"):
+            assert f"int {ph}(" + ", ".join(f"taco_tensor_t* t{a}" for a in range(n)) + ")" in src
+            assert f"taco_b200_{fam}_{ph}" in src
+        f = tmp_path / f"{fam}.c"
+        f.write_text(src)
+        subprocess.check_call(["/usr/bin/gcc", "-std=gnu99", "-Wall", "-Werror", "-shared", "-fPIC", str(f), "-o",
+                               str(tmp_path / f"{fam}.so")])

@@ -375,3 +375,16 @@ def test_partition_pos_device_matches_host():
     assert host.tolist() == dev.tolist()
     sizes = np.diff(w["A_pos"][host])
     assert sizes.max() - sizes.min() <= np.diff(w["A_pos"]).max()      # nnz-balanced up to one row
+
+
+# ---------------------------------------------------------------------------------------------------------
+# (e) drop-in: an ordinary taco C++ program on the UNMODIFIED reference library, kernels forwarded to libtaco_b200
+# ---------------------------------------------------------------------------------------------------------
+def test_dropin_demo_through_unmodified_reference():
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe = os.path.join(root, "oracle", "_ref", "taco_dropin_demo")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref (the compiled reference) was not shipped with this snapshot")
+    r = subprocess.run([exe, tb.LIB_PATH], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
