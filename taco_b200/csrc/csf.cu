@@ -181,7 +181,7 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
 
 struct MkSlice { int f0, f1, l0, l1, row, zlo; };   // fibers, leaves, row of A, first row to zero before `row`
 
-template <typename T, int U, int WARPS, int MINB>
+template <typename T, int U, int WARPS, int MINB, bool SINGLE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
@@ -238,7 +238,7 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
           for (int r = m.row + 1; r < Idim; r++)
             for (int j = lane; j < R; j += 32) A[(size_t)r * R + j] = T(0);
       }
-      for (int j0 = 0; j0 < R; j0 += 32) {
+      for (int j0 = 0; j0 < (SINGLE ? 1 : R); j0 += 32) {      // SINGLE: R <= 32, one pass over the slice's leaves
         const bool active = j0 + lane < R;
         const T* Cj = C + (active ? j0 + lane : 0);
         const T* Dj = D + (active ? j0 + lane : 0);
@@ -326,9 +326,18 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
 
 template <typename T, int U, int WARPS, int MINB>
 static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices) {
-  mttkrp_csf_kernel<T, U, WARPS, MINB><<<(nslots + WARPS - 1) / WARPS, WARPS * 32, 0, stream()>>>(
-      cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D,
-      A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
+  const dim3 grid((nslots + WARPS - 1) / WARPS);
+  // The single-pass specialisation (R <= 32) spills less but measures SLOWER at C4 (23.1 vs 16.7 ms, same box, A/B):
+  // ptxas unrolls the leaf loop of the general version four deep, which is what keeps HBM at 98 % of its peak.
+  static const bool single = getenv("TACO_B200_MTTKRP_SINGLE") != nullptr;
+  if (R <= 32 && single)
+    mttkrp_csf_kernel<T, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(
+        cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
+  else
+    mttkrp_csf_kernel<T, U, WARPS, MINB, false><<<grid, WARPS * 32, 0, stream()>>>(
+        cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
 }
 
 template <typename T>
