@@ -15,6 +15,7 @@
 // SpGEMM = sorted set of reachable columns per row, entries that sum to zero are kept.
 // SpGEMM values are accumulated in the reference's order (A-row order, then B-row order) -> bit-identical.
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -72,10 +73,10 @@ spadd_fill_kernel(int n, const int* __restrict__ Apos, const int* __restrict__ A
 // are moved between HBM and shared memory with fully coalesced accesses and the per-row two-finger merges run out of
 // shared memory.  MODE: 0 = count (symbolic), 1 = crd only (assemble), 2 = vals only (compute), 3 = crd + vals
 // (evaluate).  A row block whose segments exceed the staging capacity takes the direct path below.
-constexpr int SPADD_THREADS = 256;     // staging threads; the first rb of them also merge one row each
-constexpr int SPADD_CAP = 2048;       // staged entries per operand per CTA
-
-template <typename T, int MODE>
+// SPADD_CAP = staged entries per operand per CTA, SPADD_THREADS = staging threads (the first rb of them also merge one
+// row each).  Small CTAs (512 entries, 64 threads, 24 KB for the fused fp64 fill) keep 9 CTAs per SM in different phases
+// (load / merge / store), which is what hides the phase latencies.
+template <typename T, int MODE, int SPADD_CAP, int SPADD_THREADS>
 __global__ void __launch_bounds__(SPADD_THREADS)
 spadd_block_kernel(int n, int rb, const int* __restrict__ Apos, const int* __restrict__ Acrd, const T* __restrict__ Av,
                    const int* __restrict__ Bpos, const int* __restrict__ Bcrd, const T* __restrict__ Bv,
@@ -155,26 +156,41 @@ spadd_block_kernel(int n, int rb, const int* __restrict__ Apos, const int* __res
   }
 }
 
-template <typename T, int MODE>
-static int spadd_block_launch(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
-                              const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
+template <typename T, int MODE, int CAP, int THREADS>
+static int spadd_block_launch_cfg(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
+                                  const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
   constexpr bool CRD = (MODE & 1) != 0, VALS = (MODE & 2) != 0;
-  const size_t smem = sizeof(int) * SPADD_CAP * (2 + (CRD ? 2 : 0)) + (VALS ? sizeof(T) * SPADD_CAP * 4 : 0);
+  const size_t smem = sizeof(int) * CAP * (2 + (CRD ? 2 : 0)) + (VALS ? sizeof(T) * CAP * 4 : 0);
   static bool configured = false;
   if (!configured) {
-    TB_CUDA(cudaFuncSetAttribute(spadd_block_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TB_CUDA(cudaFuncSetAttribute(spadd_block_kernel<T, MODE, CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  // rows per CTA: as many as keep an average segment at ~70% of the staging capacity
+  // rows per CTA: as many as keep an average segment at ~70% of the staging capacity (at most one per thread)
   const double avg = (double)(nnzA > nnzB ? nnzA : nnzB) / (n > 0 ? n : 1);
-  int rb = avg > 0 ? (int)(0.7 * SPADD_CAP / avg) : SPADD_THREADS;
-  rb = rb > 128 ? 128 : (rb < 4 ? 4 : rb);
+  int rb = avg > 0 ? (int)(0.7 * CAP / avg) : THREADS;
+  rb = rb > THREADS ? THREADS : (rb < 4 ? 4 : rb);
   const int grid = (n + rb - 1) / rb;
-  spadd_block_kernel<T, MODE><<<grid, SPADD_THREADS, smem, stream()>>>(n, rb, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd, Cv,
-                                                                       counts);
+  spadd_block_kernel<T, MODE, CAP, THREADS><<<grid, THREADS, smem, stream()>>>(n, rb, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd,
+                                                                               Cv, counts);
   count_launch(1);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
+}
+
+template <typename T, int MODE>
+static int spadd_block_launch(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
+                              const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
+  static const int variant = getenv("TACO_B200_SPADD_VARIANT") ? atoi(getenv("TACO_B200_SPADD_VARIANT")) : 0;
+#define TB_SPADD_ARGS n, nnzA, nnzB, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd, Cv, counts
+  switch (variant) {
+    case 1: return spadd_block_launch_cfg<T, MODE, 2048, 256>(TB_SPADD_ARGS);
+    case 2: return spadd_block_launch_cfg<T, MODE, 1024, 128>(TB_SPADD_ARGS);
+    case 3: return spadd_block_launch_cfg<T, MODE, 256, 32>(TB_SPADD_ARGS);
+    case 4: return spadd_block_launch_cfg<T, MODE, 512, 128>(TB_SPADD_ARGS);
+    default: return spadd_block_launch_cfg<T, MODE, 512, 64>(TB_SPADD_ARGS);
+  }
+#undef TB_SPADD_ARGS
 }
 
 // =========================================================================================================
@@ -216,7 +232,7 @@ spgemm_bound_kernel(int n, const int* __restrict__ Apos, const int* __restrict__
 // Expansion shared by the count and the fill kernel: visit every product (t, k, a*b) of row i in generation order
 // t = 0,1,.. (A entries ascending, then the B row in order -- the order of the reference's workspace loop, Appendix
 // A.5).  G lanes share one A entry, so short B rows still fill the warp.
-template <typename T, bool VALS, typename F>
+template <typename T, bool VALS, bool UNIFORM, typename F>
 __device__ __forceinline__ int spgemm_expand(int i, int G, const int* __restrict__ Apos, const int* __restrict__ Acrd,
                                              const T* __restrict__ Av, const int* __restrict__ Bpos,
                                              const int* __restrict__ Bcrd, const T* __restrict__ Bv, F&& visit) {
@@ -248,11 +264,22 @@ __device__ __forceinline__ int spgemm_expand(int i, int G, const int* __restrict
       if (q0 + grp >= cnt) qlen = 0;
       const int qoff = __shfl_sync(0xffffffffu, off, q);
       const T qa = __shfl_sync(0xffffffffu, av, q);
-      for (int l = gl; l < qlen; l += G) {
-        const int k = __ldg(Bcrd + qbs + l);
-        T prod = T(0);
-        if (VALS) prod = qa * __ldg(Bv + qbs + l);
-        visit(qoff + l, k, prod);
+      if (UNIFORM) {
+        // warp-uniform trip count (visit() uses warp barriers): lanes past the end of their B row pass valid=false
+        const int iters = (__reduce_max_sync(0xffffffffu, qlen) + G - 1) / G;
+        for (int it = 0; it < iters; it++) {
+          const int l = gl + it * G;
+          const bool valid = l < qlen;
+          const int k = valid ? __ldg(Bcrd + qbs + l) : -1;
+          visit(qoff + l, k, T(0), valid);
+        }
+      } else {
+        for (int l = gl; l < qlen; l += G) {
+          const int k = __ldg(Bcrd + qbs + l);
+          T prod = T(0);
+          if (VALS) prod = qa * __ldg(Bv + qbs + l);
+          visit(qoff + l, k, prod, true);
+        }
       }
     }
     total += __shfl_sync(0xffffffffu, incl, 31);
@@ -277,17 +304,18 @@ spgemm_count_warp_kernel(const int* __restrict__ rows_list, int nrows_bin, int G
   __syncwarp();
   const int i = __ldg(rows_list + ridx);
   int mine = 0;
-  spgemm_expand<float, false>(i, G, Apos, Acrd, (const float*)nullptr, Bpos, Bcrd, (const float*)nullptr,
-                              [&](int, int k, float) {
-                                unsigned h = ((unsigned)k * 2654435761u) >> 7;
-                                while (true) {
-                                  h &= SLOTS - 1;
-                                  const int old = atomicCAS(table + h, -1, k);
-                                  if (old == -1) { mine++; break; }
-                                  if (old == k) break;
-                                  h++;
-                                }
-                              });
+  // (A barrier-based insert without shared-memory atomics was measured slower: 0.99 vs 0.70 ms at C5.)
+  spgemm_expand<float, false, false>(i, G, Apos, Acrd, (const float*)nullptr, Bpos, Bcrd, (const float*)nullptr,
+                                     [&](int, int k, float, bool) {
+                                       unsigned h = ((unsigned)k * 2654435761u) >> 7;
+                                       while (true) {
+                                         h &= SLOTS - 1;
+                                         const int old = atomicCAS(table + h, -1, k);
+                                         if (old == -1) { mine++; break; }
+                                         if (old == k) break;
+                                         h++;
+                                       }
+                                     });
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
   if (lane == 0) counts[i] = mine;
@@ -311,9 +339,11 @@ spgemm_fill_warp_kernel(const int* __restrict__ rows_list, int nrows_bin, int G,
   KEY* skey = skey_all[wid];
   T* sval = sval_all[wid];
   const int i = __ldg(rows_list + ridx);
-  const int total = spgemm_expand<T, VALS>(i, G, Apos, Acrd, Av, Bpos, Bcrd, Bv, [&](int t, int k, T prod) {
-    skey[t] = ((KEY)(unsigned)k << 8) | (KEY)t;
-    if (VALS) sval[t] = prod;
+  const int total = spgemm_expand<T, VALS, false>(i, G, Apos, Acrd, Av, Bpos, Bcrd, Bv, [&](int t, int k, T prod, bool valid) {
+    if (valid) {
+      skey[t] = ((KEY)(unsigned)k << 8) | (KEY)t;
+      if (VALS) sval[t] = prod;
+    }
   });
   for (int t = total + lane; t < N; t += 32) skey[t] = ~(KEY)0;
   __syncwarp();
