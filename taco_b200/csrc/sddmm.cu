@@ -131,8 +131,8 @@ __device__ __forceinline__ void sddmm_ld_keep(const T* p, T (&v)[VEC], uint64_t 
     v[0] = __ldg(p);
 }
 
-template <typename T, int VEC, int G, int UREQ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename T, int VEC, int G, int UREQ, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 sddmm_csr_chunk_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ bvals,
                        const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ avals, int K, int nnz, int nslots,
                        const int* __restrict__ slot_first) {
@@ -206,11 +206,13 @@ template <typename T, int VEC, int G>
 static void sddmm_chunk_go(int variant, int grid8, int grid4, const int* pos, const int* crd, const T* bvals, const T* C, const T* D,
                            T* avals, int K, int nnz, int nslots, const int* first) {
   switch (variant) {
-    case 1: sddmm_csr_chunk_kernel<T, VEC, G, 4, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    case 2: sddmm_csr_chunk_kernel<T, VEC, G, 8, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    case 3: sddmm_csr_chunk_kernel<T, VEC, G, 4, 4><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    case 4: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
-    default: sddmm_csr_chunk_kernel<T, VEC, G, 2, 8><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 1: sddmm_csr_chunk_kernel<T, VEC, G, 2, 8, 6><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 2: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8, 3><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 3: sddmm_csr_chunk_kernel<T, VEC, G, 16, 8, 2><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 4: sddmm_csr_chunk_kernel<T, VEC, G, 16, 8, 3><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 5: sddmm_csr_chunk_kernel<T, VEC, G, 8, 4, 8><<<grid4, 128, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    case 6: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8, 5><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
+    default: sddmm_csr_chunk_kernel<T, VEC, G, 8, 8, 4><<<grid8, 256, 0, stream()>>>(pos, crd, bvals, C, D, avals, K, nnz, nslots, first); break;
   }
 }
 

@@ -22,6 +22,8 @@
 //              most two tiles (<= 2048 nonzeros always do) therefore stay bit-exact; longer rows are deterministic and
 //              within 1e-12 of the sequential sum.
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*(cols + rows).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tb {
@@ -88,8 +90,8 @@ __device__ __forceinline__ T spmv_block_sum(const T* prod, int a, int b, T* red)
   return tot;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(SPMV_THREADS)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(SPMV_THREADS, MINB)
 spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
                 int* __restrict__ flag, int epoch) {
@@ -229,11 +231,17 @@ static int spmv_launch(const CsrView& A, const In& pos, const In& crd, const In&
     TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
     g_spmv_epoch = 1;
   }
+  static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
   {
     ProfScope ps("spmv_csr");
-    spmv_csr_kernel<T><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<T>(), x.as<T>(),
-                                                              y.as<T>(), A.rows, nnz, (T*)g_spmv_partial, g_spmv_flag,
-                                                              g_spmv_epoch);
+#define TB_SPMV_GO(MINB)                                                                                               \
+  spmv_csr_kernel<T, MINB><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<T>(), x.as<T>(), \
+                                                                  y.as<T>(), A.rows, nnz, (T*)g_spmv_partial, g_spmv_flag, \
+                                                                  g_spmv_epoch)
+    if (variant == 1) TB_SPMV_GO(8);
+    else if (variant == 2) TB_SPMV_GO(7);
+    else TB_SPMV_GO(6);
+#undef TB_SPMV_GO
   }
   count_launch(1);
   TB_CUDA(cudaGetLastError());
