@@ -52,8 +52,8 @@ def algorithmic_bytes(wl, s):
         return s["nnz"] * (4 + 2 * e) + 4 * (s["rows"] + 1) + e * s["K"] * (s["cols"] + s["rows"])
     if wl == "mttkrp":
         return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * s["R"] * (s["Kd"] + s["Ld"] + s["I"])
-    if wl == "spadd":      # numeric phase: both operands + result values, all pos arrays
-        return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * e + 12 * (s["rows"] + 1)
+    if wl == "spadd":      # fused union kernel: both operands (crd + vals) read, result crd + vals written, all pos arrays
+        return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * (4 + e) + 12 * (s["rows"] + 1)
     if wl == "spgemm":     # fill pass (sort + compress): A, the gathered B rows (crd + vals), the result, all pos arrays
         return (4 + e) * (s["nnzA"] + s["products"] + s["nnzC"]) + 12 * (s["rows"] + 1)
     raise KeyError(wl)

@@ -156,6 +156,285 @@ spadd_block_kernel(int n, int rb, const int* __restrict__ Apos, const int* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Element-parallel union kernel (default).  The two-finger merge above is serial per row; here every stored entry of
+// the row block is one unit of work:
+//   entry a of A(i,:)  ->  lb = #{entries of B(i,:) with column < j_a}   (binary search in the staged row of B)
+//   entry b of B(i,:)  ->  ub = #{entries of A(i,:) with column <= j_b}; b is a DUPLICATE if A(i,:) holds j_b
+// With A and B flattened over the row block, a's position in the union with duplicates is q_a + lb and the number of
+// duplicates in front of any entry equals the number of MATCHED A entries in front of it -- an exclusive scan M over
+// A's match flags -- so   final(a) = q_a + lb - M[q_a],   final(b) = q_b + ub - M[ub]   (duplicates dropped).
+// The result is the reference's merge-lattice union (ascending columns, value a+b / a / b, explicit zeros kept),
+// produced with coalesced loads, a CTA scan and coalesced stores.  MODE 0..3 as above; MODE 4 = one pass: tiles take
+// tickets, publish their result count and obtain their offset in C by decoupled look-back, so pos, crd and vals are
+// written by a single kernel that reads A and B exactly once (used by `evaluate` when the result arrays may be
+// allocated at their upper bound nnzA + nnzB).
+constexpr unsigned long long SPADD_AGG = 1ull << 32, SPADD_INCL = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// exclusive offset of `tile` from the per-tile states (warp 0 calls this; every lane returns the same value)
+__device__ __forceinline__ int spadd_look_back(const unsigned long long* state, int tile, int lane) {
+  int excl = 0;
+  for (int base = tile - 1; base >= 0; base -= 32) {
+    const int p = base - lane;
+    unsigned long long v = SPADD_INCL;               // virtual tiles in front of tile 0: inclusive prefix 0
+    if (p >= 0) {
+      do { v = ld_relaxed_u64(state + p); } while ((v >> 32) == 0);
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) == 2);
+    const int first = incl ? __ffs(incl) - 1 : 31;    // nearest predecessor that already knows its inclusive prefix
+    int val = lane <= first ? (int)(unsigned)v : 0;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+    excl += val;
+    if (incl) break;
+  }
+  return excl;
+}
+
+template <typename T, int MODE, int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+spadd_union_kernel(int n, int rb, const int* __restrict__ Apos, const int* __restrict__ Acrd, const T* __restrict__ Av,
+                   const int* __restrict__ Bpos, const int* __restrict__ Bcrd, const T* __restrict__ Bv,
+                   int* __restrict__ Cpos, int* __restrict__ Ccrd, T* __restrict__ Cv, int* __restrict__ counts,
+                   unsigned long long* __restrict__ tile_state, int* __restrict__ ticket) {
+  constexpr int E = CAP / THREADS;
+  static_assert(E == 4 && CAP == 4 * THREADS, "the CTA scan reads one int4 per thread");
+  constexpr bool COUNT = MODE == 0, ONEPASS = MODE == 4;
+  constexpr bool CRD = MODE == 1 || MODE == 3 || ONEPASS, VALS = MODE == 2 || MODE == 3 || ONEPASS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* sF = (int*)smem_raw;                          // [CAP + 4] match flags of A -> exclusive scan (+ total)
+  int* sAc = sF + CAP + 4;                           // [CAP]
+  int* sBc = sAc + CAP;                              // [CAP]
+  int* sAp = sBc + CAP;                              // [THREADS + 1] row starts of A relative to the block
+  int* sBp = sAp + THREADS + 1;                      // [THREADS + 1]
+  int* sCc = sBp + THREADS + 1 + ((2 * THREADS + 2) & 1);               // [2 CAP] if CRD (kept 8-byte aligned)
+  unsigned short* sRa = (unsigned short*)(sCc + (CRD ? 2 * CAP : 0));  // [CAP] row of each A entry
+  unsigned short* sRb = sRa + CAP;                                     // [CAP]
+  T* sBv = (T*)(sRb + CAP);                          // [CAP] if VALS
+  T* sCv = sBv + (VALS ? CAP : 0);                   // [2 CAP] if VALS
+  __shared__ int s_tile, s_c0, s_warp[THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int tile = blockIdx.x;
+  if (ONEPASS) {
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    tile = s_tile;
+  }
+  const int r0 = tile * rb, r1 = min(r0 + rb, n), nr = r1 - r0;
+  if (COUNT && tile == gridDim.x - 1 && tid == 0) counts[n] = 0;
+  const int a0 = __ldg(Apos + r0), a1 = __ldg(Apos + r1), b0 = __ldg(Bpos + r0), b1 = __ldg(Bpos + r1);
+  const int nA = a1 - a0, nB = b1 - b0;
+  const bool staged = nA <= CAP && nB <= CAP;
+  int my_as = 0, my_ae = 0, my_bs = 0, my_be = 0;
+  if (tid < nr) {
+    my_as = __ldg(Apos + r0 + tid) - a0; my_ae = __ldg(Apos + r0 + tid + 1) - a0;
+    my_bs = __ldg(Bpos + r0 + tid) - b0; my_be = __ldg(Bpos + r0 + tid + 1) - b0;
+  }
+  if (staged) {
+    // ---- stage: crd of both operands (and B's values) in shared memory, A's values in registers ------------------
+    int ja[E], jb[E];
+    T va[E], vb[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int q = tid + k * THREADS;
+      ja[k] = 0; jb[k] = 0; va[k] = T(0); vb[k] = T(0);
+      if (q < nA) { ja[k] = tbd::ldg_stream_i32(Acrd + a0 + q); if (VALS) va[k] = __ldg(Av + a0 + q); }
+      if (q < nB) { jb[k] = tbd::ldg_stream_i32(Bcrd + b0 + q); if (VALS) vb[k] = __ldg(Bv + b0 + q); }
+    }
+    if (tid < nr) {
+      sAp[tid] = my_as; sBp[tid] = my_bs;
+      if (tid == nr - 1) { sAp[nr] = my_ae; sBp[nr] = my_be; }
+      for (int q = my_as; q < my_ae; q++) sRa[q] = (unsigned short)tid;
+      if (!COUNT) for (int q = my_bs; q < my_be; q++) sRb[q] = (unsigned short)tid;
+    }
+    if (COUNT) { if (tid < nr) sF[tid] = 0; }
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int q = tid + k * THREADS;
+      if (q < nA) sAc[q] = ja[k];
+      if (q < nB) { sBc[q] = jb[k]; if (VALS) sBv[q] = vb[k]; }
+    }
+    __syncthreads();
+    // ---- A entries: rank among the entries of the same row of B, match flag ---------------------------------------
+    int lbA[E];
+    bool mA[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int q = tid + k * THREADS;
+      lbA[k] = 0; mA[k] = false;
+      if (q < nA) {
+        const int row = sRa[q];
+        int lo = sBp[row], hi = sBp[row + 1];
+        const int be = hi;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sBc[mid] < ja[k]) lo = mid + 1; else hi = mid; }
+        lbA[k] = lo;
+        mA[k] = lo < be && sBc[lo] == ja[k];
+        if (COUNT && mA[k]) atomicAdd(sF + row, 1);
+      }
+      if (!COUNT) sF[q] = mA[k] ? 1 : 0;             // q < CAP always; entries beyond nA are zero
+    }
+    __syncthreads();
+    if (COUNT) {
+      if (tid < nr) counts[r0 + tid] = (my_ae - my_as) + (my_be - my_bs) - sF[tid];
+      return;
+    }
+    // ---- exclusive scan of the match flags (one int4 per thread, warp shuffles, one partial per warp) -------------
+    int4 f = ((int4*)sF)[tid];
+    const int tsum = f.x + f.y + f.z + f.w;
+    int incl = tsum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) { const int v = s_warp[w]; if (w < wid) wbase += v; total += v; }
+    int ex = wbase + incl - tsum;
+    ((int4*)sF)[tid] = make_int4(ex, ex + f.x, ex + f.x + f.y, ex + f.x + f.y + f.z);
+    if (tid == 0) sF[CAP] = total;
+    const int nC = nA + nB - total;
+    if (ONEPASS && tid == 0) st_relaxed_u64(tile_state + tile, (tile == 0 ? SPADD_INCL : SPADD_AGG) | (unsigned)nC);
+    __syncthreads();
+    // ---- scatter into the staged result ------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int q = tid + k * THREADS;
+      if (q < nA) {
+        const int fin = q + lbA[k] - sF[q];
+        if (CRD) sCc[fin] = ja[k];
+        if (VALS) sCv[fin] = mA[k] ? va[k] + sBv[lbA[k]] : va[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int q = tid + k * THREADS;
+      if (q < nB) {
+        const int row = sRb[q];
+        int lo = sAp[row], hi = sAp[row + 1];
+        const int as = lo;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sAc[mid] <= jb[k]) lo = mid + 1; else hi = mid; }
+        if (!(lo > as && sAc[lo - 1] == jb[k])) {
+          const int fin = q + lo - sF[lo];
+          if (CRD) sCc[fin] = jb[k];
+          if (VALS) sCv[fin] = vb[k];
+        }
+      }
+    }
+    int c0;
+    if (ONEPASS) {
+      if (wid == 0) {
+        const int excl = spadd_look_back(tile_state, tile, lane);
+        if (lane == 0) {
+          if (tile > 0) st_relaxed_u64(tile_state + tile, SPADD_INCL | (unsigned)(excl + nC));
+          s_c0 = excl;
+        }
+      }
+      __syncthreads();
+      c0 = s_c0;
+      if (tid < nr) {
+        Cpos[r0 + tid] = c0 + my_as + my_bs - sF[my_as];
+        if (r0 + tid == n - 1) Cpos[n] = c0 + nC;
+      }
+    } else {
+      c0 = __ldg(Cpos + r0);
+      __syncthreads();
+    }
+#pragma unroll 4
+    for (int q = tid; q < nC; q += THREADS) { if (CRD) Ccrd[c0 + q] = sCc[q]; if (VALS) Cv[c0 + q] = sCv[q]; }
+    return;
+  }
+  // ---- direct path: a row block too long to stage; one thread merges one row against global memory -------------------
+  const bool mine = tid < nr;
+  int a = a0 + my_as, ae = a0 + my_ae, b = b0 + my_bs, be = b0 + my_be;
+  int p = 0;
+  if (COUNT || ONEPASS) {
+    int cnt = 0, x = a, y = b;
+    if (mine) {
+      while (x < ae && y < be) {
+        const int jx = __ldg(Acrd + x), jy = __ldg(Bcrd + y), j = min(jx, jy);
+        cnt++; x += (jx == j); y += (jy == j);
+      }
+      cnt += (ae - x) + (be - y);
+    }
+    if (COUNT) { if (mine) counts[r0 + tid] = cnt; return; }
+    // one pass: CTA scan of the row sizes, publish, look back
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) { const int v = s_warp[w]; if (w < wid) wbase += v; total += v; }
+    if (tid == 0) st_relaxed_u64(tile_state + tile, (tile == 0 ? SPADD_INCL : SPADD_AGG) | (unsigned)total);
+    if (wid == 0) {
+      const int excl = spadd_look_back(tile_state, tile, lane);
+      if (lane == 0) {
+        if (tile > 0) st_relaxed_u64(tile_state + tile, SPADD_INCL | (unsigned)(excl + total));
+        s_c0 = excl;
+      }
+    }
+    __syncthreads();
+    p = s_c0 + wbase + incl - cnt;
+    if (mine) {
+      Cpos[r0 + tid] = p;
+      if (r0 + tid == n - 1) Cpos[n] = p + cnt;
+    }
+  } else if (mine) {
+    p = __ldg(Cpos + r0 + tid);
+  }
+  if (!mine) return;
+  while (a < ae && b < be) {
+    const int ja = __ldg(Acrd + a), jb = __ldg(Bcrd + b), j = min(ja, jb);
+    if (CRD) Ccrd[p] = j;
+    if (VALS) Cv[p] = (ja == j && jb == j) ? (__ldg(Av + a) + __ldg(Bv + b)) : (ja == j ? __ldg(Av + a) : __ldg(Bv + b));
+    p++;
+    a += (ja == j);
+    b += (jb == j);
+  }
+  for (; a < ae; a++, p++) { if (CRD) Ccrd[p] = __ldg(Acrd + a); if (VALS) Cv[p] = __ldg(Av + a); }
+  for (; b < be; b++, p++) { if (CRD) Ccrd[p] = __ldg(Bcrd + b); if (VALS) Cv[p] = __ldg(Bv + b); }
+}
+
+template <typename T, int MODE, int CAP, int THREADS>
+static int spadd_union_launch_cfg(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
+                                  const int* Bcrd, const T* Bv, int* Cpos, int* Ccrd, T* Cv, int* counts) {
+  constexpr bool ONEPASS = MODE == 4;
+  constexpr bool CRD = MODE == 1 || MODE == 3 || ONEPASS, VALS = MODE == 2 || MODE == 3 || ONEPASS;
+  const size_t smem = sizeof(int) * ((CAP + 4) + 2 * CAP + 2 * (THREADS + 1) + ((2 * THREADS + 2) & 1) + (CRD ? 2 * CAP : 0)) +
+                      sizeof(unsigned short) * 2 * CAP + (VALS ? sizeof(T) * 3 * CAP : 0);
+  static bool configured = false;
+  if (!configured) {
+    TB_CUDA(cudaFuncSetAttribute(spadd_union_kernel<T, MODE, CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  // rows per CTA: as many as keep an average segment at ~75% of the staging capacity (at most one per thread)
+  const double avg = (double)(nnzA > nnzB ? nnzA : nnzB) / (n > 0 ? n : 1);
+  int rb = avg > 0 ? (int)(0.75 * CAP / avg) : THREADS;
+  rb = rb > THREADS ? THREADS : (rb < 4 ? 4 : rb);
+  const int grid = (n + rb - 1) / rb;
+  unsigned long long* state = nullptr;
+  if (ONEPASS) {
+    TB_TRY(scratch_alloc((void**)&state, sizeof(unsigned long long) * ((size_t)grid + 1)));
+    TB_CUDA(cudaMemsetAsync(state, 0, sizeof(unsigned long long) * ((size_t)grid + 1), stream()));
+  }
+  spadd_union_kernel<T, MODE, CAP, THREADS><<<grid, THREADS, smem, stream()>>>(n, rb, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd,
+                                                                               Cv, counts, state, (int*)(state + grid));
+  count_launch(1);
+  if (ONEPASS) scratch_free(state);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
 template <typename T, int MODE, int CAP, int THREADS>
 static int spadd_block_launch_cfg(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
                                   const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
@@ -183,15 +462,33 @@ static int spadd_block_launch(int n, int nnzA, int nnzB, const int* Apos, const 
                               const int* Bcrd, const T* Bv, const int* Cpos, int* Ccrd, T* Cv, int* counts) {
   static const int variant = getenv("TACO_B200_SPADD_VARIANT") ? atoi(getenv("TACO_B200_SPADD_VARIANT")) : 0;
 #define TB_SPADD_ARGS n, nnzA, nnzB, Apos, Acrd, Av, Bpos, Bcrd, Bv, Cpos, Ccrd, Cv, counts
+#define TB_SPADD_UARGS n, nnzA, nnzB, Apos, Acrd, Av, Bpos, Bcrd, Bv, (int*)Cpos, Ccrd, Cv, counts
   switch (variant) {
     case 1: return spadd_block_launch_cfg<T, MODE, 2048, 256>(TB_SPADD_ARGS);
     case 2: return spadd_block_launch_cfg<T, MODE, 1024, 128>(TB_SPADD_ARGS);
     case 3: return spadd_block_launch_cfg<T, MODE, 256, 32>(TB_SPADD_ARGS);
     case 4: return spadd_block_launch_cfg<T, MODE, 512, 128>(TB_SPADD_ARGS);
-    default: return spadd_block_launch_cfg<T, MODE, 512, 64>(TB_SPADD_ARGS);
+    case 5: return spadd_block_launch_cfg<T, MODE, 512, 64>(TB_SPADD_ARGS);
+    case 6: return spadd_union_launch_cfg<T, MODE, 1024, 256>(TB_SPADD_UARGS);
+    case 7: return spadd_union_launch_cfg<T, MODE, 256, 64>(TB_SPADD_UARGS);
+    default: return spadd_union_launch_cfg<T, MODE, 512, 128>(TB_SPADD_UARGS);
   }
 #undef TB_SPADD_ARGS
 }
+
+// one-pass union (MODE 4): Cpos is an output
+template <typename T>
+static int spadd_onepass_launch(int n, int nnzA, int nnzB, const int* Apos, const int* Acrd, const T* Av, const int* Bpos,
+                                const int* Bcrd, const T* Bv, int* Cpos, int* Ccrd, T* Cv) {
+  static const int variant = getenv("TACO_B200_SPADD_VARIANT") ? atoi(getenv("TACO_B200_SPADD_VARIANT")) : 0;
+  int* counts = nullptr;
+  switch (variant) {
+    case 6: return spadd_union_launch_cfg<T, 4, 1024, 256>(TB_SPADD_UARGS);
+    case 7: return spadd_union_launch_cfg<T, 4, 256, 64>(TB_SPADD_UARGS);
+    default: return spadd_union_launch_cfg<T, 4, 512, 128>(TB_SPADD_UARGS);
+  }
+}
+#undef TB_SPADD_UARGS
 
 // =========================================================================================================
 // SpGEMM
@@ -652,6 +949,26 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* 
   const bool with_vals = av != nullptr;
   int* dpos = nullptr;
   TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
+  // evaluate: ONE kernel builds pos, crd and vals (tickets + decoupled look-back) into arrays allocated at the upper
+  // bound nnzA + nnzB; the host learns nnz afterwards.  TACO_B200_SPADD_ONEPASS=0 selects the two-phase path.
+  static const bool onepass_on = !(getenv("TACO_B200_SPADD_ONEPASS") && atoi(getenv("TACO_B200_SPADD_ONEPASS")) == 0) &&
+                                 !(getenv("TACO_B200_SPADD_VARIANT") && atoi(getenv("TACO_B200_SPADD_VARIANT")) >= 1 &&
+                                   atoi(getenv("TACO_B200_SPADD_VARIANT")) <= 5);
+  const size_t bound = (size_t)s.nnzA + (size_t)s.nnzB;
+  if (with_vals && onepass_on && n > 0 && bound > 0 && bound * (4 + sizeof(T)) <= ((size_t)8 << 30)) {
+    int* dcrd = nullptr;
+    void* dvals = nullptr;
+    TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * bound));
+    TB_TRY(device_result_alloc(&dvals, sizeof(T) * bound));
+    {
+      ProfScope ps("spadd_numeric");
+      TB_TRY(spadd_onepass_launch<T>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), av, s.bpos.as<int>(),
+                                     s.bcrd.as<int>(), bv, dpos, dcrd, (T*)dvals));
+    }
+    int32_t nnzC = 0;
+    TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
+    return publish_structure(C, n, dpos, dcrd, nnzC, sizeof(T), dvals);
+  }
   if (n > 0) {
     ProfScope ps("spadd_symbolic");
     TB_TRY((spadd_block_launch<T, 0>(n, s.nnzA, s.nnzB, s.apos.as<int>(), s.acrd.as<int>(), nullptr, s.bpos.as<int>(),

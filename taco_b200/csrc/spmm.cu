@@ -38,7 +38,10 @@ __device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p, uint64
                  : "=f"(f.v[0]), "=f"(f.v[1]), "=f"(f.v[2]), "=f"(f.v[3]) : "l"(p));
   } else if constexpr (VEC == 2 && sizeof(T) == 8) {
     asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(f.v[0]), "=d"(f.v[1]) : "l"(p));
+  } else if constexpr (VEC == 2 && sizeof(T) == 4) {
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(f.v[0]), "=f"(f.v[1]) : "l"(p));
   } else {
+    static_assert(VEC == 1, "unhandled fragment width");
     f.v[0] = __ldg(p);
   }
   return f;
@@ -57,7 +60,10 @@ __device__ __forceinline__ void store_row(T* __restrict__ C, int row, int col, i
                    "f"(f.v[3]) : "memory");
     } else if constexpr (VEC == 2 && sizeof(T) == 8) {
       asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(f.v[0]), "d"(f.v[1]) : "memory");
+    } else if constexpr (VEC == 2 && sizeof(T) == 4) {
+      asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]) : "memory");
     } else {
+      static_assert(VEC == 1, "unhandled fragment width");
       p[0] = f.v[0];
     }
   }
@@ -264,6 +270,13 @@ static int spmm_launch(const int* pos, const int* crd, const T* vals, const T* B
                        bool colmajor) {
   constexpr int V = 16 / sizeof(T);
   bool vec_ok = (K % V == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)C & 15) == 0);
+  // TACO_B200_SPMM_SLICE=1: one column per lane, so the launch becomes ceil(K/32) passes over A (grid.y, scheduled one
+  // after the other), each gathering 32-column slices of the rows of B -- a 4x smaller working set per pass in L2
+  static const int sliced = getenv("TACO_B200_SPMM_SLICE") ? atoi(getenv("TACO_B200_SPMM_SLICE")) : 0;
+  if (sliced == 1) vec_ok = false;
+  if constexpr (sizeof(T) == 4) {          // =2: two columns per lane (64-column slices, 256-byte gathers)
+    if (sliced == 2 && vec_ok && !colmajor) return spmm_launch_impl<T, 2, false>(pos, crd, vals, B, C, rows, K, rg);
+  }
   if (colmajor) {
     if (vec_ok) return spmm_launch_impl<T, V, true>(pos, crd, vals, B, C, rows, K, rg);
     return spmm_launch_impl<T, 1, true>(pos, crd, vals, B, C, rows, K, rg);

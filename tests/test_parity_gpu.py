@@ -262,6 +262,29 @@ def test_oracle_spadd(space, dtype):
     assert np.array_equal(pos, cp) and np.array_equal(crd, cc) and np.array_equal(vals, cv)
 
 
+@pytest.mark.parametrize("phases", ["evaluate", "separate"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_oracle_spadd_evaluate_and_skewed_rows(phases, dtype):
+    # evaluate = the one-pass union kernel (tickets + look-back); R-MAT operands put hub rows (> staging capacity) next to
+    # empty ones, so staged and direct row blocks alternate inside one launch; many columns coincide
+    xp = synth.backend(None)
+    ap, ac, av = synth.csr_rmat(xp, 13, 12, 91, np.dtype(dtype))
+    bp, bc, bv = synth.csr_rmat(xp, 13, 20, 91, np.dtype(dtype))       # same seed, more edges: heavy overlap with A
+    n = 1 << 13
+    assert np.diff(ap).max() > 1024 and (np.diff(ap) == 0).sum() > 100
+    cp, cc, cv = oracle.spadd(ap, ac, av, bp, bc, bv)
+    assert len(cc) < len(ac) + len(bc)
+    w = dict(dims=[n, n], A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv)
+    for space in SPACES:
+        pos, crd, vals = G.run("spadd", place(w, space), phases=phases)
+        assert np.array_equal(pos, cp) and np.array_equal(crd, cc) and np.array_equal(vals, cv)
+    # uniform operands at a size that is not a multiple of the row block
+    w = synth.make("spadd", None, n=77_777, deg=13, dtype=dtype)
+    cp, cc, cv = oracle.spadd(w["A_pos"], w["A_crd"], w["A_vals"], w["B_pos"], w["B_crd"], w["B_vals"])
+    pos, crd, vals = G.run("spadd", G.to_device(w), phases=phases)
+    assert np.array_equal(pos, cp) and np.array_equal(crd, cc) and np.array_equal(vals, cv)
+
+
 @pytest.mark.parametrize("space", SPACES)
 def test_oracle_spgemm(space):
     w = synth.make("spgemm", None, n=40_009, deg=10, dtype="float64")

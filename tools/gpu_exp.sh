@@ -1,0 +1,39 @@
+#!/bin/bash
+# Experiment pass on one GPU box: parity tests, then A/B runs of launch variants selected by environment variables.
+# usage: tools/gpu_exp.sh   (edit the EXPS list)   outputs: gpurun_out/exp_*.txt
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/smi.txt 2>&1; nproc >> gpurun_out/smi.txt
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log
+summ='import sys,json
+for l in sys.stdin:
+    l=l.strip()
+    if not l.startswith("{"): continue
+    j=json.loads(l); r=j["roofline"]
+    print("value",round(j["value"],1),"ms/step",round(j["ms_per_step"],4),"kernel_ms",round(r["kernel_ms"],4),"frac",round(r["frac"],4),"launches",j["gpu_launches"])'
+run() {  # workload, env assignments...
+  wl=$1; shift
+  echo "== $wl $*"
+  env "$@" timeout 600 python bench.py --workload $wl --no-e2e --no-cpu --steps 10 2>&1 | tail -1 | python -c "$summ"
+}
+ncuq() {  # workload, kernel regex, env...
+  wl=$1; k=$2; shift; shift
+  echo "== ncu $wl $k $*"
+  env "$@" timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct \
+     --clock-control none -k regex:$k --launch-skip 3 -c 1 python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu 2>&1 \
+     | grep -E "dram__|gpu__time|hit_rate|void " 
+}
+{
+run spmm X=0
+run spmm TACO_B200_SPMM_SLICE=1
+run spmm TACO_B200_SPMM_SLICE=2
+run spadd X=0
+run spadd TACO_B200_SPADD_ONEPASS=0
+run spadd TACO_B200_SPADD_VARIANT=5
+run spadd TACO_B200_SPADD_VARIANT=6
+run spadd TACO_B200_SPADD_VARIANT=7
+ncuq spmm spmm_csr TACO_B200_SPMM_SLICE=1
+ncuq spmm spmm_csr TACO_B200_SPMM_SLICE=2
+ncuq spadd spadd_union X=0
+} > gpurun_out/exp_1.txt 2>&1
+cat gpurun_out/exp_1.txt
