@@ -949,9 +949,10 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* 
   const bool with_vals = av != nullptr;
   int* dpos = nullptr;
   TB_TRY(device_result_alloc((void**)&dpos, sizeof(int) * ((size_t)n + 1)));
-  // evaluate: ONE kernel builds pos, crd and vals (tickets + decoupled look-back) into arrays allocated at the upper
-  // bound nnzA + nnzB; the host learns nnz afterwards.  TACO_B200_SPADD_ONEPASS=0 selects the two-phase path.
-  static const bool onepass_on = !(getenv("TACO_B200_SPADD_ONEPASS") && atoi(getenv("TACO_B200_SPADD_ONEPASS")) == 0) &&
+  // Default: two-phase (count -> scan -> fused crd+vals fill), measured 0.247 ms per C5a step.  TACO_B200_SPADD_ONEPASS=1
+  // selects the single-kernel variant (tickets + decoupled look-back, arrays allocated at the upper bound nnzA + nnzB):
+  // it reads A and B once, but the look-back spin costs more than the second read saves (0.285 ms, profiles/r01_variants.md).
+  static const bool onepass_on = getenv("TACO_B200_SPADD_ONEPASS") && atoi(getenv("TACO_B200_SPADD_ONEPASS")) == 1 &&
                                  !(getenv("TACO_B200_SPADD_VARIANT") && atoi(getenv("TACO_B200_SPADD_VARIANT")) >= 1 &&
                                    atoi(getenv("TACO_B200_SPADD_VARIANT")) <= 5);
   const size_t bound = (size_t)s.nnzA + (size_t)s.nnzB;

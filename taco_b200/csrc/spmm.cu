@@ -229,6 +229,183 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Ring kernel (row-major C, 16-byte lane fragments): the same slot/ownership scheme as spmm_csr_kernel, but the B-row
+// gathers no longer land in registers.  Every lane copies ITS 16 bytes of a gathered row with cp.async (LDGSTS) into a
+// per-warp ring of D rows in shared memory and later reads the same 16 bytes back, so no cross-lane synchronisation is
+// needed and D gathers stay in flight per warp at no register cost.  The nonzeros of all non-hub rows a slot owns form
+// ONE flat stream [pos[R0], pos[R1e)): the producer runs D nonzeros ahead of the consumer ACROSS row boundaries, which
+// removes the per-row latency chain (crd -> B row -> store) that bounded the register kernel on short rows (measured:
+// halving the gathered bytes per pass only cut its time by 30 %).  Within a row the products are still accumulated in
+// ascending position order with separate multiply and add, so non-hub rows stay bit-identical to the reference.
+// ---------------------------------------------------------------------------------------------------------
+template <bool CA>
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  if constexpr (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int VEC>
+__device__ __forceinline__ Frag<T, VEC> lds_frag(uint32_t addr) {
+  Frag<T, VEC> f;
+  if constexpr (sizeof(T) == 4) {
+    static_assert(VEC == 4, "ring kernel: 16-byte fragments");
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.v[0]), "=f"(f.v[1]), "=f"(f.v[2]), "=f"(f.v[3]) : "r"(addr) : "memory");
+  } else {
+    static_assert(VEC == 2, "ring kernel: 16-byte fragments");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(f.v[0]), "=d"(f.v[1]) : "r"(addr) : "memory");
+  }
+  return f;
+}
+
+template <typename T, int VEC, int D, int WARPS, int MINB, bool CA>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+spmm_ring_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
+                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
+                 const int* __restrict__ slot_rows) {
+  static_assert(D >= 2 && D <= 32 && (D & (D - 1)) == 0, "ring depth: power of two, at most one chunk");
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= nslots) return;
+  const int nnz = rg.p1;
+  const int lo = rg.p0 + w * SPMM_W, hi = min(lo + SPMM_W, nnz);
+  if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
+  else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
+  const int col = (blockIdx.y * 32 + lane) * VEC;
+  const bool active = col < K;
+  const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
+  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_raw) + (uint32_t)(threadIdx.x >> 5) * (D * 512) + lane * 16;
+  Frag<T, VEC> acc;
+
+  // (a) the piece [lo, min(hi, e)) of a hub row that started in an earlier slot: added atomically (cold path)
+  if (R0 > rg.r0 && lo < nnz) {
+    const int s = __ldg(pos + R0 - 1), e = __ldg(pos + R0);
+    if (e > lo && e - s > SPMM_LONG) {
+#pragma unroll
+      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+      spmm_accumulate<T, VEC, 1>(acc, crd, vals, Bcol, K, lo, min(hi, e), lane, 0, 0);
+      if (active) red_row<T, VEC, false>(C, R0 - 1, col, rows, K, acc);
+    }
+  }
+  if (R1 <= R0) return;
+  // (b) empty rows are zeroed by their owner; a hub row (always the last row a slot owns) contributes its first piece
+#pragma unroll
+  for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+  for (int rb = R0; rb < R1; rb += 32) {
+    const int r = rb + lane;
+    const bool valid = r < R1;
+    const int s = valid ? __ldg(pos + r) : 0, e = valid ? __ldg(pos + r + 1) : 1;
+    unsigned empty = __ballot_sync(0xffffffffu, valid && e == s);
+    while (empty) {
+      const int h = __ffs(empty) - 1;
+      empty &= empty - 1;
+      if (active) store_row<T, VEC, false>(C, rb + h, col, rows, K, acc, 0);
+    }
+  }
+  int R1e = R1;
+  {
+    const int s = __ldg(pos + R1 - 1), e = __ldg(pos + R1);
+    if (e - s > SPMM_LONG) {
+      R1e = R1 - 1;
+      spmm_accumulate<T, VEC, 1>(acc, crd, vals, Bcol, K, s, min(hi, e), lane, 0, 0);
+      if (active) red_row<T, VEC, false>(C, R1e, col, rows, K, acc);
+#pragma unroll
+      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+    }
+  }
+  if (R1e <= R0) return;
+  // (c) the flat stream of the complete rows R0 .. R1e-1
+  const int S = __ldg(pos + R0), E = __ldg(pos + R1e);
+  if (E <= S) return;
+  int crd_k = 0, crd_n = 0;                      // column ids of the chunk being consumed / the next chunk (lane = offset)
+  T val_k = T(0), val_n = T(0);
+  if (S + lane < E) { crd_k = tbd::ldg_stream_i32(crd + S + lane); val_k = __ldg(vals + S + lane); }
+  if (S + 32 + lane < E) { crd_n = tbd::ldg_stream_i32(crd + S + 32 + lane); val_n = __ldg(vals + S + 32 + lane); }
+  // prologue: the first D gathers
+#pragma unroll
+  for (int d = 0; d < D; d++) {
+    const int c = __shfl_sync(0xffffffffu, crd_k, d);
+    if (S + d < E) cp_async16<CA>(ring + d * 512, Bcol + (size_t)c * K);
+    cp_async_commit();
+  }
+  // row cursor: the ends of 32 rows at a time live in `my_e` (lane = row - rb); rows past R1e read as E
+  int rb = R0, row = R0;
+  int my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E;
+  int row_end = __shfl_sync(0xffffffffu, my_e, 0);
+  while (row_end == S) {                          // leading empty rows (already zeroed)
+    row++;
+    if (row - rb == 32) { rb += 32; my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E; }
+    row_end = __shfl_sync(0xffffffffu, my_e, row - rb);
+  }
+  const char* Bbytes = (const char*)Bcol;
+  const unsigned stride = (unsigned)K * (unsigned)sizeof(T);          // bytes between rows of B
+  constexpr uint32_t RMASK = D * 512 - 1;
+  constexpr int G = D >= 4 ? 4 : 2;                                   // nonzeros per fast-path step
+  for (int base = S; base < E; base += 32) {
+    const int cnt = min(32, E - base);
+    int j = 0;
+    while (j < cnt) {
+      const int pc = base + j;
+      const uint32_t off = ((uint32_t)(pc - S) * 512u) & RMASK;
+      const int run = min(row_end - pc, cnt - j);                     // nonzeros left in this row and this chunk
+      if (run >= G && pc + D + G <= E && (((j + D) ^ (j + D + G - 1)) & 32) == 0) {
+        // fast path: G nonzeros of one row; their G refills are all valid and come from one chunk register
+        const int src = (j + D) < 32 ? crd_k : crd_n;
+        cp_async_wait<D - G>();
+        Frag<T, VEC> bv[G];
+        T v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          bv[g] = lds_frag<T, VEC>(ring + ((off + g * 512u) & RMASK));
+          v[g] = __shfl_sync(0xffffffffu, val_k, j + g);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+          for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v[g] * bv[g].v[x];      // mul then add: never fused
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          const unsigned c = (unsigned)__shfl_sync(0xffffffffu, src, j + D + g);   // source lane is taken modulo 32
+          cp_async16<CA>(ring + ((off + g * 512u) & RMASK), Bbytes + (size_t)c * stride);
+          cp_async_commit();
+        }
+        j += G;
+      } else {
+        const uint32_t slot = ring + off;
+        cp_async_wait<D - 1>();
+        const Frag<T, VEC> b1 = lds_frag<T, VEC>(slot);
+        const T v1 = __shfl_sync(0xffffffffu, val_k, j);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v1 * b1.v[x];
+        const int jn = j + D;
+        const unsigned c = (unsigned)__shfl_sync(0xffffffffu, jn < 32 ? crd_k : crd_n, jn);
+        if (pc + D < E) cp_async16<CA>(slot, Bbytes + (size_t)c * stride);
+        cp_async_commit();
+        j += 1;
+      }
+      if (base + j == row_end) {
+        if (active) store_row<T, VEC, false>(C, row, col, rows, K, acc, 0);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+        do {                                      // next non-empty row (rows past R1e read as E: ends with base + j == E)
+          row++;
+          if (row - rb == 32) { rb += 32; my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E; }
+          row_end = __shfl_sync(0xffffffffu, my_e, row - rb);
+        } while (row_end == base + j && row < R1e);
+      }
+    }
+    crd_k = crd_n; val_k = val_n;
+    const int nb = base + 64 + lane;
+    if (nb < E) { crd_n = tbd::ldg_stream_i32(crd + nb); val_n = __ldg(vals + nb); }
+  }
+  cp_async_wait<0>();
+}
+
 // Launch variants: (gathers in flight per warp, warps per CTA, min CTAs per SM).  TACO_B200_SPMM_VARIANT selects one
 // for tuning runs; the default is the measured best at config C2 (profiles/).
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
@@ -237,6 +414,22 @@ static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
   spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
                                                                                  slot_rows);
+}
+
+template <typename T, int VEC, int D, int WARPS, int MINB, bool CA>
+static int spmm_ring_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg,
+                        int nslots, const int* slot_rows, cudaStream_t st) {
+  constexpr int smem = WARPS * D * 512;
+  static bool configured = false;
+  if (!configured) {
+    TB_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TB_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
+  spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA><<<grid, WARPS * 32, smem, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots, slot_rows);
+  return TACO_B200_OK;
 }
 
 template <typename T, int VEC, bool COLMAJOR>
@@ -252,12 +445,28 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
     ProfScope ps("spmm_csr");
     const int* sr = (const int*)slot_rows;
     cudaStream_t st = stream();
+    constexpr bool RING_OK = !COLMAJOR && VEC * sizeof(T) == 16;
+    if constexpr (RING_OK) {
+      switch (variant) {
+        case 10: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 6, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 11: TB_TRY((spmm_ring_go<T, VEC, 16, 8, 3, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 12: TB_TRY((spmm_ring_go<T, VEC, 4, 8, 8, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 13: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 4, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 14: TB_TRY((spmm_ring_go<T, VEC, 8, 4, 12, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 15: TB_TRY((spmm_ring_go<T, VEC, 16, 4, 6, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 16: TB_TRY((spmm_ring_go<T, VEC, 32, 4, 3, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 17: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 6, true>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        case 18: TB_TRY((spmm_ring_go<T, VEC, 16, 8, 3, true>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
+        default: break;
+      }
+    }
     switch (variant) {
       case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
       case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
       case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
       default: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
     }
+  launched:;
   }
   count_launch(2);
   scratch_free(slot_rows);

@@ -24,16 +24,14 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
+for v in 10 12 16; do
+  echo "== parity with TACO_B200_SPMM_VARIANT=$v"
+  TACO_B200_SPMM_VARIANT=$v timeout 600 python -m pytest tests -m gpu -x -q -k "spmm or empty or leading or smoke" 2>&1 | tail -3
+done
 run spmm X=0
-run spmm TACO_B200_SPMM_SLICE=1
-run spmm TACO_B200_SPMM_SLICE=2
+for v in 10 11 12 13 14 15 16 17 18; do run spmm TACO_B200_SPMM_VARIANT=$v; done
 run spadd X=0
-run spadd TACO_B200_SPADD_ONEPASS=0
-run spadd TACO_B200_SPADD_VARIANT=5
-run spadd TACO_B200_SPADD_VARIANT=6
-run spadd TACO_B200_SPADD_VARIANT=7
-ncuq spmm spmm_csr TACO_B200_SPMM_SLICE=1
-ncuq spmm spmm_csr TACO_B200_SPMM_SLICE=2
-ncuq spadd spadd_union X=0
-} > gpurun_out/exp_1.txt 2>&1
-cat gpurun_out/exp_1.txt
+ncuq spmm spmm_ring TACO_B200_SPMM_VARIANT=10
+ncuq spmm spmm_ring TACO_B200_SPMM_VARIANT=11
+} > gpurun_out/exp_2.txt 2>&1
+cat gpurun_out/exp_2.txt
