@@ -134,6 +134,31 @@ def ttm(t, C, I, K):
     return A
 
 
+def bspmv(pos, crd, vals, c, br, bc):
+    """a(i,j) = A(i,k,j,l) * c(k,l); vals = blocks [nnzb, br, bc], c = (Nb, bc); returns a (Mb, br)"""
+    pos, crd = _i32(pos), _i32(crd)
+    Mb = pos.size - 1
+    vals = np.ascontiguousarray(vals)
+    c = np.ascontiguousarray(c, dtype=vals.dtype)
+    a = np.empty((Mb, br), dtype=vals.dtype)
+    getattr(lib(), "oracle_bspmv_" + _sfx(vals.dtype))(ctypes.c_int32(Mb), ctypes.c_int32(br), ctypes.c_int32(bc),
+                                                      _p(pos), _p(crd), _p(vals), _p(c), _p(a))
+    return a
+
+
+def bspmm(pos, crd, vals, B, br, bc):
+    """C(i,j,m) = A(i,k,j,l) * B(k,l,m); vals = blocks [nnzb, br, bc], B = (Nb*bc, K); returns C (Mb*br, K)"""
+    pos, crd = _i32(pos), _i32(crd)
+    Mb = pos.size - 1
+    vals = np.ascontiguousarray(vals)
+    B = np.ascontiguousarray(B, dtype=vals.dtype)
+    K = B.shape[-1]
+    C = np.empty((Mb * br, K), dtype=vals.dtype)
+    getattr(lib(), "oracle_bspmm_" + _sfx(vals.dtype))(ctypes.c_int32(Mb), ctypes.c_int32(br), ctypes.c_int32(bc),
+                                                      ctypes.c_int32(K), _p(pos), _p(crd), _p(vals), _p(B), _p(C))
+    return C
+
+
 def _sparse_out(assemble_fn, compute_name, n, head_args, struct_args, Aval, Bval):
     cpos = np.empty(n + 1, dtype=np.int32)
     crd_ptr = _I32P()

@@ -10,7 +10,7 @@
 //
 // usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
 //                         [--threads N] [--reps R]
-//   kernel in {spmv, spmm, sddmm, mttkrp, spadd, spgemm, ttv, ttm}
+//   kernel in {spmv, spmm, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm}
 // Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
 //
 // Input arrays (tbin.h): dims (int32), and per kernel
@@ -22,6 +22,8 @@
 //   ttm    : B1..B3, B_vals, C (L x R)                     -> A (I x K x R dense)     dims = I K L R
 //   spadd  : A_* B_*                                       -> C_pos C_crd C_vals      dims = n m
 //   spgemm : A_* B_*                                       -> C_pos C_crd C_vals      dims = n m o
+//   bspmv  : A_pos A_crd A_vals (blocks br x bc) c (Nb x bc)   -> a (Mb x br)         dims = Mb Nb br bc
+//   bspmm  : A_pos A_crd A_vals (blocks br x bc) B (Nb x bc x K) -> C (Mb x br x K)   dims = Mb Nb br bc K
 #include <chrono>
 #include <iostream>
 #include <string>
@@ -85,6 +87,27 @@ static Tensor<T> attachCSF3(const std::string& name, std::vector<int> dims, tbin
                             makeArray((int*)crd->data, crd->count, Array::UserOwns)}));
   }
   tbin_array* v = need(f, (p + "_vals").c_str());
+  st.setIndex(Index(t.getFormat(), mi));
+  st.setValues(makeArray((T*)v->data, v->count, Array::UserOwns));
+  t.setStorage(st);
+  return t;
+}
+
+// Blocked CSR as the reference's own `bspmv` test declares it (test/tests-expr_storage.cpp:939-960):
+// order-4 tensor {Dense, Compressed, Dense, Dense} over (block row, block column, row in block, column in block).
+template <typename T>
+static Tensor<T> attachBCSR(const std::string& name, std::vector<int> dims, tbin_file& f, const std::string& p) {
+  Tensor<T> t(name, dims, Format({Dense, Sparse, Dense, Dense}));
+  auto st = t.getStorage();
+  tbin_array* pos = need(f, (p + "_pos").c_str());
+  tbin_array* crd = need(f, (p + "_crd").c_str());
+  tbin_array* v = need(f, (p + "_vals").c_str());
+  std::vector<ModeIndex> mi;
+  mi.push_back(ModeIndex({makeArray(std::vector<int>{dims[0]})}));
+  mi.push_back(ModeIndex({makeArray((int*)pos->data, pos->count, Array::UserOwns),
+                          makeArray((int*)crd->data, crd->count, Array::UserOwns)}));
+  mi.push_back(ModeIndex({makeArray(std::vector<int>{dims[2]})}));
+  mi.push_back(ModeIndex({makeArray(std::vector<int>{dims[3]})}));
   st.setIndex(Index(t.getFormat(), mi));
   st.setValues(makeArray((T*)v->data, v->count, Array::UserOwns));
   t.setStorage(st);
@@ -281,6 +304,48 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         strcpy(a.name, "C_crd"); a.dtype = 0; a.count = pos[n]; a.data = crd; outs.push_back(a);
         strcpy(a.name, "C_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
         tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "bspmv" || kernel == "bspmm") {
+      // bspmv: a(i,j) = A(i,k,j,l) * c(k,l)   (the reference's blocked-SpMV test statement)
+      // bspmm: C(i,j,m) = A(i,k,j,l) * B(k,l,m)
+      int Mb = dims[0], Nb = dims[1], br = dims[2], bc = dims[3];
+      IndexVar m("m");
+      Tensor<T> A = attachBCSR<T>("A", {Mb, Nb, br, bc}, in, "A");
+      if (kernel == "bspmv") {
+        Tensor<T> c = attachDense<T>("c", {Nb, bc}, (T*)need(in, "c")->data);
+        Tensor<T> a("a", {Mb, br}, Format({Dense, Dense}));
+        a(i, j) = A(i, k, j, l) * c(k, l);
+        double t0 = now_ms(); a.compile();
+        double t1 = now_ms(); dumpSource(a); a.assemble();
+        double t2 = now_ms(); a.compute();
+        double t3 = now_ms();
+        if (rep == 0) tm.compile = t1 - t0;
+        tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+        if (last) {
+          tbin_array o; strcpy(o.name, "a"); o.dtype = tbin_dtype<T>(); o.count = (uint64_t)Mb * br;
+          o.data = a.getStorage().getValues().getData(); outs.push_back(o);
+          tbin_write(outPath, outs.data(), outs.size());
+        }
+      } else {
+        int K = dims[4];
+        Tensor<T> B = attachDense<T>("B", {Nb, bc, K}, (T*)need(in, "B")->data);
+        Tensor<T> C("C", {Mb, br, K}, Format({Dense, Dense, Dense}));
+        C(i, j, m) = A(i, k, j, l) * B(k, l, m);
+        IndexStmt stmt = C.getAssignment().concretize();
+        if (tuned) {   // rows of blocks in parallel (the shape of scheduleSpMMCPU without the pos split)
+          stmt = stmt.parallelize(i, ParallelUnit::CPUThread, OutputRaceStrategy::NoRaces);
+        }
+        double t0 = now_ms(); if (tuned) C.compile(stmt); else C.compile();
+        double t1 = now_ms(); dumpSource(C); C.assemble();
+        double t2 = now_ms(); C.compute();
+        double t3 = now_ms();
+        if (rep == 0) tm.compile = t1 - t0;
+        tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+        if (last) {
+          tbin_array o; strcpy(o.name, "C"); o.dtype = tbin_dtype<T>(); o.count = (uint64_t)Mb * br * K;
+          o.data = C.getStorage().getValues().getData(); outs.push_back(o);
+          tbin_write(outPath, outs.data(), outs.size());
+        }
       }
     } else {
       std::cerr << "unknown kernel " << kernel << std::endl;

@@ -127,6 +127,46 @@ static int cmp_i32(const void* a, const void* b) { /* reference prelude `cmp`, s
       }                                                                                                            \
     }                                                                                                              \
   }                                                                                                                \
+  /* a(i,j) = A(i,k,j,l) * c(k,l): blocked SpMV, A = {Dense,Compressed,Dense,Dense} (the reference's `bspmv` test,  \
+     test/tests-expr_storage.cpp:939-960).  Generated loop order i, kA, j, l; tl = sum_l A*c (scalar), a[i,j] = a[i,j] + tl  \
+     after a zero fill -- captured with TACO_REF_DUMP=1 oracle/_ref/taco_ref_harness bspmv. */                                    \
+  void oracle_bspmv_##S(int32_t Mb, int32_t br, int32_t bc, const int32_t* pos, const int32_t* crd, const T* vals,  \
+                        const T* c, T* a) {                                                                          \
+    _Pragma("omp parallel for schedule(static)") for (int32_t i = 0; i < Mb; i++) {                                 \
+      T* ar = a + (size_t)i * br;                                                                                    \
+      for (int32_t j = 0; j < br; j++) ar[j] = 0;                                                                    \
+      for (int32_t kA = pos[i]; kA < pos[i + 1]; kA++) {                                                             \
+        const T* cr = c + (size_t)crd[kA] * bc;                                                                      \
+        for (int32_t j = 0; j < br; j++) {                                                                           \
+          const T* blk = vals + ((size_t)kA * br + j) * bc;                                                          \
+          T t = 0;                           /* scalar temporary per (block, row): tla_val in the generated C */    \
+          for (int32_t l = 0; l < bc; l++) t += blk[l] * cr[l];                                                      \
+          ar[j] = ar[j] + t;                                                                                         \
+        }                                                                                                            \
+      }                                                                                                              \
+    }                                                                                                                \
+  }                                                                                                                  \
+  /* C(i,j,m) = A(i,k,j,l) * B(k,l,m): blocked SpMM, B = (Nb, bc, K) and C = (Mb, br, K) dense.  Generated loop      \
+     order i, kA, j, l, m with C[mC] = C[mC] + A[lA] * B[mB] after a zero fill (dump of the reference, as above). */ \
+  void oracle_bspmm_##S(int32_t Mb, int32_t br, int32_t bc, int32_t K, const int32_t* pos, const int32_t* crd,      \
+                        const T* vals, const T* B, T* C) {                                                           \
+    _Pragma("omp parallel for schedule(static)") for (int32_t i = 0; i < Mb; i++) {                                 \
+      T* ci = C + (size_t)i * br * K;                                                                                \
+      for (size_t q = 0; q < (size_t)br * K; q++) ci[q] = 0;                                                         \
+      for (int32_t kA = pos[i]; kA < pos[i + 1]; kA++) {                                                             \
+        const T* bk = B + (size_t)crd[kA] * bc * K;                                                                  \
+        for (int32_t j = 0; j < br; j++) {                                                                           \
+          T* cj = ci + (size_t)j * K;                                                                                \
+          const T* blk = vals + ((size_t)kA * br + j) * bc;                                                          \
+          for (int32_t l = 0; l < bc; l++) {                                                                         \
+            const T av = blk[l];                                                                                     \
+            const T* bl = bk + (size_t)l * K;                                                                        \
+            for (int32_t m = 0; m < K; m++) cj[m] = cj[m] + av * bl[m];                                              \
+          }                                                                                                          \
+        }                                                                                                            \
+      }                                                                                                              \
+    }                                                                                                                \
+  }                                                                                                                  \
   /* C(i,j) = A(i,j) + B(i,j): numeric phase; the same two-finger walk as assemble, values a+b | a | b           \
      (merge lattice union, src/lower/merge_lattice.cpp:1005; Appendix A.4 of SURVEY.md). */                       \
   void oracle_spadd_compute_##S(int32_t n, const int32_t* Apos, const int32_t* Acrd, const T* Avals,              \

@@ -6,7 +6,7 @@
  *
  * Parity pin: tests/test_oracle_golden.py checks every function against
  *   (1) the reference's own known-answer vectors (test/tests-expr_storage.cpp groups spmv :873, matrix_add :523,
- *       matrix_mul :996, tensor_vector_mul :1037, tensor_matrix_mul :1096, mttkrp :1145 over the fixtures in
+ *       matrix_mul :996, bspmv :939, tensor_vector_mul :1037, tensor_matrix_mul :1096, mttkrp :1145 over the fixtures in
  *       test/test_tensors.cpp), and
  *   (2) outputs of the reference itself (oracle/_ref/taco_ref_harness, built from /root/reference by
  *       oracle/Makefile) committed as fixtures under tests/golden/ by tests/golden/make_golden.py.
@@ -38,6 +38,10 @@ int  oracle_get_max_threads(void);
   void oracle_ttm_##S(int32_t R, const int32_t* B1_pos, const int32_t* B1_crd, const int32_t* B2_pos,             \
                       const int32_t* B2_crd, const int32_t* B3_pos, const int32_t* B3_crd, const T* Bvals,        \
                       const T* C, int32_t I, int32_t K, T* A);                                                     \
+  void oracle_bspmv_##S(int32_t Mb, int32_t br, int32_t bc, const int32_t* pos, const int32_t* crd, const T* vals,  \
+                        const T* c, T* a);                                                                           \
+  void oracle_bspmm_##S(int32_t Mb, int32_t br, int32_t bc, int32_t K, const int32_t* pos, const int32_t* crd,      \
+                        const T* vals, const T* B, T* C);                                                            \
   void oracle_spadd_compute_##S(int32_t n, const int32_t* Apos, const int32_t* Acrd, const T* Avals,              \
                                 const int32_t* Bpos, const int32_t* Bcrd, const T* Bvals, const int32_t* Cpos,    \
                                 T* Cvals);                                                                         \

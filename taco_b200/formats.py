@@ -5,6 +5,9 @@ Level semantics follow the reference exactly:
     (/root/reference/src/lower/mode_format_compressed.cpp:80-105)
   * dense level: position = parent_pos * dim + coord (/root/reference/src/lower/mode_format_dense.cpp:50-55)
   * CSR  = {Dense, Compressed}; CSF(3) = {Compressed, Compressed, Compressed}
+  * BCSR = {Dense, Compressed, Dense, Dense} over (block row, block column, row in block, column in block), the
+    blocked format of the reference's `bspmv` test (/root/reference/test/tests-expr_storage.cpp:939-960):
+    vals = [number of stored blocks][br][bc]
 """
 import numpy as np
 
@@ -83,3 +86,23 @@ def csf3_to_coo(t):
     i = t["B1_crd"][fib_slice][leaf_fib]
     k = t["B2_crd"][leaf_fib]
     return i, k, t["B3_crd"], t["B_vals"]
+
+
+def bcsr_from_dense(dense, br, bc):
+    """dense (Mb*br, Nb*bc) -> BCSR pos[Mb+1], crd[nnzb], vals[nnzb, br, bc]; a block is stored iff it has a nonzero."""
+    dense = np.asarray(dense)
+    Mb, Nb = dense.shape[0] // br, dense.shape[1] // bc
+    assert dense.shape == (Mb * br, Nb * bc)
+    blocks = dense.reshape(Mb, br, Nb, bc).transpose(0, 2, 1, 3)         # (Mb, Nb, br, bc)
+    keep = (blocks != 0).any(axis=(2, 3))
+    bi, bj = np.nonzero(keep)
+    pos = np.zeros(Mb + 1, dtype=np.int64)
+    np.add.at(pos, bi + 1, 1)
+    return np.cumsum(pos).astype(np.int32), bj.astype(np.int32), np.ascontiguousarray(blocks[bi, bj])
+
+
+def bcsr_to_dense(Mb, Nb, br, bc, pos, crd, vals):
+    out = np.zeros((Mb, Nb, br, bc), dtype=np.asarray(vals).dtype)
+    rows = np.repeat(np.arange(Mb), np.diff(pos))
+    out[rows, crd] = np.asarray(vals).reshape(-1, br, bc)
+    return out.transpose(0, 2, 1, 3).reshape(Mb * br, Nb * bc)

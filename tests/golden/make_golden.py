@@ -133,6 +133,26 @@ def main():
             for sched in ("default", "cpu"):
                 out = run_ref("spgemm", inp, sfx, sched)
                 cases[f"spgemm_{tag}_{sfx}_{sched}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    # ---- blocked SpMV / SpMM (BCSR = {Dense,Compressed,Dense,Dense}, the reference's bspmv statement) -----------
+    for integer in (True, False):
+        tag = "int" if integer else "frac"
+        for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
+            rng = np.random.default_rng(77001 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
+            for (Mb, Nb, br, bc, K) in ((9, 7, 4, 4, 12), (5, 6, 16, 16, 40), (4, 5, 32, 32, 128), (6, 4, 3, 5, 7)):
+                blk = rng.random((Mb, Nb)) < 0.45
+                blk[2 % Mb] = False                                   # an empty block row
+                A = dense_fill(rng, (Mb * br, Nb * bc), integer, dtype) + (1 if integer else 0.5)
+                A = (A.reshape(Mb, br, Nb, bc) * blk[:, None, :, None]).reshape(Mb * br, Nb * bc).astype(dtype)
+                p, c, v = formats.bcsr_from_dense(A, br, bc)
+                B = dense_fill(rng, (Nb * bc, K), integer, dtype)
+                inp = dict(dims=np.array([Mb, Nb, br, bc, K], np.int32), A_pos=p, A_crd=c, A_vals=v.reshape(-1), B=B)
+                out = run_ref("bspmm", inp, sfx, "default")
+                cases[f"bspmm_{tag}_{sfx}_{br}x{bc}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+                if (br, bc) in ((4, 4), (3, 5)):
+                    cv = dense_fill(rng, (Nb, bc), integer, dtype)
+                    inp = dict(dims=np.array([Mb, Nb, br, bc], np.int32), A_pos=p, A_crd=c, A_vals=v.reshape(-1), c=cv)
+                    out = run_ref("bspmv", inp, sfx, "default")
+                    cases[f"bspmv_{tag}_{sfx}_{br}x{bc}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
     for name, arrs in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
     print(f"wrote {len(cases)} golden cases to {OUT}")

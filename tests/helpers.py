@@ -69,3 +69,14 @@ def d333a():  # :328-339  -> (i, j, k, vals)
     c = [(0, 0, 0, 2), (0, 0, 1, 3), (0, 2, 2, 4), (1, 0, 1, 5), (1, 2, 0, 6), (1, 2, 2, 7), (2, 1, 2, 8), (2, 2, 1, 9)]
     i, j, k, v = map(np.array, zip(*c))
     return i, j, k, v.astype(np.float64)
+
+
+def d3322a():  # :369-386  -> BCSR (pos, crd, blocks[nnzb,2,2]) of the order-4 fixture, dims (3,3,2,2)
+    pos = np.array([0, 1, 1, 3], np.int32)
+    crd = np.array([1, 0, 2], np.int32)
+    blocks = np.array([[[2.1, 2.2], [2.3, 2.4]], [[3.1, 3.2], [3.3, 3.4]], [[4.1, 4.2], [4.3, 4.4]]])
+    return pos, crd, blocks
+
+
+def d32b():   # :358-367
+    return np.array([[10.0, 11.0], [20.0, 21.0], [30.0, 31.0]])

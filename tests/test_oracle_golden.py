@@ -76,6 +76,17 @@ def test_kat_tensor_matrix_mul():
     assert np.array_equal(A.reshape(-1), [0, 4, 0, 0, 0, 0, 12, 0, 16, 0, 0, 0, 0, 0, 0, 21, 12, 28])
 
 
+def test_kat_bspmv():
+    # tests-expr_storage.cpp:939-960: d3322a("B",{Dense,Sparse,Dense,Dense})(i,k,j,l) * d32b("c")(k,l)
+    #                                  == {88.2, 96.4, 0.0, 0.0, 319.4, 335.8}
+    pos, crd, blocks = H.d3322a()
+    a = oracle.bspmv(pos, crd, blocks, H.d32b(), 2, 2)
+    H.assert_close(a.reshape(-1), np.array([88.2, 96.4, 0.0, 0.0, 319.4, 335.8]), np.float64)
+    # the same statement as a one-column blocked SpMM
+    C = oracle.bspmm(pos, crd, blocks, H.d32b().reshape(6, 1), 2, 2)
+    H.assert_close(C.reshape(-1), a.reshape(-1), np.float64)      # (different summation order: scalar temporary)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # 2. outputs of the reference itself
 # ---------------------------------------------------------------------------------------------------------
@@ -148,3 +159,19 @@ def test_golden_spgemm(name):
     cp, cc, cv = oracle.spgemm(g["A_pos"], g["A_crd"], g["A_vals"], g["B_pos"], g["B_crd"], g["B_vals"], int(g["dims"][2]))
     assert np.array_equal(cp, g["out_C_pos"]) and np.array_equal(cc, g["out_C_crd"]), "structure must be bit-exact"
     assert np.array_equal(cv, g["out_C_vals"])
+
+
+@pytest.mark.parametrize("name", H.golden_cases("bspmv"))
+def test_golden_bspmv(name):
+    g = H.load_golden(name)
+    Mb, Nb, br, bc = g["dims"]
+    a = oracle.bspmv(g["A_pos"], g["A_crd"], g["A_vals"].reshape(-1, br, bc), g["c"].reshape(Nb, bc), br, bc)
+    assert np.array_equal(a.reshape(-1), g["out_a"]), "default schedule: the oracle restates the operation order"
+
+
+@pytest.mark.parametrize("name", H.golden_cases("bspmm"))
+def test_golden_bspmm(name):
+    g = H.load_golden(name)
+    Mb, Nb, br, bc, K = g["dims"]
+    C = oracle.bspmm(g["A_pos"], g["A_crd"], g["A_vals"].reshape(-1, br, bc), g["B"].reshape(Nb * bc, K), br, bc)
+    assert np.array_equal(C.reshape(-1), g["out_C"]), "default schedule: the oracle restates the operation order"
