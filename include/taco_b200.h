@@ -82,7 +82,7 @@ int  taco_b200_launch_count(void);                /* number of kernels launched 
 
 /* Per-kernel device timing for bench.py's roofline line: when enabled, each dominant kernel launch is bracketed by
  * CUDA events on the launch stream.  kernel_name in {"spmv_csr","spmm_csr","sddmm_csr","mttkrp_csf","ttv_csf",
- * "ttm_csf","spadd_symbolic","spadd_numeric","spgemm_symbolic","spgemm_numeric"}. */
+ * "ttm_csf","bspmv_bcsr","bspmm_bcsr","spadd_symbolic","spadd_numeric","spgemm_symbolic","spgemm_numeric"}. */
 int  taco_b200_profile_enable(int on);
 int  taco_b200_profile_get(const char* kernel_name, double* total_ms, int* launches);
 int  taco_b200_profile_reset(void);
@@ -127,6 +127,19 @@ int taco_b200_sddmm_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* 
 int taco_b200_mttkrp_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 int taco_b200_mttkrp_compute (taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 int taco_b200_mttkrp_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
+
+/* a(i,j) = A(i,k,j,l) * c(k,l)  (blocked SpMV)   and   C(i,j,m) = A(i,k,j,l) * B(k,l,m)  (blocked SpMM)
+ * A = {Dense,Compressed,Dense,Dense} over (block row, block column, row in block, column in block), the blocked
+ * format of the reference's `bspmv` test (test/tests-expr_storage.cpp:939-960); c, a, B, C dense row-major; fp32 | fp64.
+ * Blocked SpMM is the one hot-path contraction that is dense inside a block: fp32 with 16x16 / 32x32 blocks runs on the
+ * tcgen05 tensor cores (3xTF32 split, fp32 accumulation in tensor memory); everything else keeps the reference's
+ * summation order on CUDA cores.  Replaces what CodeGen_CUDA emits for these statements (codegen_cuda.cpp:619-812). */
+int taco_b200_bspmv_assemble(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c);
+int taco_b200_bspmv_compute (taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c);
+int taco_b200_bspmv_evaluate(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c);
+int taco_b200_bspmm_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
+int taco_b200_bspmm_compute (taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
+int taco_b200_bspmm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
 
 /* A(i,j) = B(i,j,k) * c(k)  (TTV)   and   A(i,j,l) = B(i,j,k) * C(k,l)  (TTM);  B CSF, A dense
  * replace scheduleTTVGPU (:308-325) and scheduleTTMGPU (:289-306) */
@@ -179,6 +192,8 @@ int _shim_taco_b200_sddmm_assemble(void** p);  int _shim_taco_b200_sddmm_compute
 int _shim_taco_b200_mttkrp_assemble(void** p); int _shim_taco_b200_mttkrp_compute(void** p); int _shim_taco_b200_mttkrp_evaluate(void** p);
 int _shim_taco_b200_ttv_assemble(void** p);    int _shim_taco_b200_ttv_compute(void** p);    int _shim_taco_b200_ttv_evaluate(void** p);
 int _shim_taco_b200_ttm_assemble(void** p);    int _shim_taco_b200_ttm_compute(void** p);    int _shim_taco_b200_ttm_evaluate(void** p);
+int _shim_taco_b200_bspmv_assemble(void** p);  int _shim_taco_b200_bspmv_compute(void** p);  int _shim_taco_b200_bspmv_evaluate(void** p);
+int _shim_taco_b200_bspmm_assemble(void** p);  int _shim_taco_b200_bspmm_compute(void** p);  int _shim_taco_b200_bspmm_evaluate(void** p);
 int _shim_taco_b200_spadd_assemble(void** p);  int _shim_taco_b200_spadd_compute(void** p);  int _shim_taco_b200_spadd_evaluate(void** p);
 int _shim_taco_b200_spgemm_assemble(void** p); int _shim_taco_b200_spgemm_compute(void** p); int _shim_taco_b200_spgemm_evaluate(void** p);
 

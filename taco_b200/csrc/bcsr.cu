@@ -1,0 +1,535 @@
+// bcsr.cu -- blocked SpMV / SpMM over the reference's blocked format {Dense, Compressed, Dense, Dense}
+//   a(i,j)   = A(i,k,j,l) * c(k,l)        (the reference's `bspmv` statement, /root/reference/test/tests-expr_storage.cpp:939-960)
+//   C(i,j,m) = A(i,k,j,l) * B(k,l,m)      (blocked SpMM: the one hot-path contraction that is DENSE inside a block)
+// A is order 4 over (block row i, block column k, row in block j, column in block l): pos = int32[Mb+1] and crd over the
+// block columns, vals = [stored blocks][br][bc]; B = (Nb, bc, K) and C = (Mb, br, K) are dense, i.e. row-major
+// (Nb*bc) x K and (Mb*br) x K matrices.
+//
+// Two kernels:
+//   * bspmm_rows_kernel (fp32 / fp64, any block shape): CUDA cores, the reference's summation order (block by block,
+//     then column l inside the block, separate multiply and add) -> bit-identical to the reference's generated C.
+//   * bspmm_tc_kernel (fp32, 16x16 and 32x32 blocks, K % 4 == 0): tcgen05 tensor cores.  The block product is computed
+//     transposed, D[k', i2] += Bt[k', j2] * At[j2, i2], so the MMA's M dimension is the 128-wide tile of dense columns
+//     (always full) and its N dimension is the block height.  fp32 inputs are split into two TF32 terms
+//     (x = hi + lo, hi = top 19 bits) and three MMAs (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory, which
+//     keeps the result within the fp32 tolerance of the north star (1e-5 relative; a single TF32 pass would be 1e-3).
+//     Warp-specialised: 8 producer warps (global -> registers -> hi/lo split -> K-major canonical UMMA layouts in smem, the B
+//     tile transposed on the fly, mbarrier ring), 1 MMA warp (one thread issues tcgen05.mma, tcgen05.commit frees stages), 4 epilogue warps (tcgen05.ld of
+//     the accumulator, coalesced 128-byte stores), two accumulators in TMEM so the epilogue of one block row overlaps
+//     the MMAs of the next.
+// Algorithmic bytes per launch: 4(Mb+1) + nnzb*(4 + br*bc*es) + es*K*(Nb*bc + Mb*br).
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace tb {
+
+struct BcsrView { int32_t Mb, Nb, br, bc; int32_t* pos; int32_t* crd; void* vals; DType dt; };
+
+static int view_bcsr(const taco_tensor_t* t, const char* name, BcsrView* v) {
+  if (!t) return fail(TACO_B200_ERR_ARG, "%s: NULL tensor", name);
+  if (t->order != 4 || t->mode_types[0] != taco_mode_dense || t->mode_types[1] != taco_mode_sparse ||
+      t->mode_types[2] != taco_mode_dense || t->mode_types[3] != taco_mode_dense)
+    return fail(TACO_B200_ERR_FORMAT, "%s: expected blocked CSR ({Dense,Compressed,Dense,Dense})", name);
+  for (int l = 0; l < 4; l++)
+    if (t->mode_ordering[l] != l) return fail(TACO_B200_ERR_FORMAT, "%s: blocked CSR needs mode ordering 0,1,2,3", name);
+  v->Mb = t->dimensions[0]; v->Nb = t->dimensions[1]; v->br = t->dimensions[2]; v->bc = t->dimensions[3];
+  if (v->Mb < 0 || v->Nb < 0 || v->br <= 0 || v->bc <= 0) return fail(TACO_B200_ERR_ARG, "%s: bad dimension", name);
+  v->pos = t->indices && t->indices[1] ? (int32_t*)t->indices[1][0] : nullptr;
+  v->crd = t->indices && t->indices[1] ? (int32_t*)t->indices[1][1] : nullptr;
+  v->vals = t->vals;
+  return dtype_of(t, &v->dt);
+}
+
+// number of stored blocks: pos[Mb] (device-resident tensors carry it in vals_size = blocks * br * bc)
+static int bcsr_nnzb(const BcsrView& A, int32_t vals_size_hint, int32_t* nnzb) {
+  if (!A.pos) return fail(TACO_B200_ERR_ARG, "blocked CSR operand has no pos array");
+  if (classify(A.pos) == Mem::Device && vals_size_hint > 0) { *nnzb = vals_size_hint / (A.br * A.bc); return TACO_B200_OK; }
+  return read_i32(A.pos + A.Mb, nnzb);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-core kernels (reference order)
+// ---------------------------------------------------------------------------------------------------------
+// One thread per result row (i, j): tl = sum_l A[kA][j][l] * c[k][l] (scalar temporary), a[i,j] = a[i,j] + tl.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bspmv_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
+             const T* __restrict__ c, T* __restrict__ a, int Mb, int br, int bc) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)Mb * br) return;
+  const int i = (int)(t / br), j = (int)(t % br);
+  T acc = T(0);
+  for (int kA = __ldg(pos + i); kA < __ldg(pos + i + 1); kA++) {
+    const T* blk = vals + ((size_t)kA * br + j) * bc;
+    const T* cr = c + (size_t)__ldg(crd + kA) * bc;
+    T tl = T(0);
+    for (int l = 0; l < bc; l++) tl = tl + __ldg(blk + l) * __ldg(cr + l);
+    acc = acc + tl;
+  }
+  a[t] = acc;
+}
+
+// CTA = one block row x one tile of TK dense columns.  Warp w owns the rows j = w, w + WARPS, ... (RJ accumulators per
+// lane and column), lanes own columns.  The A block is staged in shared memory (broadcast reads), a row of B is read
+// once per (block, l) and applied to all rows the warp owns.  Order per result: blocks ascending, then l ascending.
+template <typename T, int WARPS, int RJ>
+__global__ void __launch_bounds__(WARPS * 32)
+bspmm_rows_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
+                  const T* __restrict__ B, T* __restrict__ C, int br, int bc, int K) {
+  extern __shared__ __align__(16) unsigned char bs_smem[];
+  T* sA = (T*)bs_smem;                                   // [br * bc]
+  const int i = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.y * 32 + lane;
+  const bool active = m < K;
+  const int p0 = __ldg(pos + i), p1 = __ldg(pos + i + 1);
+  for (int j0 = 0; j0 < br; j0 += WARPS * RJ) {           // row groups (one pass when br <= WARPS * RJ)
+    T acc[RJ];
+#pragma unroll
+    for (int r = 0; r < RJ; r++) acc[r] = T(0);
+    for (int kA = p0; kA < p1; kA++) {
+      __syncthreads();
+      for (int q = threadIdx.x; q < br * bc; q += WARPS * 32) sA[q] = __ldg(vals + (size_t)kA * br * bc + q);
+      __syncthreads();
+      const T* bk = B + (size_t)__ldg(crd + kA) * bc * K + (active ? m : 0);
+      for (int l = 0; l < bc; l++) {
+        const T b = __ldg(bk + (size_t)l * K);
+#pragma unroll
+        for (int r = 0; r < RJ; r++) {
+          const int j = j0 + w + r * WARPS;
+          if (j < br) acc[r] = acc[r] + sA[j * bc + l] * b;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RJ; r++) {
+      const int j = j0 + w + r * WARPS;
+      if (j < br && active) C[((size_t)i * br + j) * K + m] = acc[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------------------
+namespace tc {
+
+constexpr int TILE_K = 128;                  // dense columns per CTA tile = the MMA's M
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS;          // warp 4
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra WAIT_DONE;\nbra WAIT_LOOP;\n"
+      "WAIT_DONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {   // arrives on `bar` when all MMAs issued so far have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), leading byte offset
+// >> 4 at [16,30), stride byte offset >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+
+template <int BR, int BC>
+struct Cfg {
+  static_assert(BR % 16 == 0 && BR >= 16 && BR <= 64, "block height = MMA N: multiple of 16");
+  static_assert(BC >= 8 && BC <= 64 && (BC & (BC - 1)) == 0, "block width: power of two, multiple of the TF32 MMA K (8)");
+  static constexpr int BT_BYTES = BC * TILE_K * 4;        // one B tile (BC rows x 128 columns), hi or lo
+  static constexpr int AB_BYTES = BR * BC * 4;            // one A block, hi or lo
+  static constexpr int STAGE_BYTES = 2 * BT_BYTES + 2 * AB_BYTES;
+  // Both operands are K-major, no swizzle (measured with tools/tc_probe.cu: the MN-major / "transpose" bit yields zeros
+  // for kind::tf32): core matrix = 8 rows x 16 bytes (4 j2); SBO = stride between 8-row groups, LBO = stride between
+  // the two 16-byte chunks of one K = 8 step.  Chunk jc of row group g lives at (jc * groups + g) * 128.
+  static constexpr int BT_SBO = 128;
+  static constexpr int BT_LBO = (TILE_K / 8) * 128;       // B tile transposed: rows = dense columns k' (16 groups)
+  static constexpr int AB_SBO = 128;
+  static constexpr int AB_LBO = (BR / 8) * 128;           // A block: rows = rows of the block
+  static constexpr int TMEM_COLS = 2 * BR < 32 ? 32 : 2 * BR;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B TF32, both K-major, N = BR, M = 128
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BR >> 3) << 17) |
+                                    ((uint32_t)(TILE_K >> 4) << 24);
+};
+
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int BR, int BC, int STAGES>
+__global__ void __launch_bounds__(THREADS)
+bspmm_tc_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const float* __restrict__ vals,
+                const float* __restrict__ B, float* __restrict__ C, int Mb, int K) {
+  using CF = Cfg<BR, BC>;
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const uint32_t bars = smem0 + STAGES * CF::STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.y * TILE_K;                                // first dense column of this CTA's tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), PROD_WARPS * 32); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(CF::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < EPI_WARPS) {
+    // ===== epilogue: accumulator (TMEM lane = dense column k', TMEM column = row in block) -> C ======================
+    const int col = k0 + warp * 32 + lane;
+    uint32_t acc_it = 0;
+    for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+      const int n = __ldg(pos + i1 + 1) - __ldg(pos + i1);
+      float* crow = C + (size_t)i1 * BR * K + col;
+      if (n == 0) {                                                  // empty block row: its owner writes the zeros
+        if (col < K) for (int j = 0; j < BR; j++) crow[(size_t)j * K] = 0.0f;
+        continue;
+      }
+      const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + a * BR;
+      uint32_t v[BR];
+#pragma unroll
+      for (int c = 0; c < BR; c += 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[c + 0]), "=r"(v[c + 1]), "=r"(v[c + 2]), "=r"(v[c + 3]), "=r"(v[c + 4]), "=r"(v[c + 5]), "=r"(v[c + 6]),
+              "=r"(v[c + 7]), "=r"(v[c + 8]), "=r"(v[c + 9]), "=r"(v[c + 10]), "=r"(v[c + 11]), "=r"(v[c + 12]),
+              "=r"(v[c + 13]), "=r"(v[c + 14]), "=r"(v[c + 15])
+            : "r"(taddr + c) : "memory");
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));                                    // the MMA warp may overwrite this accumulator
+      if (col < K) {
+#pragma unroll
+        for (int j = 0; j < BR; j++) crow[(size_t)j * K] = __uint_as_float(v[j]);     // 128 bytes per warp and row
+      }
+      acc_it++;
+    }
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer (one thread) =====================================================================================
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+        const int n = __ldg(pos + i1 + 1) - __ldg(pos + i1);
+        if (n == 0) continue;
+        const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);                           // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BR;
+        for (int b = 0; b < n; b++, it++) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = smem0 + s * CF::STAGE_BYTES;
+          const uint32_t bt_hi = st, bt_lo = st + CF::BT_BYTES, ab_hi = st + 2 * CF::BT_BYTES, ab_lo = ab_hi + CF::AB_BYTES;
+#pragma unroll
+          for (int g = 0; g < BC / 8; g++) {                         // one TF32 MMA consumes 8 columns of the block
+            const uint32_t ao = g * 2 * CF::BT_LBO, bo = g * 2 * CF::AB_LBO;
+            const uint64_t a_hi = smem_desc(bt_hi + ao, CF::BT_LBO, CF::BT_SBO), a_lo = smem_desc(bt_lo + ao, CF::BT_LBO, CF::BT_SBO);
+            const uint64_t b_hi = smem_desc(ab_hi + bo, CF::AB_LBO, CF::AB_SBO), b_lo = smem_desc(ab_lo + bo, CF::AB_LBO, CF::AB_SBO);
+            tc_mma_tf32(d_tmem, a_lo, b_hi, CF::IDESC, (b | g) != 0);          // small terms first
+            tc_mma_tf32(d_tmem, a_hi, b_lo, CF::IDESC, 1);
+            tc_mma_tf32(d_tmem, a_hi, b_hi, CF::IDESC, 1);
+          }
+          tc_commit(empty_bar(s));                                   // stage is free once these MMAs have read it
+        }
+        tc_commit(tfull_bar(a));                                     // accumulator complete
+        acc_it++;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== producers: global -> registers -> (hi, lo) -> canonical UMMA layouts in shared memory ====================
+    const int pt = threadIdx.x - (EPI_WARPS + 1) * 32;               // 0 .. 255
+    const int pw = pt >> 5;
+    const int r = lane & 7, q = lane >> 3;                           // A block: 8 rows x 4 chunks per warp access
+    const int kq = pt & (TILE_K - 1), half = pt >> 7;                // B tile: thread <-> dense column k', half of the chunks
+    constexpr int BT_PER = (BC / 4 + 1) / 2;                         // 4-row chunks of the B tile per thread
+    constexpr int AB_CG = BC / 16 > 0 ? BC / 16 : 1;                 // warp accesses per 8-row group of the A block
+    constexpr int AB_ITERS = (BR / 8) * AB_CG;
+    constexpr int AB_PER = (AB_ITERS + PROD_WARPS - 1) / PROD_WARPS;
+    const bool col_ok = k0 + kq < K;
+    uint32_t it = 0;
+    for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+      const int p0 = __ldg(pos + i1), p1 = __ldg(pos + i1 + 1);
+      for (int p = p0; p < p1; p++, it++) {
+        const int j1 = __ldg(crd + p);
+        // B tile, transposed on the fly: a thread reads ONE column k' of 4 consecutive rows (a warp reads 128 contiguous
+        // bytes per row) and owns the 16-byte chunk (k', j2 = 4 jc .. 4 jc + 3) of the K-major operand
+        float4 xb[BT_PER], xa[AB_PER];
+        const float* bcol = B + (size_t)j1 * BC * K + k0 + kq;
+#pragma unroll
+        for (int u = 0; u < BT_PER; u++) {
+          const int jc = half + 2 * u;
+          xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && jc < BC / 4) {
+            const float* b4 = bcol + (size_t)(4 * jc) * K;
+            xb[u].x = __ldg(b4); xb[u].y = __ldg(b4 + K); xb[u].z = __ldg(b4 + 2 * (size_t)K); xb[u].w = __ldg(b4 + 3 * (size_t)K);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < AB_PER; u++) {
+          const int acc_id = pw + u * PROD_WARPS;
+          xa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (acc_id < AB_ITERS) {
+            const int ig = acc_id / AB_CG, cg = acc_id % AB_CG;
+            const int i2 = ig * 8 + r, jc = cg * 4 + q;
+            if (jc < BC / 4) xa[u] = tbd::ldg_stream_f4(vals + ((size_t)p * BR + i2) * BC + jc * 4);
+          }
+        }
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t st = smem0 + s * CF::STAGE_BYTES;
+#pragma unroll
+        for (int u = 0; u < BT_PER; u++) {
+          const int jc = half + 2 * u;
+          if (jc < BC / 4) {
+            float4 hi, lo;
+            split_tf32(xb[u], hi, lo);
+            const uint32_t off = (uint32_t)(jc * (TILE_K / 8) + (kq >> 3)) * 128 + (uint32_t)(kq & 7) * 16;
+            sts_f4(st + off, hi);
+            sts_f4(st + CF::BT_BYTES + off, lo);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < AB_PER; u++) {
+          const int acc_id = pw + u * PROD_WARPS;
+          if (acc_id < AB_ITERS) {
+            const int ig = acc_id / AB_CG, cg = acc_id % AB_CG;
+            const int jc = cg * 4 + q;
+            if (jc < BC / 4) {
+              float4 hi, lo;
+              split_tf32(xa[u], hi, lo);
+              const uint32_t off = (uint32_t)(jc * (BR / 8) + ig) * 128 + (uint32_t)r * 16;
+              sts_f4(st + 2 * CF::BT_BYTES + off, hi);
+              sts_f4(st + 2 * CF::BT_BYTES + CF::AB_BYTES + off, lo);
+            }
+          }
+        }
+        fence_async_smem();                                          // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(full_bar(s));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
+  }
+}
+
+template <int BR, int BC, int STAGES>
+static int launch(const int* pos, const int* crd, const float* vals, const float* B, float* C, int Mb, int K, int ctas_per_sm) {
+  using CF = Cfg<BR, BC>;
+  const int smem = STAGES * CF::STAGE_BYTES + 8 * (2 * STAGES + 4) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TB_CUDA(cudaFuncSetAttribute(bspmm_tc_kernel<BR, BC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int gx = num_sms() * ctas_per_sm;
+  const int gy = (K + TILE_K - 1) / TILE_K;
+  gx = (gx + gy - 1) / gy;
+  if (gx > Mb) gx = Mb;
+  if (gx < 1) gx = 1;
+  bspmm_tc_kernel<BR, BC, STAGES><<<dim3(gx, gy), THREADS, smem, stream()>>>(pos, crd, vals, B, C, Mb, K);
+  return TACO_B200_OK;
+}
+
+}  // namespace tc
+
+// TACO_B200_BSPMM_TC=0 forces the CUDA-core kernel (reference order), =1 (default) uses tensor cores where they apply.
+static bool tc_enabled() {
+  static const int v = getenv("TACO_B200_BSPMM_TC") ? atoi(getenv("TACO_B200_BSPMM_TC")) : 1;
+  return v != 0;
+}
+
+template <typename T>
+static int bspmm_launch(const BcsrView& A, const int* pos, const int* crd, const T* vals, const T* B, T* C, int K) {
+  if (A.Mb == 0 || K == 0) return TACO_B200_OK;
+  ProfScope ps("bspmm_bcsr");
+  if constexpr (sizeof(T) == 4) {
+    const bool aligned = (K % 4 == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)vals & 15) == 0);
+    static const int variant = getenv("TACO_B200_BSPMM_VARIANT") ? atoi(getenv("TACO_B200_BSPMM_VARIANT")) : 0;
+    if (tc_enabled() && aligned) {
+      if (A.br == 32 && A.bc == 32) {
+        count_launch(1);
+        if (variant == 1) return tc::launch<32, 32, 2>(pos, crd, vals, B, C, A.Mb, K, 2);
+        return tc::launch<32, 32, 4>(pos, crd, vals, B, C, A.Mb, K, 1);
+      }
+      if (A.br == 16 && A.bc == 16) {
+        count_launch(1);
+        if (variant == 1) return tc::launch<16, 16, 4>(pos, crd, vals, B, C, A.Mb, K, 2);
+        return tc::launch<16, 16, 8>(pos, crd, vals, B, C, A.Mb, K, 1);
+      }
+    }
+  }
+  constexpr int WARPS = 8, RJ = 4;
+  const size_t smem = sizeof(T) * (size_t)A.br * A.bc;
+  if (smem > 48 * 1024) return fail(TACO_B200_ERR_UNSUPPORTED, "bspmm: blocks larger than 48 KB are not supported");
+  dim3 grid(A.Mb, (K + 31) / 32);
+  bspmm_rows_kernel<T, WARPS, RJ><<<grid, WARPS * 32, smem, stream()>>>(pos, crd, vals, B, C, A.br, A.bc, K);
+  count_launch(1);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
+static int bspmm_views(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B, DenseView* Cv, BcsrView* Av, DenseView* Bv) {
+  TB_TRY(ensure_init());
+  TB_TRY(view_dense(C, 3, "C", Cv));
+  TB_TRY(view_bcsr(A, "A", Av));
+  TB_TRY(view_dense(B, 3, "B", Bv));
+  for (int l = 0; l < 3; l++)
+    if (Cv->mode_order[l] != l || Bv->mode_order[l] != l) return fail(TACO_B200_ERR_FORMAT, "bspmm: B and C must be row-major");
+  if (Cv->dim[0] != Av->Mb || Cv->dim[1] != Av->br || Bv->dim[0] != Av->Nb || Bv->dim[1] != Av->bc || Cv->dim[2] != Bv->dim[2])
+    return fail(TACO_B200_ERR_ARG, "bspmm: dimension mismatch C[%d x %d x %d] = A[%d x %d x %d x %d] * B[%d x %d x %d]", Cv->dim[0],
+                Cv->dim[1], Cv->dim[2], Av->Mb, Av->Nb, Av->br, Av->bc, Bv->dim[0], Bv->dim[1], Bv->dim[2]);
+  if (Cv->dt != Av->dt || Bv->dt != Av->dt) return fail(TACO_B200_ERR_FORMAT, "bspmm: mixed component types");
+  return TACO_B200_OK;
+}
+
+static int bspmv_views(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c, DenseView* av, BcsrView* Av, DenseView* cv) {
+  TB_TRY(ensure_init());
+  TB_TRY(view_dense(a, 2, "a", av));
+  TB_TRY(view_bcsr(A, "A", Av));
+  TB_TRY(view_dense(c, 2, "c", cv));
+  for (int l = 0; l < 2; l++)
+    if (av->mode_order[l] != l || cv->mode_order[l] != l) return fail(TACO_B200_ERR_FORMAT, "bspmv: a and c must be row-major");
+  if (av->dim[0] != Av->Mb || av->dim[1] != Av->br || cv->dim[0] != Av->Nb || cv->dim[1] != Av->bc)
+    return fail(TACO_B200_ERR_ARG, "bspmv: dimension mismatch a[%d x %d] = A[%d x %d x %d x %d] * c[%d x %d]", av->dim[0], av->dim[1],
+                Av->Mb, Av->Nb, Av->br, Av->bc, cv->dim[0], cv->dim[1]);
+  if (av->dt != Av->dt || cv->dt != Av->dt) return fail(TACO_B200_ERR_FORMAT, "bspmv: mixed component types");
+  return TACO_B200_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int taco_b200_bspmm_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  DenseView Cv, Bv; BcsrView Av;
+  TB_TRY(bspmm_views(C, A, B, &Cv, &Av, &Bv));
+  void* p = result_alloc(Cv.count() * dsize(Cv.dt));
+  if (!p) return fail(TACO_B200_ERR_ALLOC, "bspmm: cannot allocate result");
+  C->vals = (uint8_t*)p;
+  return TACO_B200_OK;
+}
+
+int taco_b200_bspmm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  DenseView Cv, Bv; BcsrView Av;
+  TB_TRY(bspmm_views(C, A, B, &Cv, &Av, &Bv));
+  int32_t nnzb = 0;
+  TB_TRY(bcsr_nnzb(Av, A->vals_size, &nnzb));
+  if (nnzb < 0 || (long long)nnzb * Av.br * Av.bc > (long long)INT32_MAX * 16) return fail(TACO_B200_ERR_ARG, "bspmm: bad block count %d", nnzb);
+  if (!Cv.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  const int K = Bv.dim[2];
+  const size_t es = dsize(Av.dt);
+  In pos, crd, vals, bin; Out cout;
+  TB_TRY(pos.acquire(Av.pos, sizeof(int32_t) * ((size_t)Av.Mb + 1)));
+  TB_TRY(crd.acquire(Av.crd ? (void*)Av.crd : (void*)Av.pos, sizeof(int32_t) * (size_t)nnzb));
+  TB_TRY(vals.acquire(Av.vals ? Av.vals : (void*)Av.pos, es * (size_t)nnzb * Av.br * Av.bc));
+  TB_TRY(bin.acquire(Bv.vals, es * (size_t)Av.Nb * Av.bc * K));
+  TB_TRY(cout.acquire(Cv.vals, es * (size_t)Av.Mb * Av.br * K));
+  if (Av.dt == DType::F32)
+    TB_TRY(bspmm_launch<float>(Av, pos.as<int>(), crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(), K));
+  else
+    TB_TRY(bspmm_launch<double>(Av, pos.as<int>(), crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(), K));
+  TB_CUDA(cudaGetLastError());
+  TB_TRY(cout.commit());
+  return finish_call();
+}
+
+int taco_b200_bspmm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  TB_TRY(taco_b200_bspmm_assemble(C, A, B));
+  return taco_b200_bspmm_compute(C, A, B);
+}
+
+int taco_b200_bspmv_assemble(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c) {
+  DenseView av, cv; BcsrView Av;
+  TB_TRY(bspmv_views(a, A, c, &av, &Av, &cv));
+  void* p = result_alloc(av.count() * dsize(av.dt));
+  if (!p) return fail(TACO_B200_ERR_ALLOC, "bspmv: cannot allocate result");
+  a->vals = (uint8_t*)p;
+  return TACO_B200_OK;
+}
+
+int taco_b200_bspmv_compute(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c) {
+  DenseView av, cv; BcsrView Av;
+  TB_TRY(bspmv_views(a, A, c, &av, &Av, &cv));
+  int32_t nnzb = 0;
+  TB_TRY(bcsr_nnzb(Av, A->vals_size, &nnzb));
+  if (nnzb < 0) return fail(TACO_B200_ERR_ARG, "bspmv: bad block count %d", nnzb);
+  if (!av.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  const size_t es = dsize(Av.dt);
+  In pos, crd, vals, cin; Out aout;
+  TB_TRY(pos.acquire(Av.pos, sizeof(int32_t) * ((size_t)Av.Mb + 1)));
+  TB_TRY(crd.acquire(Av.crd ? (void*)Av.crd : (void*)Av.pos, sizeof(int32_t) * (size_t)nnzb));
+  TB_TRY(vals.acquire(Av.vals ? Av.vals : (void*)Av.pos, es * (size_t)nnzb * Av.br * Av.bc));
+  TB_TRY(cin.acquire(cv.vals, es * (size_t)Av.Nb * Av.bc));
+  TB_TRY(aout.acquire(av.vals, es * (size_t)Av.Mb * Av.br));
+  const long long rows = (long long)Av.Mb * Av.br;
+  if (rows > 0) {
+    ProfScope ps("bspmv_bcsr");
+    const int grid = (int)((rows + 255) / 256);
+    if (Av.dt == DType::F32)
+      bspmv_kernel<float><<<grid, 256, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<float>(), cin.as<float>(), aout.as<float>(),
+                                                     Av.Mb, Av.br, Av.bc);
+    else
+      bspmv_kernel<double><<<grid, 256, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<double>(), cin.as<double>(),
+                                                      aout.as<double>(), Av.Mb, Av.br, Av.bc);
+    count_launch(1);
+    TB_CUDA(cudaGetLastError());
+  }
+  TB_TRY(aout.commit());
+  return finish_call();
+}
+
+int taco_b200_bspmv_evaluate(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c) {
+  TB_TRY(taco_b200_bspmv_assemble(a, A, c));
+  return taco_b200_bspmv_compute(a, A, c);
+}
+
+}  // extern "C"

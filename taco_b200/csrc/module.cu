@@ -41,6 +41,8 @@ static const Family kFamilies[] = {
     {"mttkrp", "T0(a,b)=T1(a,c,d)*T2(c,b)*T3(d,b)",   {"dd", "sss", "dd", "dd"}, 4, TB_FAM3(mttkrp)},
     {"ttv",    "T0(a,b)=T1(a,b,c)*T2(c)",             {"dd", "sss", "d", ""},    3, TB_FAM3(ttv)},
     {"ttm",    "T0(a,b,c)=T1(a,b,d)*T2(d,c)",         {"ddd", "sss", "dd", ""},  3, TB_FAM3(ttm)},
+    {"bspmv",  "T0(a,b)=T1(a,c,b,d)*T2(c,d)",         {"dd", "dsdd", "dd", ""},  3, TB_FAM3(bspmv)},
+    {"bspmm",  "T0(a,b,c)=T1(a,d,b,e)*T2(d,e,c)",     {"ddd", "dsdd", "ddd", ""}, 3, TB_FAM3(bspmm)},
 };
 
 // "y(i) = A(i,j) * x(j)"  ->  canonical "T0(a)=T1(a,b)*T2(b)" + tensor names in order of first appearance
@@ -262,7 +264,7 @@ const char* taco_b200_module_stub_source(taco_b200_module_t* m) {
   }
 #define TB_SHIMS3(n) TB_SHIM3(n, assemble) TB_SHIM3(n, compute) TB_SHIM3(n, evaluate)
 #define TB_SHIMS4(n) TB_SHIM4(n, assemble) TB_SHIM4(n, compute) TB_SHIM4(n, evaluate)
-TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS4(sddmm) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm)
+TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS4(sddmm) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm) TB_SHIMS3(bspmv) TB_SHIMS3(bspmm)
 
 }  // extern "C"
 

@@ -13,6 +13,7 @@ Configs ("workloads"):
   C3 sddmm  fp32  n x n CSR `deg` per row (as C1);  C, D dense n x K
   C4 mttkrp fp64  order-3 I x K x L, coordinates uniform, sorted, duplicates removed, CSF;  C, D dense x R
   C5 spadd / spgemm fp64  two independent C1-style matrices
+  (f)1 bspmm fp32  blocked CSR {Dense,Compressed,Dense,Dense}: C1-style block structure, dense 32 x 32 blocks
 Values are k/1024 with k uniform in [1, 1024] (well-conditioned sums, never zero).
 """
 import numpy as np
@@ -310,6 +311,8 @@ FULL = {
     "mttkrp": dict(I=10_000_000, K=1_000_000, L=1_000_000, nnz=200_000_000, R=32, dtype="float64"),
     "spadd": dict(n=1_000_000, deg=10, dtype="float64"),
     "spgemm": dict(n=1_000_000, deg=10, dtype="float64"),
+    # blocked SpMM: 1Mi x 1Mi in 32 x 32 blocks, 16 stored blocks per block row, K = 128
+    "bspmm": dict(Mb=32768, deg=16, br=32, bc=32, K=128, dtype="float32"),
 }
 
 
@@ -340,4 +343,11 @@ def make(workload, device=None, **over):
         bp, bc, bv = csr_fixed_degree(xp, p["n"], p["n"], p["deg"], SEED0 + 18, dt)
         dims = (p["n"], p["n"]) if workload == "spadd" else (p["n"], p["n"], p["n"])
         return dict(dims=dims, A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv)
+    if workload == "bspmm":
+        Mb, br, bc = p["Mb"], p["br"], p["bc"]
+        pos, crd, _ = csr_fixed_degree(xp, Mb, Mb, p["deg"], SEED0 + 20, dt)
+        nnzb = Mb * p["deg"]
+        return dict(dims=(Mb, Mb, br, bc, p["K"]), A_pos=pos, A_crd=crd,
+                    A_vals=values(xp, xp.arange(nnzb * br * bc), SEED0 + 21, dt),
+                    B=dense(xp, Mb * bc, p["K"], SEED0 + 22, dt))
     raise KeyError(workload)

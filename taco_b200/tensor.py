@@ -50,6 +50,7 @@ class Format:
 
 CSR = Format([dense, compressed])
 CSF3 = Format([compressed, compressed, compressed])
+BCSR = Format([dense, compressed, dense, dense])      # (block row, block column, row in block, column in block)
 
 
 def _is_torch(a):
@@ -251,6 +252,15 @@ def makeCSF3(name, dims, arrays):
     t = Tensor(name, dims, CSF3, dt)
     for l in range(3):
         t.set_level(l, arrays[f"B{l + 1}_pos"], arrays[f"B{l + 1}_crd"])
+    t.set_vals(vals)
+    return t
+
+
+def makeBCSR(name, dims, pos, crd, vals):
+    """dims = [Mb, Nb, br, bc]; pos/crd over the block columns, vals = [stored blocks * br * bc] (zero-copy attach)."""
+    dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
+    t = Tensor(name, dims, BCSR, dt)
+    t.set_level(1, pos, crd)
     t.set_vals(vals)
     return t
 

@@ -18,6 +18,8 @@ EXPR = {
     "ttm": "A(i,j,l) = B(i,j,k) * C(k,l)",
     "spadd": "C(i,j) = A(i,j) + B(i,j)",
     "spgemm": "C(i,k) = A(i,j) * B(j,k)",
+    "bspmv": "a(i,j) = A(i,k,j,l) * c(k,l)",
+    "bspmm": "C(i,j,m) = A(i,k,j,l) * B(k,l,m)",
 }
 
 
@@ -93,6 +95,17 @@ def build(family, w, colmajor_c=False):
         B = tb.makeCSR("B", bd, w["B_pos"], w["B_crd"], w["B_vals"])
         C = tb.Tensor("C", [d[0], bd[1]], tb.CSR, dt)
         ts = [C, A, B]
+    elif family in ("bspmv", "bspmm"):
+        dt = np_dtype(w["A_vals"])
+        A = tb.makeBCSR("A", d[:4], w["A_pos"], w["A_crd"], w["A_vals"])
+        if family == "bspmv":
+            c = tb.makeDense("c", [d[1], d[3]], w["c"])
+            a = tb.Tensor("a", [d[0], d[2]], tb.Format([tb.dense, tb.dense]), dt)
+            ts = [a, A, c]
+        else:
+            B = tb.makeDense("B", [d[1], d[3], d[4]], w["B"])
+            C = tb.Tensor("C", [d[0], d[2], d[4]], tb.Format([tb.dense] * 3), dt)
+            ts = [C, A, B]
     else:
         raise KeyError(family)
     return tb.compile(EXPR[family], *ts), ts

@@ -53,6 +53,8 @@ CASES = [
     ("A(i,j) = B(i,k,l) * C(k,j) * D(l,j)", "B:sss", "mttkrp"),
     ("A(i,j) = B(i,j,k) * c(k)", "B:sss", "ttv"),
     ("A(i,j,l) = B(i,j,k) * C(k,l)", "B:sss", "ttm"),
+    ("a(i,j) = B(i,k,j,l) * c(k,l)", "B:dsdd", "bspmv"),                 # the reference's blocked SpMV statement
+    ("C(i,j,m) = A(i,k,j,l) * B(k,l,m)", "A:dsdd,B:ddd,C:ddd", "bspmm"),
 ]
 
 

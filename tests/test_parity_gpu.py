@@ -411,3 +411,87 @@ def test_dropin_demo_through_unmodified_reference():
         pytest.skip("oracle/_ref (the compiled reference) was not shipped with this snapshot")
     r = subprocess.run([exe, tb.LIB_PATH], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------
+# blocked SpMV / SpMM (BCSR = {Dense,Compressed,Dense,Dense}), SURVEY.md 8(f) item 1
+# ---------------------------------------------------------------------------------------------------------
+def _uses_tensor_cores(br, bc, K, dtype):
+    return np.dtype(dtype) == np.float32 and (br, bc) in ((16, 16), (32, 32)) and K % 4 == 0
+
+
+def _bspmm_check(C, want, br, bc, K, dtype):
+    if _uses_tensor_cores(br, bc, K, dtype):
+        # tcgen05 path: three TF32 products per fp32 product, fp32 accumulation, reduction order differs from the
+        # reference -> north-star fp32 tolerance (1e-5), measured against the largest entry of the result row block
+        H.assert_close(C.reshape(-1), want.reshape(-1), np.float32, scale=float(np.max(np.abs(want))) if want.size else 1.0)
+    else:
+        assert np.array_equal(C.reshape(-1), want.reshape(-1)), "CUDA-core blocked SpMM keeps the reference's order"
+
+
+def test_kat_bspmv():
+    # tests-expr_storage.cpp:939-960
+    pos, crd, blocks = H.d3322a()
+    a = G.run("bspmv", dict(dims=[3, 3, 2, 2], A_pos=pos, A_crd=crd, A_vals=blocks.reshape(-1), c=H.d32b().reshape(-1)))
+    H.assert_close(a, np.array([88.2, 96.4, 0.0, 0.0, 319.4, 335.8]), np.float64)
+    assert np.array_equal(a, oracle.bspmv(pos, crd, blocks, H.d32b(), 2, 2).reshape(-1))
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("bspmv"))
+def test_golden_bspmv(name, space):
+    g = H.load_golden(name)
+    a = G.run("bspmv", place(_inputs(g), space))
+    assert np.array_equal(a, g["out_a"])
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("bspmm"))
+def test_golden_bspmm(name, space):
+    g = H.load_golden(name)
+    Mb, Nb, br, bc, K = [int(x) for x in g["dims"]]
+    C = G.run("bspmm", place(_inputs(g), space))
+    _bspmm_check(C, g["out_C"], br, bc, K, g["A_vals"].dtype)
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("br,bc,K,dtype", [(32, 32, 128, "float32"), (16, 16, 128, "float32"), (32, 32, 200, "float32"),
+                                           (16, 16, 36, "float32"), (32, 32, 64, "float64"), (8, 8, 50, "float32"),
+                                           (32, 32, 130, "float32"), (5, 3, 17, "float64")])
+def test_oracle_bspmm(space, br, bc, K, dtype):
+    w = synth.make("bspmm", None, Mb=300, deg=7, br=br, bc=bc, K=K, dtype=dtype)
+    w["A_pos"] = w["A_pos"].copy()
+    w["A_pos"][41:] -= 7                   # block row 40 becomes empty (its blocks are dropped below)
+    w["A_crd"] = np.delete(w["A_crd"], slice(40 * 7, 41 * 7))
+    w["A_vals"] = np.delete(w["A_vals"].reshape(-1, br, bc), slice(40 * 7, 41 * 7), axis=0).reshape(-1)
+    Mb = 300
+    C = G.run("bspmm", place(w, space))
+    want = oracle.bspmm(w["A_pos"], w["A_crd"], w["A_vals"].reshape(-1, br, bc), w["B"].reshape(Mb * bc, K), br, bc)
+    assert not want[40 * br:41 * br].any()
+    _bspmm_check(C, want, br, bc, K, dtype)
+
+
+def test_bspmm_tensor_core_path_is_accurate_on_signed_data():
+    # mixed-sign operands (cancellation): the 3xTF32 split must stay within 1e-5 of the fp32 result's scale
+    rng = np.random.default_rng(5)
+    Mb, Nb, br, bc, K = 64, 80, 32, 32, 128
+    A = (rng.standard_normal((Mb * br, Nb * bc)) * (rng.random((Mb, 1, Nb, 1)) < 0.2).repeat(br, 1).repeat(bc, 3).reshape(Mb * br, Nb * bc)).astype(np.float32)
+    p, c, v = formats.bcsr_from_dense(A, br, bc)
+    B = rng.standard_normal((Nb * bc, K)).astype(np.float32)
+    C = G.run("bspmm", dict(dims=[Mb, Nb, br, bc, K], A_pos=p, A_crd=c, A_vals=v.reshape(-1), B=B.reshape(-1)))
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    err = np.abs(C.reshape(Mb * br, K) - want).max() / np.abs(want).max()
+    assert err < 1e-5, err
+
+
+def test_bspmm_empty_and_errors():
+    z = np.zeros(0, np.float32)
+    C = G.run("bspmm", dict(dims=[3, 4, 16, 16, 8], A_pos=np.zeros(4, np.int32), A_crd=np.zeros(0, np.int32), A_vals=z,
+                            B=np.ones(4 * 16 * 8, np.float32)))
+    assert C.shape == (3 * 16 * 8,) and not C.any()
+    A = tb.makeBCSR("A", [3, 4, 16, 16], np.zeros(4, np.int32), np.zeros(0, np.int32), z)
+    B = tb.makeDense("B", [4, 8, 8], np.ones(4 * 8 * 8, np.float32))           # block width 8 != 16
+    Ct = tb.Tensor("C", [3, 16, 8], tb.Format([tb.dense] * 3), np.float32)
+    k = tb.compile(G.EXPR["bspmm"], Ct, A, B)
+    with pytest.raises(tb.TacoError):
+        k(Ct, A, B)
