@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the taco GPU hot path on B200, next to the reference's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm]
     python bench.py --impl reference ...          # the reference's own C/OpenMP codegen on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU; rank 0 prints the JSON line)
 
@@ -36,9 +36,10 @@ FLOPS = {   # per step, as the reference counts them
     "mttkrp": lambda s: 3.0 * s["nnz"] * s["R"],
     "spadd": lambda s: 1.0 * s["nnzC"],
     "spgemm": lambda s: 2.0 * s["products"],
+    "bspmm": lambda s: 2.0 * s["nnzb"] * s["br"] * s["bc"] * s["K"],
 }
 DOMINANT = {"spmv": "spmv_csr", "spmm": "spmm_csr", "sddmm": "sddmm_csr", "mttkrp": "mttkrp_csf",
-            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric"}
+            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr"}
 
 
 def algorithmic_bytes(wl, s):
@@ -56,6 +57,8 @@ def algorithmic_bytes(wl, s):
         return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * (4 + e) + 12 * (s["rows"] + 1)
     if wl == "spgemm":     # fill pass (sort + compress): A, the gathered B rows (crd + vals), the result, all pos arrays
         return (4 + e) * (s["nnzA"] + s["products"] + s["nnzC"]) + 12 * (s["rows"] + 1)
+    if wl == "bspmm":      # blocks streamed once, every row of B and C touched once
+        return 4 * (s["Mb"] + 1) + s["nnzb"] * (4 + e * s["br"] * s["bc"]) + e * s["K"] * (s["Nb"] * s["bc"] + s["Mb"] * s["br"])
     raise KeyError(wl)
 
 
@@ -71,6 +74,8 @@ def sizes_of(wl, w, extra=None):
     elif wl == "mttkrp":
         s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3], nnz=int(w["B3_crd"].shape[0]), nfib=int(w["B2_crd"].shape[0]),
                  nslices=int(w["B1_crd"].shape[0]))
+    elif wl == "bspmm":
+        s.update(Mb=d[0], Nb=d[1], br=d[2], bc=d[3], K=d[4], nnzb=int(w["A_crd"].shape[0]))
     else:
         s.update(rows=d[0], nnzA=int(w["A_crd"].shape[0]), nnzB=int(w["B_crd"].shape[0]))
     if extra:
@@ -139,7 +144,7 @@ def make_workload(wl, device, rank, scale_down):
     if scale_down:    # quick functional runs (tests); never used for reported numbers
         over = {"spmm": dict(scale=16), "spmv": dict(n=100_000), "sddmm": dict(n=100_000),
                 "mttkrp": dict(I=100_000, K=20_000, L=20_000, nnz=2_000_000), "spadd": dict(n=100_000),
-                "spgemm": dict(n=50_000)}[wl]
+                "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048)}[wl]
     old = synth.SEED0
     synth.SEED0 = old + 1000 * rank       # each rank owns a different row shard of the (N x larger) global operand
     try:
@@ -148,6 +153,10 @@ def make_workload(wl, device, rank, scale_down):
             synth.SEED0 = old
             n = w["dims"][1]
             w["B"] = synth.dense(synth.backend(device), n, w["dims"][2], synth.SEED0 + 4, np.dtype("float32"))
+        if rank and wl == "bspmm":
+            synth.SEED0 = old
+            w["B"] = synth.dense(synth.backend(device), w["dims"][1] * w["dims"][3], w["dims"][4], synth.SEED0 + 22,
+                                 np.dtype("float32"))
     finally:
         synth.SEED0 = old
     return w
@@ -175,6 +184,14 @@ def reference_sample(wl, w, budget_rows):
             h.update(B_pos=bpos, B_crd=G.to_host(w["B_crd"][:bz]), B_vals=G.to_host(w["B_vals"][:bz]))
         else:
             h.update(B_pos=G.to_host(w["B_pos"]), B_crd=G.to_host(w["B_crd"]), B_vals=G.to_host(w["B_vals"]))
+    elif wl == "bspmm":
+        rows = min(budget_rows, int(w["dims"][0]))
+        pos = G.to_host(w["A_pos"][: rows + 1])
+        nb = int(pos[-1])
+        bsz = int(w["dims"][2]) * int(w["dims"][3])
+        h.update(A_pos=pos, A_crd=G.to_host(w["A_crd"][:nb]), A_vals=G.to_host(w["A_vals"][: nb * bsz]), B=G.to_host(w["B"]))
+        dims = [rows] + [int(x) for x in w["dims"][1:]]
+        frac = nb / max(int(w["A_crd"].shape[0]), 1)
     elif wl == "sddmm":
         rows = min(budget_rows, int(w["dims"][0]))
         pos = G.to_host(w["B_pos"][: rows + 1])
@@ -234,6 +251,8 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
         "mttkrp": lambda: oracle.mttkrp(h, h["C"].reshape(d[1], -1), h["D"].reshape(d[2], -1), d[0]),
         "spadd": lambda: oracle.spadd(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"]),
         "spgemm": lambda: oracle.spgemm(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"], d[-1]),
+        "bspmm": lambda: oracle.bspmm(h["A_pos"], h["A_crd"], h["A_vals"].reshape(-1, d[2], d[3]),
+                                      h["B"].reshape(d[1] * d[3], -1), d[2], d[3]),
     }[wl]
     best = None
     for _ in range(max(reps, 2)):
@@ -245,7 +264,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
 
 
 SAMPLE_ROWS = {"spmm": 1 << 19, "spmv": 1_000_000, "sddmm": 250_000, "mttkrp": 500_000, "spadd": 1_000_000,
-               "spgemm": 200_000}
+               "spgemm": 200_000, "bspmm": 2048}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -462,6 +481,9 @@ def workload_name(wl, s):
         return f"CSR SpMV fp64 uniform {s['rows']}x{s['cols']} nnz={s['nnz']}"
     if wl == "sddmm":
         return f"CSR SDDMM fp32 uniform {s['rows']}x{s['cols']} nnz={s['nnz']} K={s['K']}"
+    if wl == "bspmm":
+        return (f"BCSR SpMM fp32 {s['Mb'] * s['br']}x{s['Nb'] * s['bc']} in {s['br']}x{s['bc']} blocks, "
+                f"{s['nnzb']} stored blocks, K={s['K']}")
     if wl == "mttkrp":
         return f"CSF MTTKRP fp64 {s['I']}x{s['Kd']}x{s['Ld']} nnz={s['nnz']} R={s['R']}"
     return f"CSR {wl} fp64 {s['rows']} rows nnzA={s['nnzA']} nnzB={s['nnzB']} (GPU assembly + numeric)"

@@ -3,8 +3,6 @@
 # usage: tools/gpu_exp.sh   (edit the EXPS list)   outputs: gpurun_out/exp_*.txt
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/smi.txt 2>&1; nproc >> gpurun_out/smi.txt
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
-tail -5 gpurun_out/pytest_gpu.log
 summ='import sys,json
 for l in sys.stdin:
     l=l.strip()
@@ -24,14 +22,10 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-for v in 10 12 16; do
-  echo "== parity with TACO_B200_SPMM_VARIANT=$v"
-  TACO_B200_SPMM_VARIANT=$v timeout 600 python -m pytest tests -m gpu -x -q -k "spmm or empty or leading or smoke" 2>&1 | tail -3
-done
-run spmm X=0
-for v in 10 11 12 13 14 15 16 17 18; do run spmm TACO_B200_SPMM_VARIANT=$v; done
-run spadd X=0
-ncuq spmm spmm_ring TACO_B200_SPMM_VARIANT=10
-ncuq spmm spmm_ring TACO_B200_SPMM_VARIANT=11
-} > gpurun_out/exp_2.txt 2>&1
-cat gpurun_out/exp_2.txt
+run bspmm X=0
+run bspmm TACO_B200_BSPMM_VARIANT=1
+run bspmm TACO_B200_BSPMM_VARIANT=2
+run bspmm TACO_B200_BSPMM_VARIANT=3
+ncuq bspmm bspmm_tc X=0
+} > gpurun_out/exp_5.txt 2>&1
+cat gpurun_out/exp_5.txt

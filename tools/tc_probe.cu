@@ -78,7 +78,7 @@ int main() {
     std::vector<float> imgB(4096, 0.f);
     for (int n = 0; n < N; n++) for (int k = 0; k < K; k++) imgB[((k / 4) * (N / 8) + n / 8) * 32 + (n % 8) * 4 + (k % 4)] = B[n * K + k];
     const uint32_t lboB = (N / 8) * 128, sboB = 128;
-    for (int hyp = 0; hyp < 10; hyp++) {
+    for (int hyp = 0; hyp < 16; hyp++) {
       std::vector<float> imgA(4096, 0.f);
       Params P{};
       P.n = N; P.fence = 1; P.lboB = lboB; P.sboB = sboB;
@@ -89,6 +89,33 @@ int main() {
         if (hyp == 0) { P.lboA = 2048; P.sboA = 128; name = "A K-major  LBO=k-chunk stride, SBO=row-group stride        "; }
         if (hyp == 1) { P.lboA = 128; P.sboA = 2048; name = "A K-major  LBO/SBO swapped (A only)                        "; }
         if (hyp == 4) { P.lboA = 128; P.sboA = 2048; P.lboB = sboB; P.sboB = lboB; name = "A,B K-major both LBO/SBO swapped                           "; }
+      } else if (hyp >= 12) {                       // truncation vs rounding of fp32 -> tf32 operands (K-major, as hyp 0)
+        // A[m][0] = 1 + 2^-11 + 2^-12 (above half a tf32 ulp), B[n][0] = 1, everything else 0:
+        // D = 1 if the tensor core truncates the low 13 bits, 1 + 2^-10 if it rounds to nearest
+        if (hyp > 12) continue;
+        std::vector<float> imgB2(4096, 0.f);
+        for (int n = 0; n < N; n++) imgB2[(n / 8) * 32 + (n % 8) * 4] = 1.0f;
+        for (int m = 0; m < M; m++) imgA[(m / 8) * 32 + (m % 8) * 4] = 1.0f + 0.00048828125f + 0.000244140625f;
+        P.idesc = idesc(N, 0, 0); P.lboA = 2048; P.sboA = 128;
+        cudaMemcpy(dA, imgA.data(), 16384, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, imgB2.data(), 16384, cudaMemcpyHostToDevice);
+        probe<<<1, 128, 40000>>>(dA, dB, P, dO);
+        cudaDeviceSynchronize();
+        float g[2];
+        cudaMemcpy(g, dO, 8, cudaMemcpyDeviceToHost);
+        printf("N=%2d hyp 12 fp32 -> tf32 operand conversion: D = %.10f (1.0 = truncation, 1.0009765625 = round to nearest)\n", N, g[0]);
+        continue;
+      } else if (hyp >= 10) {                       // A MN-major, 128-byte swizzle with 32-byte atoms (the only MN-major tf32
+        // layout CUTLASS uses: Swizzle<2,5,2> on byte addresses): panel = 32 m (128 B) x 8 k rows, 32-byte chunk ^= k % 4
+        const int pbytes = 1024;
+        for (int m = 0; m < M; m++) for (int k = 0; k < K; k++) {
+          const int mi = m % 32;
+          imgA[((m / 32) * pbytes + k * 128 + (((mi / 8) ^ (k % 4)) * 32) + (mi % 8) * 4) / 4] = A[m * K + k];
+        }
+        P.idesc = idesc(N, 1, 0);
+        P.layoutA = 1;
+        if (hyp == 10) { P.lboA = 1024; P.sboA = 512; name = "A MN-major SW128/32B-atom LBO=panel(1024), SBO=4-row group(512)"; }
+        if (hyp == 11) { P.lboA = 512; P.sboA = 1024; name = "A MN-major SW128/32B-atom LBO=4-row group(512), SBO=panel(1024)"; }
       } else if (hyp >= 6) {                        // A MN-major, 128-byte swizzle: panels of 32 m (128 B) x 8 k rows,
         const int pstride = 2048 / 4;               // 16-byte chunk index XOR (k % 8); panels 2048 B apart
         for (int m = 0; m < M; m++) for (int k = 0; k < K; k++)
