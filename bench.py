@@ -145,6 +145,9 @@ def make_workload(wl, device, rank, scale_down):
         over = {"spmm": dict(scale=16), "spmv": dict(n=100_000), "sddmm": dict(n=100_000),
                 "mttkrp": dict(I=100_000, K=20_000, L=20_000, nnz=2_000_000), "spadd": dict(n=100_000),
                 "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048)}[wl]
+    if wl == "bspmm" and os.environ.get("TACO_B200_BENCH_BLOCK"):      # block-shape sweep (experiments only): 16 -> 16x16 blocks,
+        b = int(os.environ["TACO_B200_BENCH_BLOCK"])                  # same matrix dimension and number of stored values
+        over.update(br=b, bc=b, Mb=over.get("Mb", 32768) * 32 // b, deg=16 * 32 // b)
     old = synth.SEED0
     synth.SEED0 = old + 1000 * rank       # each rank owns a different row shard of the (N x larger) global operand
     try:

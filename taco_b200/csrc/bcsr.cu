@@ -5,19 +5,24 @@
 // block columns, vals = [stored blocks][br][bc]; B = (Nb, bc, K) and C = (Mb, br, K) are dense, i.e. row-major
 // (Nb*bc) x K and (Mb*br) x K matrices.
 //
-// Two kernels:
+// Kernels:
 //   * bspmm_rows_kernel (fp32 / fp64, any block shape): CUDA cores, the reference's summation order (block by block,
 //     then column l inside the block, separate multiply and add) -> bit-identical to the reference's generated C.
-//   * bspmm_tc_kernel (fp32, 16x16 and 32x32 blocks, K % 4 == 0): tcgen05 tensor cores.  The block product is computed
-//     transposed, D[k', i2] += Bt[k', j2] * At[j2, i2], so the MMA's M dimension is the 128-wide tile of dense columns
-//     (always full) and its N dimension is the block height.  fp32 inputs are split into two TF32 terms
-//     (x = hi + lo, hi = top 19 bits) and three MMAs (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory, which
-//     keeps the result within the fp32 tolerance of the north star (1e-5 relative; a single TF32 pass would be 1e-3).
-//     Warp-specialised: 8 producer warps (global -> registers -> hi/lo split -> K-major canonical UMMA layouts in smem, the B
-//     tile transposed on the fly, mbarrier ring), 1 MMA warp (one thread issues tcgen05.mma, tcgen05.commit frees stages), 4 epilogue warps (tcgen05.ld of
-//     the accumulator, coalesced 128-byte stores), two accumulators in TMEM so the epilogue of one block row overlaps
-//     the MMAs of the next.
+//   * bspmm_tma_kernel (DEFAULT for fp32, 16x16 and 32x32 blocks, K % 4 == 0) and bspmm_tc_kernel (its register-staged
+//     predecessor, TACO_B200_BSPMM_VARIANT=4): tcgen05 tensor cores.  The block product is computed transposed,
+//     D[k', i2] += Bt[k', j2] * At[j2, i2], so the MMA's M dimension is the 128-wide tile of dense columns (always
+//     full) and its N dimension is the block height.  fp32 inputs are split into two TF32 terms (x = hi + lo, hi = top
+//     19 bits) and the three products hi*hi, hi*lo, lo*hi accumulate in fp32 in tensor memory (two MMAs per K step: the
+//     A block is ONE operand of 2*br rows [hi ; lo]), which keeps the result within the fp32 tolerance of the north
+//     star (1e-5 relative; a single TF32 pass would be 1e-3).  Warp-specialised: TMA (or producer) warps -> mbarrier
+//     rings -> 1 MMA warp (one thread issues tcgen05.mma, tcgen05.commit frees stages) -> 4 epilogue warps
+//     (tcgen05.ld, coalesced 128-byte stores); two accumulators in TMEM so the epilogue of one block row overlaps the
+//     MMAs of the next.  Measured at the bench config (32768^2 blocks of 32x32, 16 per block row, K = 128):
+//     CUDA cores 21.3 ms -> register-staged tcgen05 2.64 ms -> TMA-fed 1.60 ms = 85.6 TFLOP/s with 10.2 GB of DRAM
+//     traffic, i.e. 6.4 TB/s = the measured HBM peak (profiles/r01_bspmm.md).
 // Algorithmic bytes per launch: 4(Mb+1) + nnzb*(4 + br*bc*es) + es*K*(Nb*bc + Mb*br).
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -422,6 +427,300 @@ static int launch(const int* pos, const int* crd, const float* vals, const float
   return TACO_B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 kernel, TMA-fed ("bspmm_tma_kernel")
+// ---------------------------------------------------------------------------------------------------------
+// Same math and the same accumulator / epilogue as bspmm_tc_kernel, but no operand passes through registers on its way
+// in.  Measured with tools/tc_probe.cu on B200:
+//   * kind::tf32 reads fp32 containers and IGNORES the low 13 mantissa bits (truncation), so the raw fp32 B tile is
+//     already the "hi" operand; only lo = x - trunc(x) has to be computed;
+//   * an MN-major tf32 operand must use the 128-byte swizzle with 32-byte atoms (descriptor layout type 1, Swizzle<2,5,2>
+//     on byte addresses, LBO = stride between 32-column panels, SBO = 512 = four 128-byte rows) -- exactly what TMA
+//     writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and a {32 columns, BC rows} box.  So the B tile is NOT transposed:
+//     rows j2 of B are the K rows of the MMA's A operand.
+// Roles: 4 epilogue warps, 1 MMA warp, 1 TMA warp (per stored block: four tensor boxes of B + one 1-D bulk copy of the A
+// block into the raw ring), CW converter warps (raw ring -> lo ring: Bt_lo in place-identical swizzled positions, the A
+// block as the merged K-major [hi ; lo] operand).  Rings: RS raw stages (TMA in flight), LS lo stages.
+namespace tma {
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// MN-major operand, 128-byte swizzle with 32-byte atoms (layout type 1)
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return smem_desc(addr, lbo, sbo) | (1ull << 61);
+}
+
+template <int BR, int BC>
+struct TCfg {
+  using CF = Cfg<BR, BC>;
+  static constexpr int PANEL_BYTES = BC * 128;                      // one TMA box: BC rows x 32 dense columns
+  static constexpr int BT_BYTES = 4 * PANEL_BYTES;                  // = CF::BT_BYTES
+  static constexpr int AB_BYTES = BR * BC * 4;
+  static constexpr int RAW_BYTES = BT_BYTES + AB_BYTES;             // raw stage: B tile (swizzled panels) + A block (row-major)
+  static constexpr int LO_BYTES = BT_BYTES + 2 * AB_BYTES;          // lo stage: Bt_lo + merged [A_hi ; A_lo] (K-major, no swizzle)
+  static_assert(RAW_BYTES % 1024 == 0 && LO_BYTES % 1024 == 0, "stages keep the 1024-byte swizzle phase");
+  static constexpr uint32_t idesc(int n) { return CF::idesc(n) | (1u << 15); }     // A operand (the B tile) is MN-major
+};
+
+template <int BR, int BC, int RS, int LS, int CW, int MINB>
+__global__ void __launch_bounds__((EPI_WARPS + 2 + CW) * 32, MINB)
+bspmm_tma_kernel(const __grid_constant__ CUtensorMap tmB, const int* __restrict__ pos, const int* __restrict__ crd,
+                 const float* __restrict__ vals, float* __restrict__ C, int Mb, int K) {
+  using CF = Cfg<BR, BC>;
+  using TC = TCfg<BR, BC>;
+  constexpr int TMA_WARP = EPI_WARPS + 1, CONV_WARP0 = EPI_WARPS + 2;
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const uint32_t raw0 = smem0, lo0 = smem0 + RS * TC::RAW_BYTES;
+  const uint32_t bars = lo0 + LS * TC::LO_BYTES;        // raw_full[RS] raw_empty[RS] lo_full[LS] lo_empty[LS] tfull[2] tempty[2] slot
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (RS + s); };
+  auto lo_full = [&](int s) { return bars + 8u * (2 * RS + s); };
+  auto lo_empty = [&](int s) { return bars + 8u * (2 * RS + LS + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * RS + 2 * LS + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * RS + 2 * LS + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * RS + 2 * LS + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.y * TILE_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 1); }
+    for (int s = 0; s < LS; s++) { mbar_init(lo_full(s), CW * 32); mbar_init(lo_empty(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(CF::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == TMA_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < EPI_WARPS) {
+    // ===== epilogue (as bspmm_tc_kernel): TMEM lane = dense column k', TMEM column = row in block =====================
+    const int col = k0 + warp * 32 + lane;
+    uint32_t acc_it = 0;
+    for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+      const int n = __ldg(pos + i1 + 1) - __ldg(pos + i1);
+      float* crow = C + (size_t)i1 * BR * K + col;
+      if (n == 0) {
+        if (col < K) for (int j = 0; j < BR; j++) crow[(size_t)j * K] = 0.0f;
+        continue;
+      }
+      const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + a * CF::ACC_COLS;
+#pragma unroll
+      for (int c = 0; c < BR; c += 16) {
+        uint32_t v[16], x[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr + c) : "memory");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),
+              "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15])
+            : "r"(taddr + BR + c) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 16 >= BR) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(a));
+        }
+        if (col < K) {
+#pragma unroll
+          for (int j = 0; j < 16; j++) crow[(size_t)(c + j) * K] = __uint_as_float(v[j]) + __uint_as_float(x[j]);
+        }
+      }
+      acc_it++;
+    }
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer ==================================================================================================
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+        const int n = __ldg(pos + i1 + 1) - __ldg(pos + i1);
+        if (n == 0) continue;
+        const uint32_t a = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * CF::ACC_COLS;
+        for (int b = 0; b < n; b++, it++) {
+          const uint32_t rs = it % RS, rph = (it / RS) & 1, ls = it % LS, lph = (it / LS) & 1;
+          mbar_wait(raw_full(rs), rph);                              // TMA bytes have landed (async proxy -> async proxy)
+          mbar_wait(lo_full(ls), lph);                               // converters have written Bt_lo and [A_hi ; A_lo]
+          tc_fence_after();
+          const uint32_t bt_hi = raw0 + rs * TC::RAW_BYTES, bt_lo = lo0 + ls * TC::LO_BYTES, ab = bt_lo + TC::BT_BYTES;
+#pragma unroll
+          for (int g = 0; g < BC / 8; g++) {                         // 8 rows of the B tile = one K step = 1024 bytes per panel
+            const uint64_t a_hi = smem_desc_mn32(bt_hi + g * 1024, TC::PANEL_BYTES, 512);
+            const uint64_t a_lo = smem_desc_mn32(bt_lo + g * 1024, TC::PANEL_BYTES, 512);
+            const uint64_t b_all = smem_desc(ab + g * 2 * CF::AB_LBO, CF::AB_LBO, CF::AB_SBO);
+            tc_mma_tf32(d_tmem, a_hi, b_all, TC::idesc(2 * BR), (b | g) != 0);
+            tc_mma_tf32(d_tmem, a_lo, b_all, TC::idesc(BR), 1);
+          }
+          tc_commit(raw_empty(rs));
+          tc_commit(lo_empty(ls));
+        }
+        tc_commit(tfull_bar(a));
+        acc_it++;
+      }
+    }
+    __syncwarp();
+  } else if (warp == TMA_WARP) {
+    // ===== TMA producer: the whole warp reads up to 32 block columns of a row at once, lane 0 issues ===================
+    uint32_t it = 0;
+    for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+      const int p0 = __ldg(pos + i1), p1 = __ldg(pos + i1 + 1);
+      for (int pc = p0; pc < p1; pc += 32) {
+        const int mine = pc + lane < p1 ? __ldg(crd + pc + lane) : 0;
+        const int cnt = min(32, p1 - pc);
+        for (int b = 0; b < cnt; b++, it++) {
+          const int j1 = __shfl_sync(0xffffffffu, mine, b);
+          if (lane == 0) {
+            const uint32_t rs = it % RS, rph = (it / RS) & 1;
+            mbar_wait(raw_empty(rs), rph ^ 1);
+            const uint32_t st = raw0 + rs * TC::RAW_BYTES;
+            mbar_expect_tx(raw_full(rs), TC::RAW_BYTES);
+#pragma unroll
+            for (int c = 0; c < 4; c++) tma_box_2d(st + c * TC::PANEL_BYTES, &tmB, k0 + 32 * c, j1 * BC, raw_full(rs));
+            bulk_copy(st + TC::BT_BYTES, vals + (size_t)(pc + b) * BR * BC, TC::AB_BYTES, raw_full(rs));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== converters: raw ring -> lo ring ================================================================================
+    const int ct = threadIdx.x - CONV_WARP0 * 32;                    // 0 .. CW*32-1
+    constexpr int CT = CW * 32;
+    constexpr int BT_CHUNKS = TC::BT_BYTES / 16, BT_PER = (BT_CHUNKS + CT - 1) / CT;
+    constexpr int AB_CHUNKS = TC::AB_BYTES / 16, AB_PER = (AB_CHUNKS + CT - 1) / CT;
+    constexpr int JC = BC / 4;                                       // 16-byte chunks per row of the A block
+    static_assert(JC == 4 || JC == 8, "diagonal chunk assignment below is written for 16- and 32-wide blocks");
+    // chunk index -> (row, chunk in row) along diagonals: the 8 lanes of one shared-memory wavefront read 8 different
+    // bank groups of the row-major block ((i2 * JC + jc) % 8) AND write 8 different ones of the K-major operand (i2 % 8);
+    // the straight assignment made every store 8-way conflicted (ncu: 246 M conflict wavefronts of 347 M)
+    auto ab_row = [](int ch) { return ((ch >> 3) / JC) * 8 + (ch & 7); };
+    auto ab_chunk = [](int ch) { return (((ch & 7) * JC >> 3) + (ch >> 3) % JC) % JC; };
+    uint32_t it = 0;
+    for (int i1 = blockIdx.x; i1 < Mb; i1 += gridDim.x) {
+      const int n = __ldg(pos + i1 + 1) - __ldg(pos + i1);
+      for (int b = 0; b < n; b++, it++) {
+        const uint32_t rs = it % RS, rph = (it / RS) & 1, ls = it % LS, lph = (it / LS) & 1;
+        const uint32_t src = raw0 + rs * TC::RAW_BYTES, dst = lo0 + ls * TC::LO_BYTES;
+        mbar_wait(raw_full(rs), rph);
+        float4 xb[BT_PER], xa[AB_PER];
+#pragma unroll
+        for (int u = 0; u < BT_PER; u++) {
+          const int ch = ct + u * CT;
+          if (BT_CHUNKS % CT == 0 || ch < BT_CHUNKS) xb[u] = lds_f4(src + ch * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < AB_PER; u++) {
+          const int ch = ct + u * CT;
+          if (AB_CHUNKS % CT == 0 || ch < AB_CHUNKS) xa[u] = lds_f4(src + TC::BT_BYTES + (ab_row(ch) * JC + ab_chunk(ch)) * 16);
+        }
+        mbar_wait(lo_empty(ls), lph ^ 1);
+#pragma unroll
+        for (int u = 0; u < BT_PER; u++) {
+          const int ch = ct + u * CT;
+          if (BT_CHUNKS % CT == 0 || ch < BT_CHUNKS) {
+            float4 hi, lo;
+            split_tf32(xb[u], hi, lo);
+            sts_f4(dst + ch * 16, lo);                               // same swizzled position as the raw element
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < AB_PER; u++) {
+          const int ch = ct + u * CT;
+          if (AB_CHUNKS % CT == 0 || ch < AB_CHUNKS) {
+            const int i2 = ab_row(ch), jc = ab_chunk(ch);            // row-major A block: row i2, columns 4 jc .. 4 jc + 3
+            float4 hi, lo;
+            split_tf32(xa[u], hi, lo);
+            const uint32_t off = (uint32_t)(jc * (2 * BR / 8) + (i2 >> 3)) * 128 + (uint32_t)(i2 & 7) * 16;
+            sts_f4(dst + TC::BT_BYTES + off, hi);
+            sts_f4(dst + TC::BT_BYTES + (BR / 8) * 128 + off, lo);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(lo_full(ls));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+template <int BR, int BC, int RS, int LS, int CW, int MINB>
+static int launch(const int* pos, const int* crd, const float* vals, const float* B, float* C, int Mb, int Nb, int K) {
+  using TC = TCfg<BR, BC>;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(TACO_B200_ERR_CUDA, "bspmm: cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Nb * BC};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)BC}, estr[2] = {1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)B, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TACO_B200_ERR_CUDA, "bspmm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  constexpr int threads = (EPI_WARPS + 2 + CW) * 32;
+  const int smem = RS * TC::RAW_BYTES + LS * TC::LO_BYTES + 8 * (2 * RS + 2 * LS + 4) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TB_CUDA(cudaFuncSetAttribute(bspmm_tma_kernel<BR, BC, RS, LS, CW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int gx = num_sms() * MINB;
+  const int gy = (K + TILE_K - 1) / TILE_K;
+  gx = (gx + gy - 1) / gy;
+  if (gx > Mb) gx = Mb;
+  if (gx < 1) gx = 1;
+  bspmm_tma_kernel<BR, BC, RS, LS, CW, MINB><<<dim3(gx, gy), threads, smem, stream()>>>(tm, pos, crd, vals, C, Mb, K);
+  return TACO_B200_OK;
+}
+
+}  // namespace tma
+
 }  // namespace tc
 
 // TACO_B200_BSPMM_TC=0 forces the CUDA-core kernel (reference order), =1 (default) uses tensor cores where they apply.
@@ -440,15 +739,31 @@ static int bspmm_launch(const BcsrView& A, const int* pos, const int* crd, const
     if (tc_enabled() && aligned) {
       if (A.br == 32 && A.bc == 32) {
         count_launch(1);
+        // TMA-fed kernel (default): (raw stages, lo stages, converter warps, CTAs per SM); measured 1.60 / 2.00 / 1.93 / 1.59 ms
+        // for variants 0, 11, 12, 13 at the bench config (10.2 GB of DRAM traffic -> 6.4 TB/s, the measured HBM peak)
+        switch (variant) {
+          case 0: return tc::tma::launch<32, 32, 3, 2, 8, 2>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 11: return tc::tma::launch<32, 32, 4, 2, 8, 1>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 12: return tc::tma::launch<32, 32, 6, 3, 8, 1>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 13: return tc::tma::launch<32, 32, 3, 2, 4, 2>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          default: break;
+        }
         switch (variant) {     // (stages, producer warps, CTAs per SM); measured at the bench config: 2.64 / 3.73 / 3.17 / 4.81 ms
           case 1: return tc::launch<32, 32, 4, 8, 1>(pos, crd, vals, B, C, A.Mb, K);
           case 2: return tc::launch<32, 32, 2, 16, 2>(pos, crd, vals, B, C, A.Mb, K);
           case 3: return tc::launch<32, 32, 4, 16, 1>(pos, crd, vals, B, C, A.Mb, K);
-          default: return tc::launch<32, 32, 2, 8, 2>(pos, crd, vals, B, C, A.Mb, K);
+          default: return tc::launch<32, 32, 2, 8, 2>(pos, crd, vals, B, C, A.Mb, K);     // variant 4: register-staged kernel
         }
       }
       if (A.br == 16 && A.bc == 16) {
         count_launch(1);
+        switch (variant) {
+          case 0: return tc::tma::launch<16, 16, 6, 3, 8, 2>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 11: return tc::tma::launch<16, 16, 6, 3, 4, 2>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 12: return tc::tma::launch<16, 16, 8, 4, 8, 1>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          case 13: return tc::tma::launch<16, 16, 4, 2, 4, 2>(pos, crd, vals, B, C, A.Mb, A.Nb, K);
+          default: break;
+        }
         switch (variant) {
           case 1: return tc::launch<16, 16, 8, 8, 1>(pos, crd, vals, B, C, A.Mb, K);
           case 2: return tc::launch<16, 16, 4, 16, 2>(pos, crd, vals, B, C, A.Mb, K);

@@ -22,10 +22,8 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-run bspmm X=0
-run bspmm TACO_B200_BSPMM_VARIANT=1
-run bspmm TACO_B200_BSPMM_VARIANT=2
-run bspmm TACO_B200_BSPMM_VARIANT=3
-ncuq bspmm bspmm_tc X=0
-} > gpurun_out/exp_5.txt 2>&1
-cat gpurun_out/exp_5.txt
+for v in 0 11 12 13 4; do run bspmm TACO_B200_BENCH_BLOCK=16 TACO_B200_BSPMM_VARIANT=$v; done
+run bspmm TACO_B200_BENCH_BLOCK=16 TACO_B200_BSPMM_TC=0
+ncuq bspmm bspmm_t TACO_B200_BENCH_BLOCK=16
+} > gpurun_out/exp_8.txt 2>&1
+cat gpurun_out/exp_8.txt
