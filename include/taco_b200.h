@@ -128,6 +128,14 @@ int taco_b200_mttkrp_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t*
 int taco_b200_mttkrp_compute (taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 int taco_b200_mttkrp_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 
+/* C(i,k) = A(i,j) * B(j,k)   A = {Compressed,Compressed} (doubly compressed rows), B, C dense: the statement of the
+ * reference's spmmDCSRGPU test (test/tests-scheduling-eval.cpp:1309-1358); replaces what CodeGen_CUDA emits for
+ * scheduleSpMMNZRowsGPU (:358-369).  The level-0 row list is expanded to a CSR pos array on the device and the CSR
+ * kernel runs on it; rows that are not stored come out as zero rows (the reference zero-fills C). */
+int taco_b200_spmm_dcsr_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
+int taco_b200_spmm_dcsr_compute (taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
+int taco_b200_spmm_dcsr_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
+
 /* a(i,j) = A(i,k,j,l) * c(k,l)  (blocked SpMV)   and   C(i,j,m) = A(i,k,j,l) * B(k,l,m)  (blocked SpMM)
  * A = {Dense,Compressed,Dense,Dense} over (block row, block column, row in block, column in block), the blocked
  * format of the reference's `bspmv` test (test/tests-expr_storage.cpp:939-960); c, a, B, C dense row-major; fp32 | fp64.
@@ -188,6 +196,7 @@ const char* taco_b200_module_stub_source(taco_b200_module_t* m);
 /* _shim_ entry points with the reference's exact shim signature (codegen_cuda.cpp:1500-1540). */
 int _shim_taco_b200_spmv_assemble(void** p);   int _shim_taco_b200_spmv_compute(void** p);   int _shim_taco_b200_spmv_evaluate(void** p);
 int _shim_taco_b200_spmm_assemble(void** p);   int _shim_taco_b200_spmm_compute(void** p);   int _shim_taco_b200_spmm_evaluate(void** p);
+int _shim_taco_b200_spmm_dcsr_assemble(void** p); int _shim_taco_b200_spmm_dcsr_compute(void** p); int _shim_taco_b200_spmm_dcsr_evaluate(void** p);
 int _shim_taco_b200_sddmm_assemble(void** p);  int _shim_taco_b200_sddmm_compute(void** p);  int _shim_taco_b200_sddmm_evaluate(void** p);
 int _shim_taco_b200_mttkrp_assemble(void** p); int _shim_taco_b200_mttkrp_compute(void** p); int _shim_taco_b200_mttkrp_evaluate(void** p);
 int _shim_taco_b200_ttv_assemble(void** p);    int _shim_taco_b200_ttv_compute(void** p);    int _shim_taco_b200_ttv_evaluate(void** p);

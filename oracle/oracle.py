@@ -75,6 +75,18 @@ def spmm(pos, crd, vals, B):
     return C
 
 
+def spmm_dcsr(n, pos1, crd1, pos2, crd2, vals, B):
+    """C(i,k) = A(i,j) * B(j,k) with A = {Sparse,Sparse}; n = number of rows of A / C"""
+    pos1, crd1, pos2, crd2 = _i32(pos1), _i32(crd1), _i32(pos2), _i32(crd2)
+    vals = np.ascontiguousarray(vals)
+    B = np.ascontiguousarray(B, dtype=vals.dtype)
+    K = B.shape[1]
+    C = np.empty((n, K), dtype=vals.dtype)
+    getattr(lib(), "oracle_spmm_dcsr_" + _sfx(vals.dtype))(ctypes.c_int32(n), ctypes.c_int32(K), _p(pos1), _p(crd1), _p(pos2),
+                                                          _p(crd2), _p(vals), _p(B), _p(C))
+    return C
+
+
 def sddmm(pos, crd, bvals, C, D):
     """returns (A_pos, A_crd, A_vals)"""
     pos, crd = _i32(pos), _i32(crd)

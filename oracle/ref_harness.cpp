@@ -10,7 +10,7 @@
 //
 // usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
 //                         [--threads N] [--reps R]
-//   kernel in {spmv, spmm, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm}
+//   kernel in {spmv, spmm, spmm_dcsr, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm}
 // Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
 //
 // Input arrays (tbin.h): dims (int32), and per kernel
@@ -73,6 +73,26 @@ static Tensor<T> attachCSR(const std::string& name, std::vector<int> dims, tbin_
   int* crd = (int*)need(f, (p + "_crd").c_str())->data;
   T* vals = (T*)need(f, (p + "_vals").c_str())->data;
   return makeCSR<T>(name, dims, pos, crd, vals);
+}
+
+// Doubly compressed rows {Sparse, Sparse} (the operand of the reference's spmmDCSRGPU test,
+// test/tests-scheduling-eval.cpp:1309-1358): level arrays A1_pos[2], A1_crd[nzrows], A2_pos[nzrows+1], A2_crd[nnz]
+template <typename T>
+static Tensor<T> attachDCSR(const std::string& name, std::vector<int> dims, tbin_file& f, const std::string& p) {
+  Tensor<T> t(name, dims, Format({Sparse, Sparse}));
+  auto st = t.getStorage();
+  std::vector<ModeIndex> mi;
+  for (int l = 1; l <= 2; l++) {
+    tbin_array* pos = need(f, (p + std::to_string(l) + "_pos").c_str());
+    tbin_array* crd = need(f, (p + std::to_string(l) + "_crd").c_str());
+    mi.push_back(ModeIndex({makeArray((int*)pos->data, pos->count, Array::UserOwns),
+                            makeArray((int*)crd->data, crd->count, Array::UserOwns)}));
+  }
+  tbin_array* v = need(f, (p + "_vals").c_str());
+  st.setIndex(Index(t.getFormat(), mi));
+  st.setValues(makeArray((T*)v->data, v->count, Array::UserOwns));
+  t.setStorage(st);
+  return t;
 }
 
 template <typename T>
@@ -156,14 +176,14 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         a.data = y.getStorage().getValues().getData(); outs.push_back(a);
         tbin_write(outPath, outs.data(), outs.size());
       }
-    } else if (kernel == "spmm") {
+    } else if (kernel == "spmm" || kernel == "spmm_dcsr") {
       int n = dims[0], m = dims[1], K = dims[2];
-      Tensor<T> A = attachCSR<T>("A", {n, m}, in, "A");
+      Tensor<T> A = kernel == "spmm" ? attachCSR<T>("A", {n, m}, in, "A") : attachDCSR<T>("A", {n, m}, in, "A");
       Tensor<T> B = attachDense<T>("B", {m, K}, (T*)need(in, "B")->data);
       Tensor<T> C("C", {n, K}, Format({Dense, Dense}));
       C(i, k) = A(i, j) * B(j, k);
       IndexStmt stmt = C.getAssignment().concretize();
-      if (tuned) {
+      if (tuned && kernel == "spmm") {
         IndexVar i0("i0"), i1("i1"), jpos("jpos"), jpos0("jpos0"), jpos1("jpos1");
         stmt = stmt.split(i, i0, i1, 16).pos(j, jpos, A(i, j)).split(jpos, jpos0, jpos1, 8)
                    .reorder({i0, i1, jpos0, k, jpos1})

@@ -63,6 +63,22 @@ static int cmp_i32(const void* a, const void* b) { /* reference prelude `cmp`, s
       }                                                                                                            \
     }                                                                                                              \
   }                                                                                                                \
+  /* C(i,k) = A(i,j) * B(j,k), A doubly compressed {Sparse,Sparse} (the operand of the reference's spmmDCSRGPU test,  \
+     test/tests-scheduling-eval.cpp:1309-1358).  Generated code (dumped through oracle/ref_harness.cpp): zero ALL of C,  \
+     then for iA in [A1_pos[0], A1_pos[1]): i = A1_crd[iA]; for jA in [A2_pos[iA], A2_pos[iA+1]): j = A2_crd[jA];       \
+     C[i,k] = C[i,k] + A[jA] * B[j,k] -- position loops of mode_format_compressed.cpp:80-105 at both levels. */         \
+  void oracle_spmm_dcsr_##S(int32_t n, int32_t K, const int32_t* pos1, const int32_t* crd1, const int32_t* pos2,       \
+                            const int32_t* crd2, const T* vals, const T* B, T* C) {                                    \
+    _Pragma("omp parallel for schedule(static)") for (int64_t q = 0; q < (int64_t)n * K; q++) C[q] = 0;                \
+    _Pragma("omp parallel for schedule(static)") for (int32_t iA = pos1[0]; iA < pos1[1]; iA++) {                      \
+      T* c = C + (size_t)crd1[iA] * K;                                                                                 \
+      for (int32_t p = pos2[iA]; p < pos2[iA + 1]; p++) {                                                              \
+        const T* b = B + (size_t)crd2[p] * K;                                                                          \
+        T a = vals[p];                                                                                                 \
+        for (int32_t k = 0; k < K; k++) c[k] = c[k] + a * b[k];                                                        \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }                                                                                                                    \
   /* A(i,j) = B(i,j) * C(i,k) * D(j,k), A and B CSR (A has B's structure), C, D row-major.                       \
      tkA += (B[p] * C[i,k]) * D[j,k], k ascending, scalar accumulator; A_vals[jA++] = tkA. */                     \
   void oracle_sddmm_##S(int32_t n, int32_t K, const int32_t* pos, const int32_t* crd, const T* Bvals, const T* C, \

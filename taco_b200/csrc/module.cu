@@ -35,6 +35,7 @@ struct Family {
 static const Family kFamilies[] = {
     {"spmv",   "T0(a)=T1(a,b)*T2(b)",                 {"d", "ds", "d", ""},      3, TB_FAM3(spmv)},
     {"spmm",   "T0(a,b)=T1(a,c)*T2(c,b)",             {"dd", "ds", "dd", ""},    3, TB_FAM3(spmm)},
+    {"spmm_dcsr", "T0(a,b)=T1(a,c)*T2(c,b)",          {"dd", "ss", "dd", ""},    3, TB_FAM3(spmm_dcsr)},
     {"spgemm", "T0(a,b)=T1(a,c)*T2(c,b)",             {"ds", "ds", "ds", ""},    3, TB_FAM3(spgemm)},
     {"spadd",  "T0(a,b)=T1(a,b)+T2(a,b)",             {"ds", "ds", "ds", ""},    3, TB_FAM3(spadd)},
     {"sddmm",  "T0(a,b)=T1(a,b)*T2(a,c)*T3(b,c)",     {"ds", "ds", "dd", "dd"},  4, TB_FAM3(sddmm)},
@@ -168,7 +169,7 @@ taco_b200_module_t* taco_b200_module_open(const char* expr, const char* formats,
         // only the spmm result may carry a non-identity mode ordering (the reference GPU test's column-major C)
         std::string ident;
         for (size_t l = 0; l < lv.size(); l++) ident += (l ? "," : "") + std::to_string(l);
-        if (it->second.second != ident && !(std::string(f.name) == "spmm" && a == 0 && it->second.second == "1,0")) ok = false;
+        if (it->second.second != ident && !((std::string(f.name) == "spmm" || std::string(f.name) == "spmm_dcsr") && a == 0 && it->second.second == "1,0")) ok = false;
       }
     }
     if (!ok) continue;
@@ -264,7 +265,7 @@ const char* taco_b200_module_stub_source(taco_b200_module_t* m) {
   }
 #define TB_SHIMS3(n) TB_SHIM3(n, assemble) TB_SHIM3(n, compute) TB_SHIM3(n, evaluate)
 #define TB_SHIMS4(n) TB_SHIM4(n, assemble) TB_SHIM4(n, compute) TB_SHIM4(n, evaluate)
-TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS4(sddmm) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm) TB_SHIMS3(bspmv) TB_SHIMS3(bspmm)
+TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS3(spmm_dcsr) TB_SHIMS4(sddmm) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm) TB_SHIMS3(bspmv) TB_SHIMS3(bspmm)
 
 }  // extern "C"
 

@@ -514,6 +514,63 @@ static int spmm_views(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B, Dens
   return TACO_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Doubly compressed rows: A = {Compressed, Compressed} (the operand of the reference's spmmDCSRGPU test,
+// /root/reference/test/tests-scheduling-eval.cpp:1309-1358, schedule scheduleSpMMNZRowsGPU :358-369).
+// Level 0 stores only the rows that have nonzeros (pos0 = {0, stored rows}, crd0 = their row ids), level 1 is a CSR over
+// those stored rows.  On the device the level-0 list is expanded into an ordinary CSR pos array over ALL rows
+// (pos_full[i] = pos1[number of stored rows with id < i]); crd1 / vals are shared as they are.  The tuned CSR kernel
+// then runs unchanged: absent rows are empty rows (zeroed by their owner, as the reference's zero-fill of C does), and
+// every stored row keeps the reference's accumulation order.
+// ---------------------------------------------------------------------------------------------------------
+struct DcsrView { int32_t rows, cols; int32_t* pos0; int32_t* crd0; int32_t* pos1; int32_t* crd1; void* vals; DType dt; };
+
+static int view_dcsr(const taco_tensor_t* t, const char* name, DcsrView* v) {
+  if (!t) return fail(TACO_B200_ERR_ARG, "%s: NULL tensor", name);
+  if (t->order != 2 || t->mode_types[0] != taco_mode_sparse || t->mode_types[1] != taco_mode_sparse ||
+      t->mode_ordering[0] != 0 || t->mode_ordering[1] != 1)
+    return fail(TACO_B200_ERR_FORMAT, "%s: expected DCSR ({Compressed,Compressed}, mode ordering 0,1)", name);
+  v->rows = t->dimensions[0];
+  v->cols = t->dimensions[1];
+  if (v->rows < 0 || v->cols < 0) return fail(TACO_B200_ERR_ARG, "%s: negative dimension", name);
+  if (!t->indices || !t->indices[0] || !t->indices[1]) return fail(TACO_B200_ERR_ARG, "%s: missing level arrays", name);
+  v->pos0 = (int32_t*)t->indices[0][0]; v->crd0 = (int32_t*)t->indices[0][1];
+  v->pos1 = (int32_t*)t->indices[1][0]; v->crd1 = (int32_t*)t->indices[1][1];
+  if (!v->pos0 || !v->pos1) return fail(TACO_B200_ERR_ARG, "%s: a compressed level has no pos array", name);
+  v->vals = t->vals;
+  return dtype_of(t, &v->dt);
+}
+
+// One warp per stored row r (and one more for the tail): rows (crd0[r-1], crd0[r]] start at pos1[r]; the rows after the
+// last stored row, and pos_full[rows], get pos1[stored].
+__global__ void __launch_bounds__(256)
+dcsr_expand_pos_kernel(const int* __restrict__ crd0, const int* __restrict__ pos1, int stored, int rows, int* __restrict__ pos_full) {
+  const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (r > stored) return;
+  const int lo = r == 0 ? 0 : __ldg(crd0 + r - 1) + 1;
+  const int hi = r < stored ? __ldg(crd0 + r) : rows;             // inclusive
+  const int p = __ldg(pos1 + r);
+  for (int i = lo + lane; i <= hi; i += 32) pos_full[i] = p;
+}
+
+static int spmm_dcsr_views(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B, DenseView* Cv, DcsrView* Av, DenseView* Bv,
+                           bool* colmajor) {
+  TB_TRY(ensure_init());
+  TB_TRY(view_dense(C, 2, "C", Cv));
+  TB_TRY(view_dcsr(A, "A", Av));
+  TB_TRY(view_dense(B, 2, "B", Bv));
+  if (Bv->mode_order[0] != 0 || Bv->mode_order[1] != 1)
+    return fail(TACO_B200_ERR_FORMAT, "spmm_dcsr: B must be row-major {Dense,Dense}");
+  *colmajor = (Cv->mode_order[0] == 1 && Cv->mode_order[1] == 0);
+  if (!*colmajor && !(Cv->mode_order[0] == 0 && Cv->mode_order[1] == 1))
+    return fail(TACO_B200_ERR_FORMAT, "spmm_dcsr: bad mode ordering for C");
+  if (Cv->dim[0] != Av->rows || Bv->dim[0] != Av->cols || Cv->dim[1] != Bv->dim[1])
+    return fail(TACO_B200_ERR_ARG, "spmm_dcsr: dimension mismatch C[%d x %d] = A[%d x %d] * B[%d x %d]", Cv->dim[0],
+                Cv->dim[1], Av->rows, Av->cols, Bv->dim[0], Bv->dim[1]);
+  if (Cv->dt != Av->dt || Bv->dt != Av->dt) return fail(TACO_B200_ERR_FORMAT, "spmm_dcsr: mixed component types");
+  return TACO_B200_OK;
+}
+
 // TACO_B200_PIPELINE_MIN_BYTES: smallest (result + nonzero) volume that takes the chunked path (default 64 MiB;
 // 0 forces it, a huge value disables it)
 static size_t pipeline_min_bytes() {
@@ -649,6 +706,65 @@ int taco_b200_spmm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B)
 int taco_b200_spmm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
   TB_TRY(taco_b200_spmm_assemble(C, A, B));
   return taco_b200_spmm_compute(C, A, B);
+}
+
+int taco_b200_spmm_dcsr_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  DenseView Cv, Bv; DcsrView Av; bool cm;
+  TB_TRY(spmm_dcsr_views(C, A, B, &Cv, &Av, &Bv, &cm));
+  void* p = result_alloc(Cv.count() * dsize(Cv.dt));
+  if (!p) return fail(TACO_B200_ERR_ALLOC, "spmm_dcsr: cannot allocate result");
+  C->vals = (uint8_t*)p;
+  return TACO_B200_OK;
+}
+
+int taco_b200_spmm_dcsr_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  DenseView Cv, Bv; DcsrView Av; bool cm;
+  TB_TRY(spmm_dcsr_views(C, A, B, &Cv, &Av, &Bv, &cm));
+  if (!Cv.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  int32_t first = 0, stored = 0, nnz = 0;
+  TB_TRY(read_i32(Av.pos0, &first));
+  TB_TRY(read_i32(Av.pos0 + 1, &stored));
+  if (first != 0 || stored < 0 || stored > Av.rows) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: bad level-0 pos {%d, %d}", first, stored);
+  if (classify(Av.pos1) == Mem::Device && A->vals_size > 0) nnz = A->vals_size;
+  else TB_TRY(read_i32(Av.pos1 + stored, &nnz));
+  if (nnz < 0 || nnz > INT32_MAX - 65536) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: bad nnz %d", nnz);
+  if (stored > 0 && !Av.crd0) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: level 0 has no crd array");
+  const int K = Bv.dim[1];
+  const size_t es = dsize(Av.dt);
+  In crd0, pos1, crd, vals, bin; Out cout;
+  TB_TRY(crd0.acquire(Av.crd0 ? (void*)Av.crd0 : (void*)Av.pos1, sizeof(int32_t) * (size_t)stored));
+  TB_TRY(pos1.acquire(Av.pos1, sizeof(int32_t) * ((size_t)stored + 1)));
+  TB_TRY(crd.acquire(Av.crd1 ? (void*)Av.crd1 : (void*)Av.pos1, sizeof(int32_t) * (size_t)nnz));
+  TB_TRY(vals.acquire(Av.vals ? Av.vals : (void*)Av.pos1, es * (size_t)nnz));
+  TB_TRY(bin.acquire(Bv.vals, es * (size_t)Av.cols * K));
+  TB_TRY(cout.acquire(Cv.vals, es * (size_t)Av.rows * K));
+  if (Av.rows > 0 && K > 0) {
+    void* pos_full = nullptr;
+    TB_TRY(scratch_alloc(&pos_full, sizeof(int32_t) * ((size_t)Av.rows + 1)));
+    {
+      ProfScope ps("dcsr_expand_pos");
+      const size_t threads = ((size_t)stored + 1) * 32;
+      dcsr_expand_pos_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream()>>>(crd0.as<int>(), pos1.as<int>(), stored, Av.rows,
+                                                                                     (int*)pos_full);
+      count_launch(1);
+      TB_CUDA(cudaGetLastError());
+    }
+    const SpmmRange all{0, Av.rows, 0, nnz};
+    int rc;
+    if (Av.dt == DType::F32)
+      rc = spmm_launch<float>((const int*)pos_full, crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(), Av.rows, K, all, cm);
+    else
+      rc = spmm_launch<double>((const int*)pos_full, crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(), Av.rows, K, all, cm);
+    scratch_free(pos_full);
+    TB_TRY(rc);
+  }
+  TB_TRY(cout.commit());
+  return finish_call();
+}
+
+int taco_b200_spmm_dcsr_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B) {
+  TB_TRY(taco_b200_spmm_dcsr_assemble(C, A, B));
+  return taco_b200_spmm_dcsr_compute(C, A, B);
 }
 
 }  // extern "C"

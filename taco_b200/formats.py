@@ -106,3 +106,22 @@ def bcsr_to_dense(Mb, Nb, br, bc, pos, crd, vals):
     rows = np.repeat(np.arange(Mb), np.diff(pos))
     out[rows, crd] = np.asarray(vals).reshape(-1, br, bc)
     return out.transpose(0, 2, 1, 3).reshape(Mb * br, Nb * bc)
+
+
+def dcsr_from_dense(dense):
+    """dense (n, m) -> doubly compressed rows {Sparse,Sparse}: A1_pos[2], A1_crd[stored rows], A2_pos[stored rows+1],
+    A2_crd[nnz], A_vals[nnz]; a row is stored iff it has a nonzero (what taco's pack() produces)."""
+    dense = np.asarray(dense)
+    i, j = np.nonzero(dense)
+    rows, counts = np.unique(i, return_counts=True)
+    pos2 = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(counts, out=pos2[1:])
+    return dict(A1_pos=np.array([0, rows.size], np.int32), A1_crd=rows.astype(np.int32), A2_pos=pos2.astype(np.int32),
+                A2_crd=j.astype(np.int32), A_vals=np.ascontiguousarray(dense[i, j]))
+
+
+def dcsr_to_csr(n_rows, d):
+    """expand {Sparse,Sparse} level arrays to a CSR pos array over all n_rows rows (crd / vals are shared)"""
+    pos = np.zeros(n_rows + 1, dtype=np.int64)
+    pos[np.asarray(d["A1_crd"], dtype=np.int64) + 1] = np.diff(np.asarray(d["A2_pos"], dtype=np.int64))
+    return np.cumsum(pos).astype(np.int32)

@@ -50,6 +50,7 @@ class Format:
 
 CSR = Format([dense, compressed])
 CSF3 = Format([compressed, compressed, compressed])
+DCSR = Format([compressed, compressed])               # doubly compressed rows: only rows with nonzeros are stored
 BCSR = Format([dense, compressed, dense, dense])      # (block row, block column, row in block, column in block)
 
 
@@ -252,6 +253,17 @@ def makeCSF3(name, dims, arrays):
     t = Tensor(name, dims, CSF3, dt)
     for l in range(3):
         t.set_level(l, arrays[f"B{l + 1}_pos"], arrays[f"B{l + 1}_crd"])
+    t.set_vals(vals)
+    return t
+
+
+def makeDCSR(name, dims, arrays):
+    """arrays: dict with A1_pos,A1_crd,A2_pos,A2_crd,A_vals (taco_b200.formats.dcsr_from_dense layout), zero-copy."""
+    vals = arrays["A_vals"]
+    dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
+    t = Tensor(name, dims, DCSR, dt)
+    for l in range(2):
+        t.set_level(l, arrays[f"A{l + 1}_pos"], arrays[f"A{l + 1}_crd"])
     t.set_vals(vals)
     return t
 

@@ -153,6 +153,25 @@ def main():
                     inp = dict(dims=np.array([Mb, Nb, br, bc], np.int32), A_pos=p, A_crd=c, A_vals=v.reshape(-1), c=cv)
                     out = run_ref("bspmv", inp, sfx, "default")
                     cases[f"bspmv_{tag}_{sfx}_{br}x{bc}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    # ---- SpMM with a doubly compressed operand ({Sparse,Sparse}; the reference's spmmDCSRGPU test shape 102 x 103,
+    #      K = 128, sparsity .3, tests-scheduling-eval.cpp:1309-1358) -- here with many absent rows as well ----------
+    for integer in (True, False):
+        tag = "int" if integer else "frac"
+        for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
+            rng = np.random.default_rng(55001 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
+            for (n, m, K, sp, keep) in ((102, 103, 128, 0.3, 1.0), (300, 90, 20, 0.1, 0.15), (64, 50, 7, 0.2, 0.5)):
+                A = sparse_fill(rng, (n, m), sp, integer, dtype)
+                A[rng.random(n) >= keep] = 0                          # absent rows (not stored at level 0)
+                if keep < 1.0:
+                    A[0] = 0
+                    A[n - 1] = 0                                      # leading and trailing absent rows
+                d = formats.dcsr_from_dense(A)
+                B = dense_fill(rng, (m, K), integer, dtype)
+                inp = dict(dims=np.array([n, m, K], np.int32), B=B, **d)
+                out = run_ref("spmm_dcsr", inp, sfx, "default")
+                cases[f"dcsr_spmm_{tag}_{sfx}_{n}x{K}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    cases = {k: v for k, v in cases.items() if k.startswith(only)}
     for name, arrs in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
     print(f"wrote {len(cases)} golden cases to {OUT}")

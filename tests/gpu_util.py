@@ -12,6 +12,7 @@ except Exception:  # pragma: no cover
 EXPR = {
     "spmv": "y(i) = A(i,j) * x(j)",
     "spmm": "C(i,k) = A(i,j) * B(j,k)",
+    "spmm_dcsr": "C(i,k) = A(i,j) * B(j,k)",
     "sddmm": "A(i,j) = B(i,j) * C(i,k) * D(j,k)",
     "mttkrp": "A(i,j) = B(i,k,l) * C(k,j) * D(l,j)",
     "ttv": "A(i,j) = B(i,j,k) * c(k)",
@@ -62,6 +63,12 @@ def build(family, w, colmajor_c=False):
     elif family == "spmm":
         dt = np_dtype(w["A_vals"])
         A = tb.makeCSR("A", d[:2], w["A_pos"], w["A_crd"], w["A_vals"])
+        B = tb.makeDense("B", [d[1], d[2]], w["B"])
+        C = tb.Tensor("C", [d[0], d[2]], tb.Format([tb.dense, tb.dense], [1, 0] if colmajor_c else None), dt)
+        ts = [C, A, B]
+    elif family == "spmm_dcsr":
+        dt = np_dtype(w["A_vals"])
+        A = tb.makeDCSR("A", d[:2], w)
         B = tb.makeDense("B", [d[1], d[2]], w["B"])
         C = tb.Tensor("C", [d[0], d[2]], tb.Format([tb.dense, tb.dense], [1, 0] if colmajor_c else None), dt)
         ts = [C, A, B]

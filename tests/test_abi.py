@@ -47,6 +47,7 @@ CASES = [
     ("a(r) = M(r,c) * v(c)", "M:ds", "spmv"),                       # renaming, unlisted tensors are dense
     ("C(i,k) = A(i,j) * B(j,k)", "A:ds,B:dd,C:dd", "spmm"),
     ("C(i,k) = A(i,j) * B(j,k)", "A:ds,B:dd,C:dd:1,0", "spmm"),      # reference GPU test's column-major result
+    ("C(i,k) = A(i,j) * B(j,k)", "A:ss,B:dd,C:dd", "spmm_dcsr"),     # the reference's spmmDCSRGPU statement
     ("C(i,k) = A(i,j) * B(j,k)", "A:ds,B:ds,C:ds", "spgemm"),
     ("C(i,j) = A(i,j) + B(i,j)", "A:ds,B:ds,C:ds", "spadd"),
     ("A(i,j) = B(i,j) * C(i,k) * D(j,k)", "A:ds,B:ds,C:dd,D:dd", "sddmm"),

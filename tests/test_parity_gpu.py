@@ -102,6 +102,41 @@ def test_golden_spmm(name, space):
 
 
 @pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("dcsr_spmm"))
+def test_golden_spmm_dcsr(name, space):
+    # SpMM with a doubly compressed operand (the reference's spmmDCSRGPU statement): same kernel as CSR after the
+    # level-0 row list has been expanded on the device -> bit-identical to the reference, absent rows are zero rows
+    g = H.load_golden(name)
+    C = G.run("spmm_dcsr", place(_inputs(g), space))
+    assert np.array_equal(C, g["out_C"])
+    n, m, K = g["dims"]
+    Ct = G.run("spmm_dcsr", place(_inputs(g), space), colmajor_c=True)
+    assert np.array_equal(Ct.reshape(K, n).T.reshape(-1), g["out_C"])
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("keep", [0.0, 0.02, 0.6, 1.0])
+def test_oracle_spmm_dcsr(space, keep):
+    # R-MAT rows (hub rows included) with a fraction `keep` of the rows stored; keep = 0 is the empty operand
+    w = synth.make("spmm", None, scale=12, K=64, dtype="float32")
+    n, m, K = w["dims"]
+    rng = np.random.default_rng(11)
+    lens = np.diff(w["A_pos"])
+    stored = np.flatnonzero((rng.random(n) < keep) & (lens > 0)).astype(np.int32)
+    take = np.concatenate([np.arange(w["A_pos"][r], w["A_pos"][r + 1]) for r in stored]) if stored.size else np.zeros(0, np.int64)
+    pos2 = np.zeros(stored.size + 1, np.int32)
+    np.cumsum(lens[stored], out=pos2[1:])
+    d = dict(dims=w["dims"], A1_pos=np.array([0, stored.size], np.int32), A1_crd=stored, A2_pos=pos2,
+             A2_crd=w["A_crd"][take].astype(np.int32), A_vals=w["A_vals"][take], B=w["B"])
+    C = G.run("spmm_dcsr", place(d, space)).reshape(n, K)
+    want = oracle.spmm_dcsr(n, d["A1_pos"], d["A1_crd"], d["A2_pos"], d["A2_crd"], d["A_vals"], w["B"].reshape(m, K))
+    short = np.ones(n, bool)
+    short[stored] = lens[stored] <= 512
+    assert np.array_equal(C[short], want[short])
+    H.assert_close(C.reshape(-1), want.reshape(-1), np.float32)
+
+
+@pytest.mark.parametrize("space", SPACES)
 @pytest.mark.parametrize("name", H.golden_cases("sddmm"))
 def test_golden_sddmm(name, space):
     g = H.load_golden(name)
@@ -482,6 +517,21 @@ def test_bspmm_tensor_core_path_is_accurate_on_signed_data():
     want = A.astype(np.float64) @ B.astype(np.float64)
     err = np.abs(C.reshape(Mb * br, K) - want).max() / np.abs(want).max()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("br,K,deg", [(32, 128, 70), (16, 256, 45), (32, 8, 3), (16, 4, 5), (32, 260, 33)])
+def test_bspmm_long_block_rows_and_narrow_or_ragged_tiles(space, br, K, deg):
+    # block rows with more than 32 stored blocks (the TMA warp reads block columns 32 at a time), dense operands narrower
+    # than one 32-column tensor box, and a last column tile that is partly out of bounds (zero-filled by TMA)
+    Mb = 24
+    w = synth.make("bspmm", None, Mb=Mb, deg=min(deg, Mb), br=br, bc=br, K=K, dtype="float32")
+    if deg > Mb:                           # wider than tall: more block columns than block rows
+        w = synth.make("bspmm", None, Mb=96, deg=deg, br=br, bc=br, K=K, dtype="float32")
+        Mb = 96
+    C = G.run("bspmm", place(w, space))
+    want = oracle.bspmm(w["A_pos"], w["A_crd"], w["A_vals"].reshape(-1, br, br), w["B"].reshape(Mb * br, K), br, br)
+    _bspmm_check(C, want, br, br, K, "float32")
 
 
 def test_bspmm_empty_and_errors():

@@ -22,8 +22,9 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-for v in 0 11 12 13 4; do run bspmm TACO_B200_BENCH_BLOCK=16 TACO_B200_BSPMM_VARIANT=$v; done
-run bspmm TACO_B200_BENCH_BLOCK=16 TACO_B200_BSPMM_TC=0
-ncuq bspmm bspmm_t TACO_B200_BENCH_BLOCK=16
-} > gpurun_out/exp_8.txt 2>&1
-cat gpurun_out/exp_8.txt
+timeout 600 python -m pytest tests -m gpu -q -k "dcsr or bspm" 2>&1 | tail -5
+run bspmm X=0
+run bspmm TACO_B200_BSPMM_VARIANT=13
+run bspmm TACO_B200_BENCH_BLOCK=16
+} > gpurun_out/exp_9.txt 2>&1
+cat gpurun_out/exp_9.txt
