@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the taco GPU hot path on B200, next to the reference's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm|ttv|ttm]
     python bench.py --impl reference ...          # the reference's own C/OpenMP codegen on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU; rank 0 prints the JSON line)
 
@@ -37,9 +37,11 @@ FLOPS = {   # per step, as the reference counts them
     "spadd": lambda s: 1.0 * s["nnzC"],
     "spgemm": lambda s: 2.0 * s["products"],
     "bspmm": lambda s: 2.0 * s["nnzb"] * s["br"] * s["bc"] * s["K"],
+    "ttv": lambda s: 2.0 * s["nnz"],
+    "ttm": lambda s: 2.0 * s["nnz"] * s["R"],
 }
 DOMINANT = {"spmv": "spmv_csr", "spmm": "spmm_csr", "sddmm": "sddmm_csr", "mttkrp": "mttkrp_csf",
-            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr"}
+            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr", "ttv": "ttv_csf", "ttm": "ttm_csf"}
 
 
 def algorithmic_bytes(wl, s):
@@ -57,6 +59,10 @@ def algorithmic_bytes(wl, s):
         return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * (4 + e) + 12 * (s["rows"] + 1)
     if wl == "spgemm":     # fill pass (sort + compress): A, the gathered B rows (crd + vals), the result, all pos arrays
         return (4 + e) * (s["nnzA"] + s["products"] + s["nnzC"]) + 12 * (s["rows"] + 1)
+    if wl == "ttv":        # leaves + fiber / slice level arrays + c + the dense (I x K) result written once
+        return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * (s["Ld"] + s["I"] * s["Kd"])
+    if wl == "ttm":        # + every row of C and of the (I*K x R) result touched once
+        return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * s["R"] * (s["Ld"] + s["I"] * s["Kd"])
     if wl == "bspmm":      # blocks streamed once, every row of B and C touched once
         return 4 * (s["Mb"] + 1) + s["nnzb"] * (4 + e * s["br"] * s["bc"]) + e * s["K"] * (s["Nb"] * s["bc"] + s["Mb"] * s["br"])
     raise KeyError(wl)
@@ -74,6 +80,9 @@ def sizes_of(wl, w, extra=None):
     elif wl == "mttkrp":
         s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3], nnz=int(w["B3_crd"].shape[0]), nfib=int(w["B2_crd"].shape[0]),
                  nslices=int(w["B1_crd"].shape[0]))
+    elif wl in ("ttv", "ttm"):
+        s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3] if wl == "ttm" else 1, nnz=int(w["B3_crd"].shape[0]),
+                 nfib=int(w["B2_crd"].shape[0]), nslices=int(w["B1_crd"].shape[0]))
     elif wl == "bspmm":
         s.update(Mb=d[0], Nb=d[1], br=d[2], bc=d[3], K=d[4], nnzb=int(w["A_crd"].shape[0]))
     else:
@@ -144,7 +153,8 @@ def make_workload(wl, device, rank, scale_down):
     if scale_down:    # quick functional runs (tests); never used for reported numbers
         over = {"spmm": dict(scale=16), "spmv": dict(n=100_000), "sddmm": dict(n=100_000),
                 "mttkrp": dict(I=100_000, K=20_000, L=20_000, nnz=2_000_000), "spadd": dict(n=100_000),
-                "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048)}[wl]
+                "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048), "ttv": dict(I=512, K=512, L=50_000, nnz=2_000_000),
+                "ttm": dict(I=128, K=128, L=50_000, nnz=1_000_000)}[wl]
     if wl == "bspmm" and os.environ.get("TACO_B200_BENCH_BLOCK"):      # block-shape sweep (experiments only): 16 -> 16x16 blocks,
         b = int(os.environ["TACO_B200_BENCH_BLOCK"])                  # same matrix dimension and number of stored values
         over.update(br=b, bc=b, Mb=over.get("Mb", 32768) * 32 // b, deg=16 * 32 // b)
@@ -204,7 +214,7 @@ def reference_sample(wl, w, budget_rows):
                  C=G.to_host(w["C"][: rows * K]), D=G.to_host(w["D"]))
         dims = [rows, int(w["dims"][1]), K]
         frac = nz / max(int(w["B_crd"].shape[0]), 1)
-    elif wl == "mttkrp":
+    elif wl in ("mttkrp", "ttv", "ttm"):
         ns = min(budget_rows, int(w["B1_crd"].shape[0]))
         p2 = G.to_host(w["B2_pos"][: ns + 1])
         nf = int(p2[-1])
@@ -212,8 +222,13 @@ def reference_sample(wl, w, budget_rows):
         nz = int(p3[-1])
         h.update(B1_pos=np.array([0, ns], np.int32), B1_crd=G.to_host(w["B1_crd"][:ns]), B2_pos=p2,
                  B2_crd=G.to_host(w["B2_crd"][:nf]), B3_pos=p3, B3_crd=G.to_host(w["B3_crd"][:nz]),
-                 B_vals=G.to_host(w["B_vals"][:nz]), C=G.to_host(w["C"]), D=G.to_host(w["D"]))
+                 B_vals=G.to_host(w["B_vals"][:nz]))
         dims = [int(x) for x in w["dims"]]
+        if wl == "mttkrp":
+            h.update(C=G.to_host(w["C"]), D=G.to_host(w["D"]))
+        else:               # dense (I x K [x R]) result: only the slab's leading rows
+            dims[0] = int(h["B1_crd"][-1]) + 1 if ns else 1
+            h.update(c=G.to_host(w["c"])) if wl == "ttv" else h.update(C=G.to_host(w["C"]))
         frac = nz / max(int(w["B3_crd"].shape[0]), 1)
     h["dims"] = np.array(dims, np.int32)
     return h, frac
@@ -254,6 +269,8 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
         "mttkrp": lambda: oracle.mttkrp(h, h["C"].reshape(d[1], -1), h["D"].reshape(d[2], -1), d[0]),
         "spadd": lambda: oracle.spadd(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"]),
         "spgemm": lambda: oracle.spgemm(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"], d[-1]),
+        "ttv": lambda: oracle.ttv(h, h["c"], d[0], d[1]),
+        "ttm": lambda: oracle.ttm(h, h["C"].reshape(d[2], -1), d[0], d[1]),
         "bspmm": lambda: oracle.bspmm(h["A_pos"], h["A_crd"], h["A_vals"].reshape(-1, d[2], d[3]),
                                       h["B"].reshape(d[1] * d[3], -1), d[2], d[3]),
     }[wl]
@@ -267,7 +284,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
 
 
 SAMPLE_ROWS = {"spmm": 1 << 19, "spmv": 1_000_000, "sddmm": 250_000, "mttkrp": 500_000, "spadd": 1_000_000,
-               "spgemm": 200_000, "bspmm": 2048}
+               "spgemm": 200_000, "bspmm": 2048, "ttv": 1024, "ttm": 64}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -487,6 +504,10 @@ def workload_name(wl, s):
     if wl == "bspmm":
         return (f"BCSR SpMM fp32 {s['Mb'] * s['br']}x{s['Nb'] * s['bc']} in {s['br']}x{s['bc']} blocks, "
                 f"{s['nnzb']} stored blocks, K={s['K']}")
+    if wl == "ttv":
+        return f"CSF TTV fp64 {s['I']}x{s['Kd']}x{s['Ld']} nnz={s['nnz']} (dense {s['I']}x{s['Kd']} result)"
+    if wl == "ttm":
+        return f"CSF TTM fp64 {s['I']}x{s['Kd']}x{s['Ld']} nnz={s['nnz']} R={s['R']} (dense result)"
     if wl == "mttkrp":
         return f"CSF MTTKRP fp64 {s['I']}x{s['Kd']}x{s['Ld']} nnz={s['nnz']} R={s['R']}"
     return f"CSR {wl} fp64 {s['rows']} rows nnzA={s['nnzA']} nnzB={s['nnzB']} (GPU assembly + numeric)"

@@ -1,8 +1,8 @@
 // csf.cu -- order-3 CSF kernels: MTTKRP, TTV, TTM.  B is {Compressed,Compressed,Compressed}, mode order 0,1,2.
 //
 //   MTTKRP  A(i,j)   = B(i,k,l) * C(k,j) * D(l,j)      replaces scheduleMTTKRPGPU (tests-scheduling-eval.cpp:327-342)
-//   TTV     A(i,j)   = B(i,j,k) * c(k)                 replaces scheduleTTVGPU    (:308-325)
-//   TTM     A(i,j,l) = B(i,j,k) * C(k,l)               replaces scheduleTTMGPU    (:289-306)
+//   TTV     A(i,j)   = B(i,j,k) * c(k)                 replaces scheduleTTVGPU    (:308-325)   = SpMV over the fibers (spmv.cu)
+//   TTM     A(i,j,l) = B(i,j,k) * C(k,l)               replaces scheduleTTMGPU    (:289-306)   = SpMM over the fibers (spmm.cu)
 //
 // The reference's GPU MTTKRP nnz-splits the leaf level, runs two block-start binary
 // searches (taco_binarySearchBeforeBlock + IndirectBeforeBlock, codegen_cuda.cpp:110-141) and issues one global
@@ -373,9 +373,55 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
   return TACO_B200_OK;
 }
 
+// spmv.cu / spmm.cu
+int spmv_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* x, void* y, int rows, int nnz,
+                const unsigned* ymap, const char* prof_name);
+int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int K, int nnz,
+                const unsigned* rowmap, const char* prof_name);
+
+// fiber_cell[f] = B1_crd[s] * Kdim + B2_crd[f] for every fiber f of slice s: where the fiber's result lives in the dense
+// (i,j) plane of A.  One warp per slice, coalesced over its fibers.
+__global__ void __launch_bounds__(256)
+csf3_fiber_cells_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
+                        const int* __restrict__ B2_crd, unsigned Kdim, unsigned* __restrict__ cell) {
+  const int nslices = __ldg(B1_pos + 1) - __ldg(B1_pos);
+  const int lane = threadIdx.x & 31;
+  for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int iB = __ldg(B1_pos) + (int)s;
+    const unsigned base = (unsigned)__ldg(B1_crd + iB) * Kdim;
+    const int f1 = __ldg(B2_pos + iB + 1);
+    for (int f = __ldg(B2_pos + iB) + lane; f < f1; f += 32) cell[f] = base + (unsigned)__ldg(B2_crd + f);
+  }
+}
+
+static int fiber_cells(CsfCall& cc, int Kdim, void** cell) {
+  TB_TRY(scratch_alloc(cell, sizeof(unsigned) * (size_t)cc.nfib));
+  long long ctas = ((long long)cc.nslices * 32 + 255) / 256;
+  const int grid = (int)(ctas < (1 << 20) ? (ctas > 0 ? ctas : 1) : (1 << 20));
+  csf3_fiber_cells_kernel<<<grid, 256, 0, stream()>>>(cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(),
+                                                     (unsigned)Kdim, (unsigned*)*cell);
+  count_launch(1);
+  return TACO_B200_OK;
+}
+
+// TTM = SpMM over the fibers: "row" f has the leaves [B3_pos[f], B3_pos[f+1]), gathers rows of C and is stored at row
+// fiber_cell[f] of the (I*K) x R result.  The nnz-balanced slot kernel of spmm.cu keeps the reference's order (leaf
+// order, separate multiply and add).  TACO_B200_TTM_VARIANT=1 selects the warp-per-fiber kernel this replaced.
 template <typename T>
 static int ttm_launch(CsfCall& cc, const T* C, T* A, size_t a_count, int R, int Kdim) {
   TB_CUDA(cudaMemsetAsync(A, 0, a_count * sizeof(T), stream()));
+  static const int variant = getenv("TACO_B200_TTM_VARIANT") ? atoi(getenv("TACO_B200_TTM_VARIANT")) : 0;
+  if (cc.nfib > 0 && R > 0 && variant == 0 && a_count / (size_t)R <= 0xFFFFFFFFull && cc.nnz <= INT32_MAX - 65536) {
+    void* cell = nullptr;
+    TB_TRY(fiber_cells(cc, Kdim, &cell));
+    const int rc = spmm_mapped(sizeof(T) == 8 ? DType::F64 : DType::F32, cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, A,
+                               cc.nfib, R, cc.nnz, (const unsigned*)cell, "ttm_csf");
+    scratch_free(cell);
+    count_launch(1);
+    TB_TRY(rc);
+    TB_CUDA(cudaGetLastError());
+    return TACO_B200_OK;
+  }
   if (cc.nfib > 0 && R > 0) {
     long long ctas = ((long long)cc.nfib + CSF_WARPS - 1) / CSF_WARPS;
     int grid = (int)(ctas < (1 << 22) ? ctas : (1 << 22));
@@ -389,9 +435,25 @@ static int ttm_launch(CsfCall& cc, const T* C, T* A, size_t a_count, int R, int 
   return TACO_B200_OK;
 }
 
+// TTV = SpMV over the fibers: "row" f has the leaves [B3_pos[f], B3_pos[f+1]) and is stored at A[fiber_cell[f]].  The
+// nnz-balanced single-kernel SpMV (spmv.cu) keeps the reference's order (scalar accumulator, ascending leaf position).
+// TACO_B200_TTV_VARIANT=1 selects the thread-per-fiber kernel this replaced.
 template <typename T>
 static int ttv_launch(CsfCall& cc, const T* c, T* A, size_t a_count, int Kdim) {
   TB_CUDA(cudaMemsetAsync(A, 0, a_count * sizeof(T), stream()));
+  static const int variant = getenv("TACO_B200_TTV_VARIANT") ? atoi(getenv("TACO_B200_TTV_VARIANT")) : 0;
+  const bool aligned = ((((uintptr_t)cc.c3.dptr) | ((uintptr_t)cc.vals.dptr)) & 15) == 0;
+  if (cc.nfib > 0 && variant == 0 && aligned && a_count <= 0xFFFFFFFFull && cc.nnz <= INT32_MAX - 65536) {
+    void* cell = nullptr;
+    TB_TRY(fiber_cells(cc, Kdim, &cell));
+    count_launch(1);
+    const int rc = spmv_mapped(sizeof(T) == 8 ? DType::F64 : DType::F32, cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), c, A,
+                               cc.nfib, cc.nnz, (const unsigned*)cell, "ttv_csf");
+    scratch_free(cell);
+    TB_TRY(rc);
+    TB_CUDA(cudaGetLastError());
+    return TACO_B200_OK;
+  }
   if (cc.nfib > 0) {
     long long ctas = ((long long)cc.nfib + 255) / 256;
     int grid = (int)(ctas < (1 << 22) ? ctas : (1 << 22));

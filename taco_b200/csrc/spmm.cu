@@ -48,13 +48,13 @@ __device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p, uint64
 }
 
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void store_row(T* __restrict__ C, int row, int col, int rows, int K, const Frag<T, VEC>& f,
+__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f,
                                           uint64_t strm) {
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) C[(size_t)(col + e) * rows + row] = f.v[e];
   } else {
-    T* p = C + (size_t)row * K + col;
+    T* p = C + row * K + col;
     if constexpr (VEC == 4 && sizeof(T) == 4) {
       asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
                    "f"(f.v[3]) : "memory");
@@ -70,12 +70,12 @@ __device__ __forceinline__ void store_row(T* __restrict__ C, int row, int col, i
 }
 
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void red_row(T* __restrict__ C, int row, int col, int rows, int K, const Frag<T, VEC>& f) {
+__device__ __forceinline__ void red_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f) {
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) atomicAdd(C + (size_t)(col + e) * rows + row, f.v[e]);
   } else {
-    T* p = C + (size_t)row * K + col;
+    T* p = C + row * K + col;
     if constexpr (VEC == 4 && sizeof(T) == 4) {
       asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
                    "f"(f.v[3]) : "memory");
@@ -92,9 +92,11 @@ struct SpmmRange { int r0, r1, p0, p1; };
 
 // Pre-pass: slot_rows[w] = first row whose first nonzero is at or after p0 + w*W; slot_rows[nslots] = r1.
 // Also zeroes the C row of every hub row (done by the slot in which the hub row's first slot boundary falls).
-template <typename T, bool COLMAJOR>
+// RMAP (here and in spmm_csr_kernel): result row r is stored at row rowmap[r] of C (TTM: the rows are the fibers of a CSF
+// tensor, rowmap their cells in the dense (i,j) plane, csf.cu); the unmapped instantiations are unchanged by the flag.
+template <typename T, bool COLMAJOR, bool RMAP = false>
 __global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg, int rows, int nslots, int K,
-                                      int* __restrict__ slot_rows, T* __restrict__ C) {
+                                      int* __restrict__ slot_rows, T* __restrict__ C, const unsigned* __restrict__ rowmap = nullptr) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > nslots) return;
   if (w == nslots) { slot_rows[w] = rg.r1; return; }
@@ -104,8 +106,9 @@ __global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg,
     int i = tbd::search_last_le(pos, rg.r0, rg.r1, lo);      // the row that contains nonzero `lo`
     int s = __ldg(pos + i), e = __ldg(pos + i + 1);
     if (e - s > SPMM_LONG && lo - s < SPMM_W) {
-      if constexpr (COLMAJOR) { for (int k = 0; k < K; k++) C[(size_t)k * rows + i] = T(0); }
-      else { for (int k = 0; k < K; k++) C[(size_t)i * K + k] = T(0); }
+      const size_t orow = RMAP ? (size_t)__ldg(rowmap + i) : (size_t)i;
+      if constexpr (COLMAJOR) { for (int k = 0; k < K; k++) C[(size_t)k * rows + orow] = T(0); }
+      else { for (int k = 0; k < K; k++) C[orow * K + k] = T(0); }
     }
   }
 }
@@ -162,11 +165,11 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
   }
 }
 
-template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                const int* __restrict__ slot_rows) {
+                const int* __restrict__ slot_rows, const unsigned* __restrict__ rowmap = nullptr) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
@@ -209,7 +212,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     while (empty) {
       const int h = __ffs(empty) - 1;
       empty &= empty - 1;
-      if (active) store_row<T, VEC, COLMAJOR>(C, rb + h, col, rows, K, acc, strm);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, strm);
     }
     while (full) {
       const int h = __ffs(full) - 1;
@@ -222,8 +225,9 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
       spmm_accumulate<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane, keep, strm);
       if (active) {
-        if (hub) red_row<T, VEC, COLMAJOR>(C, rowbase + h, col, rows, K, acc);
-        else store_row<T, VEC, COLMAJOR>(C, rowbase + h, col, rows, K, acc, strm);
+        const size_t orow = RMAP ? (size_t)__ldg(rowmap + rowbase + h) : (size_t)(rowbase + h);
+        if (hub) red_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc);
+        else store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc, strm);
       }
     }
   }
@@ -472,6 +476,39 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   scratch_free(slot_rows);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
+}
+
+// Row-mapped launch (csf.cu, TTM): C[rowmap[r], :] = sum_p vals[p] * B[crd[p], :] over the rows r of any (pos, crd, vals) level.
+template <typename T, int VEC>
+static int spmm_mapped_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz,
+                            const unsigned* rowmap, const char* prof_name) {
+  const SpmmRange rg{0, rows, 0, nnz};
+  const int nslots = nnz > 0 ? (nnz + SPMM_W - 1) / SPMM_W : 1;
+  void* slot_rows = nullptr;
+  TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
+  spmm_slot_rows_kernel<T, false, true><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rg, rows, nslots, K, (int*)slot_rows, C, rowmap);
+  {
+    ProfScope ps(prof_name);
+    constexpr int WARPS = 8;
+    dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
+    spmm_csr_kernel<T, VEC, false, 2, WARPS, 8, true><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
+                                                                                       (const int*)slot_rows, rowmap);
+  }
+  count_launch(2);
+  scratch_free(slot_rows);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
+int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int K, int nnz,
+                const unsigned* rowmap, const char* prof_name) {
+  const bool a16 = (((uintptr_t)B | (uintptr_t)C) & 15) == 0;
+  if (dt == DType::F64) {
+    if (a16 && K % 2 == 0) return spmm_mapped_impl<double, 2>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, K, nnz, rowmap, prof_name);
+    return spmm_mapped_impl<double, 1>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, K, nnz, rowmap, prof_name);
+  }
+  if (a16 && K % 4 == 0) return spmm_mapped_impl<float, 4>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, K, nnz, rowmap, prof_name);
+  return spmm_mapped_impl<float, 1>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, K, nnz, rowmap, prof_name);
 }
 
 template <typename T>

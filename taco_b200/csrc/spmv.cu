@@ -90,11 +90,13 @@ __device__ __forceinline__ T spmv_block_sum(const T* prod, int a, int b, T* red)
   return tot;
 }
 
-template <typename T, int MINB>
+// MAPPED: row r is stored at y[ymap[r]] instead of y[r] (TTV: the rows are the fibers of a CSF tensor and ymap holds their
+// positions in the dense result, csf.cu); the unmapped instantiation is unchanged by the flag.
+template <typename T, int MINB, bool MAPPED>
 __global__ void __launch_bounds__(SPMV_THREADS, MINB)
 spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
-                int* __restrict__ flag, int epoch) {
+                int* __restrict__ flag, int epoch, const unsigned* __restrict__ ymap) {
   __shared__ T prod[SPMV_TILE + SPMV_OV];
   __shared__ T red[SPMV_THREADS / 32];
   __shared__ int s_cnt[SPMV_THREADS / 32];
@@ -169,7 +171,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     if (e <= hiov) {
       T acc = T(0);
       for (int q = s - lo; q < e - lo; q++) acc += prod[q];
-      y[r] = acc;
+      if constexpr (MAPPED) y[__ldg(ymap + r)] = acc;
+      else y[r] = acc;
     } else {                                       // only the last owned row can run past the overlap
       T acc = T(0);
       for (int q = s - lo; q < hi - lo; q++) acc += prod[q];
@@ -202,7 +205,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
             acc = (bb == b0) ? pv : acc + pv;
           }
           for (int q = 0; q < e_head - lo; q++) acc += prod[q];
-          y[r_lo - 1] = acc;
+          if constexpr (MAPPED) y[__ldg(ymap + r_lo - 1)] = acc;
+          else y[r_lo - 1] = acc;
         }
       }
     }
@@ -217,7 +221,8 @@ static int g_spmv_cap = 0;
 static int g_spmv_epoch = 0;
 
 template <typename T>
-static int spmv_launch(const CsrView& A, const In& pos, const In& crd, const In& vals, const In& x, Out& y, int nnz) {
+static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const T* x, T* y, int rows, int nnz, const unsigned* ymap,
+                           const char* prof_name) {
   const int ntiles = nnz > 0 ? (nnz + SPMV_TILE - 1) / SPMV_TILE : 1;
   if (ntiles > g_spmv_cap) {
     if (g_spmv_partial) { cudaFree(g_spmv_partial); cudaFree(g_spmv_flag); }
@@ -233,19 +238,31 @@ static int spmv_launch(const CsrView& A, const In& pos, const In& crd, const In&
   }
   static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
   {
-    ProfScope ps("spmv_csr");
-#define TB_SPMV_GO(MINB)                                                                                               \
-  spmv_csr_kernel<T, MINB><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<T>(), x.as<T>(), \
-                                                                  y.as<T>(), A.rows, nnz, (T*)g_spmv_partial, g_spmv_flag, \
-                                                                  g_spmv_epoch)
-    if (variant == 1) TB_SPMV_GO(8);
-    else if (variant == 2) TB_SPMV_GO(7);
-    else TB_SPMV_GO(6);
+    ProfScope ps(prof_name);
+#define TB_SPMV_GO(MINB, MAPPED)                                                                                       \
+  spmv_csr_kernel<T, MINB, MAPPED><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz, (T*)g_spmv_partial, \
+                                                                          g_spmv_flag, g_spmv_epoch, ymap)
+    if (ymap) TB_SPMV_GO(6, true);
+    else if (variant == 1) TB_SPMV_GO(8, false);
+    else if (variant == 2) TB_SPMV_GO(7, false);
+    else TB_SPMV_GO(6, false);
 #undef TB_SPMV_GO
   }
   count_launch(1);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
+}
+
+template <typename T>
+static int spmv_launch(const CsrView& A, const In& pos, const In& crd, const In& vals, const In& x, Out& y, int nnz) {
+  return spmv_launch_raw<T>(pos.as<int>(), crd.as<int>(), vals.as<T>(), x.as<T>(), y.as<T>(), A.rows, nnz, nullptr, "spmv_csr");
+}
+
+// csf.cu: y[ymap[r]] = sum_p vals[p] * x[crd[p]] over the "rows" r of any (pos, crd, vals) level (TTV over the fibers)
+int spmv_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* x, void* y, int rows, int nnz,
+                const unsigned* ymap, const char* prof_name) {
+  if (dt == DType::F64) return spmv_launch_raw<double>(pos, crd, (const double*)vals, (const double*)x, (double*)y, rows, nnz, ymap, prof_name);
+  return spmv_launch_raw<float>(pos, crd, (const float*)vals, (const float*)x, (float*)y, rows, nnz, ymap, prof_name);
 }
 
 int csr_nnz(const CsrView& A, int32_t vals_size_hint, int32_t* nnz) {

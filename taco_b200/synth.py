@@ -311,6 +311,9 @@ FULL = {
     "mttkrp": dict(I=10_000_000, K=1_000_000, L=1_000_000, nnz=200_000_000, R=32, dtype="float64"),
     "spadd": dict(n=1_000_000, deg=10, dtype="float64"),
     "spgemm": dict(n=1_000_000, deg=10, dtype="float64"),
+    # TTV / TTM: dense results, so the (i,j) plane is kept small enough to hold A in HBM
+    "ttv": dict(I=8192, K=8192, L=1_000_000, nnz=100_000_000, dtype="float64"),
+    "ttm": dict(I=1024, K=1024, L=1_000_000, nnz=50_000_000, R=32, dtype="float64"),
     # blocked SpMM: 1Mi x 1Mi in 32 x 32 blocks, 16 stored blocks per block row, K = 128
     "bspmm": dict(Mb=32768, deg=16, br=32, bc=32, K=128, dtype="float32"),
 }
@@ -337,6 +340,14 @@ def make(workload, device=None, **over):
         t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 9, dt)
         t.update(dims=(p["I"], p["K"], p["L"], p["R"]), C=dense(xp, p["K"], p["R"], SEED0 + 14, dt),
                  D=dense(xp, p["L"], p["R"], SEED0 + 15, dt))
+        return t
+    if workload == "ttv":
+        t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 24, dt)
+        t.update(dims=(p["I"], p["K"], p["L"]), c=dense(xp, p["L"], 1, SEED0 + 28, dt))
+        return t
+    if workload == "ttm":
+        t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 30, dt)
+        t.update(dims=(p["I"], p["K"], p["L"], p["R"]), C=dense(xp, p["L"], p["R"], SEED0 + 34, dt))
         return t
     if workload in ("spadd", "spgemm"):
         ap, ac, av = csr_fixed_degree(xp, p["n"], p["n"], p["deg"], SEED0 + 16, dt)

@@ -288,6 +288,33 @@ def test_oracle_ttv_ttm():
 
 
 @pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("dtype,R", [("float64", 32), ("float64", 7), ("float32", 64), ("float32", 5)])
+def test_oracle_ttv_ttm_long_fibers(space, dtype, R):
+    # few (i,j) cells, long fibers: fibers of thousands of leaves span several 2048-leaf SpMV tiles (hand-over between
+    # tiles) and several 64-leaf SpMM slots (hub rows, combined with red.global.add); empty slices and cells in between
+    I, K, L = 37, 23, 6000
+    w = synth.make("mttkrp", None, I=I, K=K, L=L, nnz=600_000, R=R, dtype=dtype)
+    t = {k: v for k, v in w.items() if k.startswith("B")}
+    lens = np.diff(t["B3_pos"])
+    assert lens.max() > 600
+    c = w["D"].reshape(L, R)[:, 0].copy()
+    A = G.run("ttv", place(dict(dims=[I, K, L], c=c, **t), space)).reshape(I, K)
+    want = oracle.ttv(t, c, I, K)
+    H.assert_close(A.reshape(-1), want.reshape(-1), np.dtype(dtype))
+    A = G.run("ttm", place(dict(dims=[I, K, L, R], C=w["D"], **t), space)).reshape(I, K, R)
+    want = oracle.ttm(t, w["D"].reshape(L, R), I, K)
+    H.assert_close(A.reshape(-1), want.reshape(-1), np.dtype(dtype))
+    # a tensor whose fibers are all short keeps the reference's order exactly
+    w = synth.make("mttkrp", None, I=400, K=300, L=L, nnz=300_000, R=R, dtype=dtype)
+    t = {k: v for k, v in w.items() if k.startswith("B")}
+    A = G.run("ttm", place(dict(dims=[400, 300, L, R], C=w["D"], **t), space)).reshape(400, 300, R)
+    assert np.array_equal(A, oracle.ttm(t, w["D"].reshape(L, R), 400, 300))
+    c = w["D"].reshape(L, R)[:, 0].copy()
+    A = G.run("ttv", place(dict(dims=[400, 300, L], c=c, **t), space)).reshape(400, 300)
+    assert np.array_equal(A, oracle.ttv(t, c, 400, 300))
+
+
+@pytest.mark.parametrize("space", SPACES)
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_oracle_spadd(space, dtype):
     w = synth.make("spadd", None, n=100_003, deg=10, dtype=dtype)

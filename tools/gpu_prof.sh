@@ -2,7 +2,7 @@
 # ncu captures of the dominant kernel of each workload (one launch, --set full) + launch list of our kernels only.
 # usage: tools/gpu_prof.sh "spmm:spmm_csr_kernel spmv:spmv_csr_kernel ..."   outputs: gpurun_out/ncu_<wl>.ncu-rep, launches_<wl>.csv
 mkdir -p gpurun_out
-OURS='regex:^(spmm|spmv|sddmm|csf3|spadd|spgemm|slot_first|scan_|partition|mttkrp|csr_|csf_)'
+OURS='regex:^(spmm|spmv|sddmm|csf3|spadd|spgemm|slot_first|scan_|partition|mttkrp|csr_|csf_|bspm|dcsr)'
 for item in $1; do
   wl=${item%%:*}; kern=${item##*:}
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kern --launch-skip 3 -c 1 -f \
