@@ -172,6 +172,16 @@ int taco_b200_spgemm_assemble(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t*
 int taco_b200_spgemm_compute (taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
 int taco_b200_spgemm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B);
 
+/* COO -> level arrays on the device: the replacement for TensorBase::pack()'s host qsort + JIT-compiled `pack` helper
+ * (src/tensor.cpp:295-463; helper signature `int pack(taco_tensor_t* A, taco_tensor_t* B)`, src/tensor.cpp:932-1000).
+ * `coo` is the reference's coordinate-buffer tensor: every level "sparse", indices[0][0] = int32{0, n}, indices[l][1] =
+ * the n coordinates of level l, vals = the n components (host or device arrays; ANY order -- the sort happens here).
+ * `A` gives the target format -- {Dense,Compressed}, {Compressed,Compressed} or {Compressed,Compressed,Compressed},
+ * identity mode ordering -- and receives freshly allocated pos / crd / vals in the configured result space, exactly as
+ * an assemble call does; A->vals_size = number of stored components.  Equal coordinates are added (insertion order). */
+int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo);
+int _shim_taco_b200_pack(void** p);
+
 /* ---- module object: the replacement for ir::Module on the GPU path ------------------------------------ */
 /* expr    : index notation as the CLI / Tensor API prints it, e.g. "y(i) = A(i,j) * x(j)"
  * formats : comma separated per-tensor level formats in CLI syntax (tools/taco.cpp -f=), e.g. "A:ds,x:d,y:d";

@@ -203,3 +203,52 @@ def spgemm(Apos, Acrd, Aval, Bpos, Bcrd, Bval, ncols):
     n = Apos.size - 1
     return _sparse_out(lib().oracle_spgemm_assemble, "oracle_spgemm_compute_", n,
                        [ctypes.c_int32(n), ctypes.c_int32(ncols)], [Apos, Acrd, Bpos, Bcrd], Aval, Bval)
+
+
+def pack(kind, dims, coords, vals):
+    """TensorBase::pack() restated (src/tensor.cpp:295-463): sort the coordinates lexicographically, add the values of
+    equal coordinates, build the level arrays of {Dense,Compressed} ("csr"), {Compressed,Compressed} ("dcsr") or
+    {Compressed x3} ("csf3") the way the generated `pack` helper appends them.  The sort here is stable, so duplicates are
+    added in insertion order (the reference's qsort leaves that order unspecified).  Returns a dict of level arrays named
+    like oracle/ref_harness.cpp's pack output: A<level>_pos / A<level>_crd (compressed levels only) and A_vals."""
+    coords = [np.asarray(c, dtype=np.int64) for c in coords]
+    vals = np.ascontiguousarray(vals)
+    n = vals.size
+    order = len(coords)
+    perm = np.lexsort(coords[::-1]) if n else np.zeros(0, np.int64)          # stable, first mode most significant
+    sc = [c[perm] for c in coords]
+    sv = vals[perm]
+    new = np.ones(n, bool)
+    if n:
+        new[1:] = np.logical_or.reduce([c[1:] != c[:-1] for c in sc])
+    start = np.flatnonzero(new)
+    out_vals = np.zeros(start.size, dtype=vals.dtype)
+    ends = np.append(start[1:], n)
+    for u, (a, b) in enumerate(zip(start, ends)):                              # sequential adds, insertion order
+        acc = sv[a]
+        for e in range(a + 1, b):
+            acc = acc + sv[e]
+        out_vals[u] = acc
+    uc = [c[start] for c in sc]                                                # distinct coordinates, sorted
+    res = {"A_vals": out_vals}
+    nu = start.size
+    if kind == "csr":
+        pos = np.zeros(dims[0] + 1, np.int64)
+        np.add.at(pos, uc[0] + 1, 1)
+        res.update(A2_pos=np.cumsum(pos).astype(np.int32), A2_crd=uc[1].astype(np.int32))
+        return res
+    # compressed levels from the top: nodes of level l = distinct prefixes (c0..cl)
+    parent_ids = np.zeros(nu, np.int64)
+    nparents = 1
+    for l in range(order):
+        head = np.ones(nu, bool)
+        if nu:
+            head[1:] = np.logical_or.reduce([c[1:] != c[:-1] for c in uc[: l + 1]])
+        node = np.cumsum(head) - 1                                             # node index of every distinct entry
+        nnodes = int(head.sum())
+        pos = np.zeros(nparents + 1, np.int64)
+        np.add.at(pos, parent_ids[head] + 1, 1)
+        res[f"A{l + 1}_pos"] = np.cumsum(pos).astype(np.int32)
+        res[f"A{l + 1}_crd"] = uc[l][head].astype(np.int32)
+        parent_ids, nparents = node, nnodes
+    return res

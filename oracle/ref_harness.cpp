@@ -10,7 +10,7 @@
 //
 // usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
 //                         [--threads N] [--reps R]
-//   kernel in {spmv, spmm, spmm_dcsr, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm}
+//   kernel in {spmv, spmm, spmm_dcsr, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm, pack_csr, pack_dcsr, pack_csf3}
 // Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
 //
 // Input arrays (tbin.h): dims (int32), and per kernel
@@ -323,6 +323,49 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         tbin_array a; strcpy(a.name, "C_pos"); a.dtype = 0; a.count = n + 1; a.data = pos; outs.push_back(a);
         strcpy(a.name, "C_crd"); a.dtype = 0; a.count = pos[n]; a.data = crd; outs.push_back(a);
         strcpy(a.name, "C_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "pack_csr" || kernel == "pack_dcsr" || kernel == "pack_csf3") {
+      // TensorBase::insert + pack() (src/tensor.cpp:295-463): COO entries (c0, c1[, c2], vals; any order, duplicates
+      // allowed) -> level arrays of the target format.  assemble_ms = the inserts, compute_ms = pack().
+      const int order = kernel == "pack_csf3" ? 3 : 2;
+      std::vector<int> d(dims, dims + order);
+      Format fmt = kernel == "pack_csr" ? Format({Dense, Sparse}) : kernel == "pack_dcsr" ? Format({Sparse, Sparse})
+                                                                                           : Format({Sparse, Sparse, Sparse});
+      Tensor<T> A("A", d, fmt);
+      tbin_array* cv[3] = {need(in, "c0"), need(in, "c1"), order == 3 ? need(in, "c2") : nullptr};
+      tbin_array* v = need(in, "vals");
+      double t0 = now_ms();
+      std::vector<int> c(order);
+      for (uint64_t e = 0; e < v->count; e++) {
+        for (int m = 0; m < order; m++) c[m] = ((int*)cv[m]->data)[e];
+        A.insert(c, ((T*)v->data)[e]);
+      }
+      double t1 = now_ms();
+      A.pack();
+      double t2 = now_ms();
+      if (rep == 0) tm.compile = 0;
+      tm.assemble.push_back(t1 - t0); tm.compute.push_back(t2 - t1);
+      if (last) {
+        auto st = A.getStorage();
+        auto idx = st.getIndex();
+        std::vector<std::string> names;
+        names.reserve(16);
+        size_t parent = 1;
+        for (int lv = 0; lv < order; lv++) {
+          auto mi = idx.getModeIndex(lv);
+          if (mi.numIndexArrays() < 2) { parent *= d[lv]; continue; }     // dense level
+          Array pos = mi.getIndexArray(0), crd = mi.getIndexArray(1);
+          int* pp = (int*)pos.getData();
+          tbin_array a; a.dtype = 0;
+          names.push_back("A" + std::to_string(lv + 1) + "_pos"); strcpy(a.name, names.back().c_str());
+          a.count = parent + 1; a.data = pp; outs.push_back(a);
+          names.push_back("A" + std::to_string(lv + 1) + "_crd"); strcpy(a.name, names.back().c_str());
+          a.count = pp[parent]; a.data = crd.getData(); outs.push_back(a);
+          parent = pp[parent];
+        }
+        tbin_array a; strcpy(a.name, "A_vals"); a.dtype = tbin_dtype<T>(); a.count = parent; a.data = st.getValues().getData();
+        outs.push_back(a);
         tbin_write(outPath, outs.data(), outs.size());
       }
     } else if (kernel == "bspmv" || kernel == "bspmm") {

@@ -17,7 +17,7 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // out[i] = sum(in[0..i-1]) within the tile; totals[tile] = tile sum
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_tile_kernel(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ totals, long long n) {
   __shared__ int warp_sums[SCAN_THREADS / 32];
   const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
@@ -56,7 +56,7 @@ scan_tile_kernel(const int* __restrict__ in, int* __restrict__ out, int* __restr
   if (threadIdx.x == SCAN_THREADS - 1 && totals) totals[blockIdx.x] = run;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_add_kernel(int* __restrict__ out, const int* __restrict__ offsets, long long n) {
   const int off = offsets[blockIdx.x];
   const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;

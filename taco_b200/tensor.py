@@ -209,7 +209,10 @@ class Tensor:
             else:
                 pos_ptr, crd_ptr = self._level_ptrs[l][0], self._level_ptrs[l][1]
                 pos = self._adopt((l, 0), pos_ptr, size + 1, np.int32)
-                child = int(self.ct.vals_size) if nnz is None else nnz
+                if compressed not in self.format.levels[l + 1:]:          # last compressed level: one node per stored value
+                    child = int(self.ct.vals_size) if nnz is None else nnz
+                else:           # an inner compressed level (DCSR / CSF results of pack()): its node count is pos[parent size]
+                    child = int(self.to_numpy(self._as_user_array(pos))[size])
                 crd = self._adopt((l, 1), crd_ptr, child, np.int32)
                 self.arrays[(l, 0)] = self._as_user_array(pos)
                 self.arrays[(l, 1)] = self._as_user_array(crd)
@@ -265,6 +268,24 @@ def makeDCSR(name, dims, arrays):
     for l in range(2):
         t.set_level(l, arrays[f"A{l + 1}_pos"], arrays[f"A{l + 1}_crd"])
     t.set_vals(vals)
+    return t
+
+
+def pack(name, dims, fmt, coords, vals):
+    """COO -> a packed tensor on the GPU: the mirror of `Tensor::insert()` x n + `pack()` (src/tensor.cpp:295-463).
+    coords = one int32 array per mode (any order, duplicates are added), vals = the components; numpy or CUDA tensors.
+    Returns a Tensor of format `fmt` (CSR, DCSR or CSF3) whose level arrays live in the current result space."""
+    dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
+    order = len(dims)
+    n = int(vals.numel() if _is_torch(vals) else vals.size)
+    coo = Tensor(name + "_coo", dims, Format([compressed] * order), dt)
+    coo.set_level(0, np.array([0, n], np.int32), coords[0])
+    for m in range(1, order):
+        coo.set_level(m, None, coords[m])
+    coo.set_vals(vals)
+    t = Tensor(name, dims, fmt, dt)
+    check(lib.taco_b200_pack(t.ptr, coo.ptr))
+    t.adopt_results()
     return t
 
 

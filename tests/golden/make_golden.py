@@ -170,6 +170,26 @@ def main():
                 inp = dict(dims=np.array([n, m, K], np.int32), B=B, **d)
                 out = run_ref("spmm_dcsr", inp, sfx, "default")
                 cases[f"dcsr_spmm_{tag}_{sfx}_{n}x{K}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    # ---- pack(): COO (unsorted; integer-valued cases contain duplicates) -> CSR / DCSR / CSF through the reference's
+    #      insert() + pack() (src/tensor.cpp:295-463) ------------------------------------------------------------------
+    for integer in (True, False):
+        tag = "int" if integer else "frac"
+        for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
+            rng = np.random.default_rng(66001 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
+            for kind, dims, n in (("csr", (57, 43), 700), ("csr", (300, 7), 90), ("dcsr", (200, 61), 400),
+                                  ("csf3", (23, 17, 29), 1500), ("csf3", (90, 5, 40), 300)):
+                cs = [rng.integers(0, d, n).astype(np.int32) for d in dims]
+                if kind != "csf3":
+                    cs[0][cs[0] == 3] = 4                                     # an absent row
+                if not integer:                                               # distinct coordinates: order-independent sums
+                    flat = np.ravel_multi_index(cs, dims)
+                    _, first = np.unique(flat, return_index=True)
+                    first = rng.permutation(first)
+                    cs = [c[first] for c in cs]
+                v = (np.floor(rng.random(cs[0].size) * 9) + 1 if integer else rng.random(cs[0].size) + 0.25).astype(dtype)
+                inp = dict(dims=np.array(dims, np.int32), vals=v, **{f"c{m}": c for m, c in enumerate(cs)})
+                out = run_ref("pack_" + kind, inp, sfx, "default")
+                cases[f"pack_{kind}_{tag}_{sfx}_{dims[0]}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     cases = {k: v for k, v in cases.items() if k.startswith(only)}
     for name, arrs in cases.items():

@@ -186,3 +186,20 @@ def test_golden_bspmm(name):
     Mb, Nb, br, bc, K = g["dims"]
     C = oracle.bspmm(g["A_pos"], g["A_crd"], g["A_vals"].reshape(-1, br, bc), g["B"].reshape(Nb * bc, K), br, bc)
     assert np.array_equal(C.reshape(-1), g["out_C"]), "default schedule: the oracle restates the operation order"
+
+
+@pytest.mark.parametrize("name", H.golden_cases("pack"))
+def test_golden_pack(name):
+    # COO -> CSR / DCSR / CSF: the oracle's restatement of TensorBase::pack() against the reference's own insert()+pack()
+    g = H.load_golden(name)
+    kind = name.split("_")[1]
+    dims = [int(x) for x in g["dims"]]
+    coords = [g[f"c{m}"] for m in range(len(dims))]
+    got = oracle.pack(kind, dims, coords, g["vals"])
+    outs = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    assert set(got) == set(outs), (sorted(got), sorted(outs))
+    for k, want in outs.items():
+        if k.endswith("_pos") or k.endswith("_crd"):
+            assert np.array_equal(got[k], want), k
+    # integer-valued cases (with duplicates) are exact in any order; fractional cases have distinct coordinates
+    assert np.array_equal(got["A_vals"], outs["A_vals"])

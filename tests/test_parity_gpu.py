@@ -572,3 +572,103 @@ def test_bspmm_empty_and_errors():
     k = tb.compile(G.EXPR["bspmm"], Ct, A, B)
     with pytest.raises(tb.TacoError):
         k(Ct, A, B)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pack(): COO -> CSR / DCSR / CSF on the device, src/tensor.cpp:295-463
+# ---------------------------------------------------------------------------------------------------------
+_PACK_FMT = {"csr": tb.CSR, "dcsr": tb.DCSR, "csf3": tb.CSF3}
+
+
+def _pack_levels(t, kind):
+    out = {"A_vals": G.to_host(t.vals())}
+    for l, c in enumerate(t.format.levels):
+        if c == tb.compressed:
+            pos, crd = t.level(l)
+            out[f"A{l + 1}_pos"], out[f"A{l + 1}_crd"] = G.to_host(pos), G.to_host(crd)
+    return out
+
+
+def _run_pack(kind, dims, coords, vals, space):
+    tb.set_result_space(space)
+    try:
+        if space == "device":
+            import torch
+            coords = [torch.as_tensor(c).cuda() for c in coords]
+            vals = torch.as_tensor(vals).cuda()
+        t = tb.pack("A", dims, _PACK_FMT[kind], coords, vals)
+        if space == "device":
+            tb.synchronize()
+        return {k: np.array(v) for k, v in _pack_levels(t, kind).items()}
+    finally:
+        tb.set_result_space("host")
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("pack"))
+def test_golden_pack(name, space):
+    g = H.load_golden(name)
+    kind = name.split("_")[1]
+    dims = [int(x) for x in g["dims"]]
+    got = _run_pack(kind, dims, [g[f"c{m}"] for m in range(len(dims))], g["vals"], space)
+    outs = {k[4:]: v for k, v in g.items() if k.startswith("out_")}
+    assert set(got) == set(outs)
+    for k, want in outs.items():
+        assert np.array_equal(got[k], want), k
+
+
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("kind,dims,n", [("csr", (100_000, 70_000), 1_500_000), ("dcsr", (1 << 20, 1 << 18), 300_000),
+                                         ("csf3", (3_000, 500, 2_000), 2_000_000), ("csr", (50, 40), 100_000),
+                                         ("csf3", (7, 5, 3), 4_000)])
+def test_oracle_pack(space, kind, dims, n):
+    # unsorted coordinates with duplicates (heavily duplicated in the small-dimension cases); integer values keep the
+    # duplicate sums exact in any order
+    rng = np.random.default_rng(n + len(dims))
+    coords = [rng.integers(0, d, n).astype(np.int32) for d in dims]
+    vals = np.floor(rng.random(n) * 5 + 1)
+    got = _run_pack(kind, list(dims), coords, vals, space)
+    want = oracle.pack(kind, list(dims), coords, vals) if n <= 100_000 else None
+    if want is None:       # large cases: numpy reference without the python loop over runs
+        flat = np.ravel_multi_index(coords, dims)
+        uq, inv = np.unique(flat, return_inverse=True)
+        sums = np.bincount(inv, weights=vals)
+        uc = np.unravel_index(uq, dims)
+        assert np.array_equal(got["A_vals"], sums)
+        last = f"A{len(dims)}_crd"
+        assert np.array_equal(got[last], uc[-1].astype(np.int32))
+        if kind == "csr":
+            pos = np.zeros(dims[0] + 1, np.int64)
+            np.add.at(pos, uc[0] + 1, 1)
+            assert np.array_equal(got["A2_pos"], np.cumsum(pos))
+        else:
+            assert np.array_equal(got["A1_crd"], np.unique(uc[0]))
+            assert got["A1_pos"].tolist() == [0, np.unique(uc[0]).size]
+            assert got[f"A{len(dims)}_pos"][-1] == uq.size
+    else:
+        assert set(got) == set(want)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+
+
+def test_pack_then_compute_and_edge_cases():
+    # a packed CSR tensor feeds SpMV directly; empty input; unsupported target
+    rng = np.random.default_rng(3)
+    n, m, e = 5_000, 4_000, 60_000
+    r, c = rng.integers(0, n, e).astype(np.int32), rng.integers(0, m, e).astype(np.int32)
+    v = np.floor(rng.random(e) * 7 + 1)
+    A = tb.pack("A", [n, m], tb.CSR, [r, c], v)
+    x = np.floor(rng.random(m) * 5)
+    xt = tb.makeDense("x", [m], x)
+    y = tb.Tensor("y", [n], tb.Format([tb.dense]), np.float64)
+    tb.compile(G.EXPR["spmv"], y, A, xt)(y, A, xt)
+    D = np.zeros((n, m))
+    np.add.at(D, (r, c), v)
+    assert np.array_equal(G.to_host(y.vals()), D @ x)
+    z = np.zeros(0, np.int32)
+    E = tb.pack("E", [6, 5], tb.CSR, [z, z], np.zeros(0))
+    assert np.array_equal(G.to_host(E.level(1)[0]), np.zeros(7, np.int32))
+    E = tb.pack("E", [6, 5, 4], tb.CSF3, [z, z, z], np.zeros(0))
+    assert G.to_host(E.level(0)[0]).tolist() == [0, 0]
+    with pytest.raises(tb.TacoError):
+        tb.pack("B", [6, 5], tb.Format([tb.dense, tb.dense]), [z, z], np.zeros(0))
