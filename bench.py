@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the taco GPU hot path on B200, next to the reference's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm|ttv|ttm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm|ttv|ttm|pack]
     python bench.py --impl reference ...          # the reference's own C/OpenMP codegen on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU; rank 0 prints the JSON line)
 
@@ -39,9 +39,14 @@ FLOPS = {   # per step, as the reference counts them
     "bspmm": lambda s: 2.0 * s["nnzb"] * s["br"] * s["bc"] * s["K"],
     "ttv": lambda s: 2.0 * s["nnz"],
     "ttm": lambda s: 2.0 * s["nnz"] * s["R"],
+    "pack": lambda s: 1.0 * s["n"],            # not flops: coordinates packed (metric pack_gcoords, unit Gcoord/s)
 }
+
+
+def metric_of(wl):
+    return (f"{wl}_gcoords", "Gcoord/s") if wl == "pack" else (f"{wl}_gflops", "GFLOP/s")
 DOMINANT = {"spmv": "spmv_csr", "spmm": "spmm_csr", "sddmm": "sddmm_csr", "mttkrp": "mttkrp_csf",
-            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr", "ttv": "ttv_csf", "ttm": "ttm_csf"}
+            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr", "ttv": "ttv_csf", "ttm": "ttm_csf", "pack": "pack_coo"}
 
 
 def algorithmic_bytes(wl, s):
@@ -59,6 +64,8 @@ def algorithmic_bytes(wl, s):
         return (s["nnzA"] + s["nnzB"]) * (4 + e) + s["nnzC"] * (4 + e) + 12 * (s["rows"] + 1)
     if wl == "spgemm":     # fill pass (sort + compress): A, the gathered B rows (crd + vals), the result, all pos arrays
         return (4 + e) * (s["nnzA"] + s["products"] + s["nnzC"]) + 12 * (s["rows"] + 1)
+    if wl == "pack":       # coordinates and values read once, CSR arrays written once
+        return s["n"] * (8 + e) + s["nnzC"] * (4 + e) + 4 * (s["rows"] + 1)
     if wl == "ttv":        # leaves + fiber / slice level arrays + c + the dense (I x K) result written once
         return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * (s["Ld"] + s["I"] * s["Kd"])
     if wl == "ttm":        # + every row of C and of the (I*K x R) result touched once
@@ -70,7 +77,7 @@ def algorithmic_bytes(wl, s):
 
 def sizes_of(wl, w, extra=None):
     d = [int(x) for x in w["dims"]]
-    vals = w.get("A_vals", w.get("B_vals"))
+    vals = w.get("A_vals", w.get("B_vals", w.get("vals")))
     e = 4 if "float32" in str(vals.dtype) else 8
     s = dict(esize=e)
     if wl in ("spmv", "spmm"):
@@ -80,6 +87,8 @@ def sizes_of(wl, w, extra=None):
     elif wl == "mttkrp":
         s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3], nnz=int(w["B3_crd"].shape[0]), nfib=int(w["B2_crd"].shape[0]),
                  nslices=int(w["B1_crd"].shape[0]))
+    elif wl == "pack":
+        s.update(rows=d[0], cols=d[1], n=int(w["vals"].shape[0]), nnzC=int(w["vals"].shape[0]))
     elif wl in ("ttv", "ttm"):
         s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3] if wl == "ttm" else 1, nnz=int(w["B3_crd"].shape[0]),
                  nfib=int(w["B2_crd"].shape[0]), nslices=int(w["B1_crd"].shape[0]))
@@ -154,7 +163,7 @@ def make_workload(wl, device, rank, scale_down):
         over = {"spmm": dict(scale=16), "spmv": dict(n=100_000), "sddmm": dict(n=100_000),
                 "mttkrp": dict(I=100_000, K=20_000, L=20_000, nnz=2_000_000), "spadd": dict(n=100_000),
                 "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048), "ttv": dict(I=512, K=512, L=50_000, nnz=2_000_000),
-                "ttm": dict(I=128, K=128, L=50_000, nnz=1_000_000)}[wl]
+                "ttm": dict(I=128, K=128, L=50_000, nnz=1_000_000), "pack": dict(n=50_000, nnz=400_000)}[wl]
     if wl == "bspmm" and os.environ.get("TACO_B200_BENCH_BLOCK"):      # block-shape sweep (experiments only): 16 -> 16x16 blocks,
         b = int(os.environ["TACO_B200_BENCH_BLOCK"])                  # same matrix dimension and number of stored values
         over.update(br=b, bc=b, Mb=over.get("Mb", 32768) * 32 // b, deg=16 * 32 // b)
@@ -197,6 +206,11 @@ def reference_sample(wl, w, budget_rows):
             h.update(B_pos=bpos, B_crd=G.to_host(w["B_crd"][:bz]), B_vals=G.to_host(w["B_vals"][:bz]))
         else:
             h.update(B_pos=G.to_host(w["B_pos"]), B_crd=G.to_host(w["B_crd"]), B_vals=G.to_host(w["B_vals"]))
+    elif wl == "pack":       # the first budget_rows coordinates (same dimensions)
+        n = min(budget_rows, int(w["vals"].shape[0]))
+        h.update(c0=G.to_host(w["c0"][:n]), c1=G.to_host(w["c1"][:n]), vals=G.to_host(w["vals"][:n]))
+        dims = [int(x) for x in w["dims"]]
+        frac = n / max(int(w["vals"].shape[0]), 1)
     elif wl == "bspmm":
         rows = min(budget_rows, int(w["dims"][0]))
         pos = G.to_host(w["A_pos"][: rows + 1])
@@ -247,7 +261,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
             tbin.write(fin, h)
             best = None
             for sched in (("cpu", "default") if wl != "sddmm" else ("default",)):
-                r = subprocess.run([harness, wl, fin, fout, "--dtype", sfx, "--schedule", sched, "--threads", str(threads),
+                r = subprocess.run([harness, "pack_csr" if wl == "pack" else wl, fin, fout, "--dtype", sfx, "--schedule", sched, "--threads", str(threads),
                                     "--reps", str(reps)], capture_output=True, text=True,
                                    env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
                 if r.returncode != 0:
@@ -269,6 +283,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
         "mttkrp": lambda: oracle.mttkrp(h, h["C"].reshape(d[1], -1), h["D"].reshape(d[2], -1), d[0]),
         "spadd": lambda: oracle.spadd(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"]),
         "spgemm": lambda: oracle.spgemm(h["A_pos"], h["A_crd"], h["A_vals"], h["B_pos"], h["B_crd"], h["B_vals"], d[-1]),
+        "pack": lambda: oracle.pack("csr", d, [h["c0"], h["c1"]], h["vals"]),
         "ttv": lambda: oracle.ttv(h, h["c"], d[0], d[1]),
         "ttm": lambda: oracle.ttm(h, h["C"].reshape(d[2], -1), d[0], d[1]),
         "bspmm": lambda: oracle.bspmm(h["A_pos"], h["A_crd"], h["A_vals"].reshape(-1, d[2], d[3]),
@@ -284,7 +299,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
 
 
 SAMPLE_ROWS = {"spmm": 1 << 19, "spmv": 1_000_000, "sddmm": 250_000, "mttkrp": 500_000, "spadd": 1_000_000,
-               "spgemm": 200_000, "bspmm": 2048, "ttv": 1024, "ttm": 64}
+               "spgemm": 200_000, "bspmm": 2048, "ttv": 1024, "ttm": 64, "pack": 2_000_000}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -331,15 +346,15 @@ def main():
             extra["products"] = stats["nnzA"] * (stats["nnzB"] / max(stats["rows"], 1))
         stats.update(extra)
         gflops = FLOPS[wl](stats) * frac / sec / 1e9
-        line = {"impl": "reference", "metric": f"{wl}_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": metric_of(wl)[0], "value": gflops, "unit": metric_of(wl)[1], "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 / max(frac, 1e-12),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if stats["esize"] == 4 else "f64", "data": "synthetic",
                 "config": {"workload": workload_name(wl, stats), "sample": f"first {int(h['dims'][0])} rows"},
-                "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": threads, "kind": kind,
+                "cpu_baseline": {"value": gflops, "unit": metric_of(wl)[1], "cores": threads, "kind": kind,
                                  "sample": f"first {int(h['dims'][0])} rows ({frac * 100:.1f}% of the nonzeros), "
                                            "time scaled to the full step"},
-                "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": gflops, "unit": metric_of(wl)[1], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
@@ -359,7 +374,7 @@ def main():
     k, ts = G.build(wl, w)
     res = ts[0]
     stats = sizes_of(wl, w)
-    sparse_out = wl in ("spadd", "spgemm", "sddmm")
+    sparse_out = wl in ("spadd", "spgemm", "sddmm", "pack")
     if not sparse_out:
         out = torch.empty(int(np.prod(res.dims)), dtype=torch.float32 if stats["esize"] == 4 else torch.float64, device="cuda")
         res.set_vals(out)
@@ -373,7 +388,7 @@ def main():
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    if wl == "spadd":
+    if wl in ("spadd", "pack"):
         stats["nnzC"] = int(res.ct.vals_size)
     if wl == "spgemm":
         stats["nnzC"] = int(res.ct.vals_size)
@@ -462,7 +477,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": flops_rank * world / float(t.item()) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": flops_rank * world / float(t.item()) / 1e9, "unit": metric_of(wl)[1], "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": float(t.item()) * 1e3, "steps": e2e_steps,
                "path": "taco_b200_<family>_compute(taco_tensor_t*) with pinned host arrays"}
         tb.set_result_space("device")
@@ -471,11 +486,11 @@ def main():
     if rank == 0 and not args.no_cpu:
         h, frac = reference_sample(wl, w, SAMPLE_ROWS[wl] if not args.small else 1 << 30)
         sec, kind = run_reference_cpu(wl, h, stats["esize"], 3, threads)
-        cpu = {"value": flops_rank * frac / sec / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": kind,
+        cpu = {"value": flops_rank * frac / sec / 1e9, "unit": metric_of(wl)[1], "cores": threads, "kind": kind,
                "sample": f"first {int(h['dims'][0])} rows ({frac * 100:.1f}% of the nonzeros), best of 3"}
 
     if rank == 0:
-        line = {"metric": f"{wl}_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_of(wl)[0], "value": value, "unit": metric_of(wl)[1], "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if stats["esize"] == 4 else "f64", "data": "synthetic",
                 "config": {"workload": workload_name(wl, stats), "per_gpu": True,
@@ -504,6 +519,8 @@ def workload_name(wl, s):
     if wl == "bspmm":
         return (f"BCSR SpMM fp32 {s['Mb'] * s['br']}x{s['Nb'] * s['bc']} in {s['br']}x{s['bc']} blocks, "
                 f"{s['nnzb']} stored blocks, K={s['K']}")
+    if wl == "pack":
+        return f"pack() COO -> CSR fp64 {s['rows']}x{s['cols']}, {s['n']} unsorted coordinates"
     if wl == "ttv":
         return f"CSF TTV fp64 {s['I']}x{s['Kd']}x{s['Ld']} nnz={s['nnz']} (dense {s['I']}x{s['Kd']} result)"
     if wl == "ttm":

@@ -314,6 +314,8 @@ FULL = {
     # TTV / TTM: dense results, so the (i,j) plane is kept small enough to hold A in HBM
     "ttv": dict(I=8192, K=8192, L=1_000_000, nnz=100_000_000, dtype="float64"),
     "ttm": dict(I=1024, K=1024, L=1_000_000, nnz=50_000_000, R=32, dtype="float64"),
+    # pack(): C1's shape as unsorted coordinates, uniform (a few duplicates), -> CSR
+    "pack": dict(n=1_000_000, nnz=10_000_000, dtype="float64"),
     # blocked SpMM: 1Mi x 1Mi in 32 x 32 blocks, 16 stored blocks per block row, K = 128
     "bspmm": dict(Mb=32768, deg=16, br=32, bc=32, K=128, dtype="float32"),
 }
@@ -349,6 +351,10 @@ def make(workload, device=None, **over):
         t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 30, dt)
         t.update(dims=(p["I"], p["K"], p["L"], p["R"]), C=dense(xp, p["L"], p["R"], SEED0 + 34, dt))
         return t
+    if workload == "pack":
+        e = xp.arange(p["nnz"])
+        return dict(dims=(p["n"], p["n"]), c0=xp.i32(uniform_int(xp, e, SEED0 + 40, p["n"])),
+                    c1=xp.i32(uniform_int(xp, e, SEED0 + 41, p["n"])), vals=values(xp, e, SEED0 + 42, dt))
     if workload in ("spadd", "spgemm"):
         ap, ac, av = csr_fixed_degree(xp, p["n"], p["n"], p["deg"], SEED0 + 16, dt)
         bp, bc, bv = csr_fixed_degree(xp, p["n"], p["n"], p["deg"], SEED0 + 18, dt)

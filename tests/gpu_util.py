@@ -51,6 +51,25 @@ def empty_like_space(w_array, count, dtype):
     return np.empty(count, dtype=dtype)
 
 
+class _PackHolder:
+    """stands where a result Tensor stands in the (kernel, tensors) pair: holds the tensor the last pack() produced"""
+
+    def __init__(self, dims):
+        self.dims, self.t = list(dims), None
+
+    @property
+    def ct(self):
+        return self.t.ct
+
+
+class _PackKernel:
+    """pack(): unsorted COO (w["c0"], w["c1"], w["vals"]) -> a CSR tensor (taco_b200_pack through the C ABI)"""
+
+    def __call__(self, holder, w):
+        holder.t = tb.pack("A", holder.dims, tb.CSR, [w["c0"], w["c1"]], w["vals"])
+        return True
+
+
 def build(family, w, colmajor_c=False):
     """returns (kernel, [result, operands...]) for a workload dict with the taco_b200.synth / tbin key names"""
     d = [int(x) for x in w["dims"]]
@@ -113,6 +132,8 @@ def build(family, w, colmajor_c=False):
             B = tb.makeDense("B", [d[1], d[3], d[4]], w["B"])
             C = tb.Tensor("C", [d[0], d[2], d[4]], tb.Format([tb.dense] * 3), dt)
             ts = [C, A, B]
+    elif family == "pack":
+        return _PackKernel(), [_PackHolder(d[:2]), w]
     else:
         raise KeyError(family)
     return tb.compile(EXPR[family], *ts), ts
