@@ -82,6 +82,8 @@ int device_result_alloc(void** p, size_t bytes);
 void device_result_free(void* p);
 // copy a small device array to host synchronously (e.g. pos[n] after the scan)
 int read_back(void* host, const void* dev, size_t bytes);
+// device array -> freshly malloc'ed host array through pinned chunks + parallel host copies (synchronous)
+int d2h_fresh(void* dst, const void* src, size_t bytes);
 // read one int32 that may live on host or device
 int read_i32(const int32_t* p, int32_t* out);
 

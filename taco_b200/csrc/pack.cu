@@ -152,7 +152,7 @@ static int publish_array(void** slot, void* dptr, size_t bytes) {
   if (result_space() == TACO_B200_SPACE_DEVICE) { *slot = dptr; return TACO_B200_OK; }
   void* h = malloc(bytes ? bytes : 16);
   if (!h) return fail(TACO_B200_ERR_ALLOC, "pack: cannot allocate host result array");
-  if (bytes) TB_CUDA(cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, stream()));
+  if (bytes) TB_TRY(d2h_fresh(h, dptr, bytes));
   *slot = h;
   return TACO_B200_OK;
 }

@@ -926,9 +926,9 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
     int32_t* hcrd = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnzC > 0 ? nnzC : 1));
     void* vals = malloc(esize * (size_t)(nnzC > 0 ? nnzC : 1));
     if (!hpos || !hcrd || !vals) return fail(TACO_B200_ERR_ALLOC, "cannot allocate host result arrays");
-    TB_CUDA(cudaMemcpyAsync(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, stream()));
-    if (nnzC) TB_CUDA(cudaMemcpyAsync(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC, cudaMemcpyDeviceToHost, stream()));
-    if (nnzC && dvals) TB_CUDA(cudaMemcpyAsync(vals, dvals, esize * (size_t)nnzC, cudaMemcpyDeviceToHost, stream()));
+    TB_TRY(d2h_fresh(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1)));
+    if (nnzC) TB_TRY(d2h_fresh(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC));
+    if (nnzC && dvals) TB_TRY(d2h_fresh(vals, dvals, esize * (size_t)nnzC));
     TB_CUDA(cudaStreamSynchronize(stream()));
     device_result_free(dpos);
     device_result_free(dcrd);

@@ -15,6 +15,8 @@ def t(fn, n=5):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e3
 
+if os.environ.get("PROBE_TORCH_STREAM"):
+    tb.use_torch_stream()
 w = synth.make("pack", "cuda")
 hw = {}
 for k, v in w.items():
@@ -37,3 +39,10 @@ print(f"D2H 124 MB pageable : {t(lambda: hq.copy_(d)):8.2f} ms")
 def fresh():
     x = np.empty(124_000_000, np.uint8); torch.from_numpy(x).copy_(d)
 print(f"D2H 124 MB into a fresh malloc : {t(fresh):8.2f} ms")
+
+import cProfile, pstats
+tb.set_result_space("host")
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3): tb.pack('A', dims, tb.CSR, [hw['c0'], hw['c1']], hw['vals'])
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
