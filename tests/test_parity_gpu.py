@@ -475,6 +475,45 @@ def test_dropin_demo_through_unmodified_reference():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("expr,fmts,files", [
+    ("y(i) = A(i,j) * x(j)", dict(y="d", A="ds", x="d"), dict(A=(300, 200), x=(200,))),
+    ("C(i,k) = A(i,j) * B(j,k)", dict(C="dd", A="ds", B="dd"), dict(A=(120, 90), B=(90, 16))),
+    ("C(i,j) = A(i,j) + B(i,j)", dict(C="ds", A="ds", B="ds"), dict(A=(150, 130), B=(150, 130))),
+    ("C(i,k) = A(i,j) * B(j,k)", dict(C="ds", A="ds", B="ds"), dict(A=(80, 70), B=(70, 60))),
+])
+def test_cli_dropin_read_source(tmp_path, expr, fmts, files):
+    """The reference's own `taco` command-line tool (tools/taco.cpp, compiled unmodified into oracle/_ref) evaluates the
+    statement twice -- with its C codegen and with `-read-source=<stub>` -- and `-verify` compares the two results
+    (tools/taco.cpp:1212-1259).  The stub forwards assemble / compute to libtaco_b200, so the CLI is a drop-in."""
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe = os.path.join(root, "oracle", "_ref", "taco")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/taco (the compiled reference CLI) was not shipped with this snapshot")
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import emit_stub
+    rng = np.random.default_rng(len(expr))
+    args = [exe, expr]
+    for name, f in fmts.items():
+        args.append(f"-f={name}:{f}")
+    for name, shape in files.items():
+        path = tmp_path / f"{name}.tns"                       # FROSTT coordinates, 1-based
+        dense_operand = "s" not in fmts[name]
+        with open(path, "w") as fh:
+            for idx in np.ndindex(*shape):
+                last = all(i == n - 1 for i, n in zip(idx, shape))      # pins the dimensions the CLI infers from the file
+                if dense_operand or last or rng.random() < 0.15:
+                    fh.write(" ".join(str(i + 1) for i in idx) + f" {int(rng.integers(1, 9))}\n")
+        args.append(f"-i={name}:{path}")
+    stub = tmp_path / "stub.c"
+    stub.write_text(emit_stub.stub_source(expr, ",".join(f"{n}:{f}" for n, f in fmts.items()), "f64"))
+    args += [f"-read-source={stub}", "-verify"]
+    before = tb.launch_count()
+    env = dict(os.environ, TACO_B200_LIB=tb.LIB_PATH, TACO_CFLAGS="-O3 -std=gnu99", TMPDIR=str(tmp_path))
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Verifying... done" in r.stdout and "differ" not in r.stderr, r.stdout + r.stderr
+
+
 # ---------------------------------------------------------------------------------------------------------
 # blocked SpMV / SpMM (BCSR = {Dense,Compressed,Dense,Dense}), SURVEY.md 8(f) item 1
 # ---------------------------------------------------------------------------------------------------------
