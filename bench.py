@@ -482,6 +482,28 @@ def main():
                "path": "taco_b200_<family>_compute(taco_tensor_t*) with pinned host arrays"}
         tb.set_result_space("device")
 
+    # ---- the only collective of the path: all-gather of the dense result rows between iterations ----
+    exchange = None
+    if world > 1 and not sparse_out:
+        gathered = torch.empty(world * out.numel(), dtype=out.dtype, device="cuda")
+        for _ in range(2):
+            dist.all_gather_into_tensor(gathered, out)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(gathered, out)
+        eb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ea.elapsed_time(eb) / 5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = out.numel() * out.element_size()
+        exchange = {"collective": "all_gather_into_tensor (NCCL) of every rank's dense result rows, not part of the timed step",
+                    "bytes_per_rank": nbytes, "ms": float(t.item()),
+                    "recv_GBps_per_rank": nbytes * (world - 1) / (float(t.item()) * 1e-3) / 1e9}
+        del gathered
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         h, frac = reference_sample(wl, w, SAMPLE_ROWS[wl] if not args.small else 1 << 30)
@@ -503,6 +525,8 @@ def main():
                              "peak_source": peak_src,
                              "kernel_ms": kern_ms, "algorithmic_bytes": algorithmic_bytes(wl, stats)},
                 "cpu_baseline": cpu}
+        if exchange:
+            line["exchange"] = exchange
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
