@@ -509,7 +509,8 @@ def main():
         h, frac = reference_sample(wl, w, SAMPLE_ROWS[wl] if not args.small else 1 << 30)
         sec, kind = run_reference_cpu(wl, h, stats["esize"], 3, threads)
         cpu = {"value": flops_rank * frac / sec / 1e9, "unit": metric_of(wl)[1], "cores": threads, "kind": kind,
-               "sample": f"first {int(h['dims'][0])} rows ({frac * 100:.1f}% of the nonzeros), best of 3"}
+               "sample": (f"first {int(h['vals'].shape[0])} coordinates" if wl == "pack" else f"first {int(h['dims'][0])} rows") +
+                         f" ({frac * 100:.1f}% of the nonzeros), best of 3"}
 
     if rank == 0:
         line = {"metric": metric_of(wl)[0], "value": value, "unit": metric_of(wl)[1], "n_gpus": world, "steps": args.steps,

@@ -176,8 +176,8 @@ int taco_b200_spgemm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t*
  * (src/tensor.cpp:295-463; helper signature `int pack(taco_tensor_t* A, taco_tensor_t* B)`, src/tensor.cpp:932-1000).
  * `coo` is the reference's coordinate-buffer tensor: every level "sparse", indices[0][0] = int32{0, n}, indices[l][1] =
  * the n coordinates of level l, vals = the n components (host or device arrays; ANY order -- the sort happens here).
- * `A` gives the target format -- {Dense,Compressed}, {Compressed,Compressed} or {Compressed,Compressed,Compressed},
- * identity mode ordering -- and receives freshly allocated pos / crd / vals in the configured result space, exactly as
+ * `A` gives the target format -- {Dense,Compressed}, {Compressed,Compressed} or {Compressed,Compressed,Compressed}, any
+ * mode ordering (levels in storage order on both sides, e.g. {1,0} = CSC) -- and receives freshly allocated pos / crd / vals in the configured result space, exactly as
  * an assemble call does; A->vals_size = number of stored components.  Equal coordinates are added (insertion order). */
 int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo);
 int _shim_taco_b200_pack(void** p);

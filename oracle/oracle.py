@@ -212,6 +212,8 @@ def pack(kind, dims, coords, vals):
     added in insertion order (the reference's qsort leaves that order unspecified).  Returns a dict of level arrays named
     like oracle/ref_harness.cpp's pack output: A<level>_pos / A<level>_crd (compressed levels only) and A_vals."""
     coords = [np.asarray(c, dtype=np.int64) for c in coords]
+    if kind == "csc":          # {Dense,Compressed} with mode ordering {1,0}: CSR of the transposed coordinates
+        kind, dims, coords = "csr", [dims[1], dims[0]], [coords[1], coords[0]]
     vals = np.ascontiguousarray(vals)
     n = vals.size
     order = len(coords)

@@ -325,12 +325,13 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         strcpy(a.name, "C_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
         tbin_write(outPath, outs.data(), outs.size());
       }
-    } else if (kernel == "pack_csr" || kernel == "pack_dcsr" || kernel == "pack_csf3") {
+    } else if (kernel == "pack_csr" || kernel == "pack_dcsr" || kernel == "pack_csf3" || kernel == "pack_csc") {
       // TensorBase::insert + pack() (src/tensor.cpp:295-463): COO entries (c0, c1[, c2], vals; any order, duplicates
       // allowed) -> level arrays of the target format.  assemble_ms = the inserts, compute_ms = pack().
       const int order = kernel == "pack_csf3" ? 3 : 2;
       std::vector<int> d(dims, dims + order);
-      Format fmt = kernel == "pack_csr" ? Format({Dense, Sparse}) : kernel == "pack_dcsr" ? Format({Sparse, Sparse})
+      Format fmt = kernel == "pack_csr" ? Format({Dense, Sparse}) : kernel == "pack_csc" ? Format({Dense, Sparse}, {1, 0})
+                   : kernel == "pack_dcsr" ? Format({Sparse, Sparse})
                                                                                            : Format({Sparse, Sparse, Sparse});
       Tensor<T> A("A", d, fmt);
       tbin_array* cv[3] = {need(in, "c0"), need(in, "c1"), order == 3 ? need(in, "c2") : nullptr};
@@ -354,7 +355,7 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         size_t parent = 1;
         for (int lv = 0; lv < order; lv++) {
           auto mi = idx.getModeIndex(lv);
-          if (mi.numIndexArrays() < 2) { parent *= d[lv]; continue; }     // dense level
+          if (mi.numIndexArrays() < 2) { parent *= d[fmt.getModeOrdering()[lv]]; continue; }     // dense level
           Array pos = mi.getIndexArray(0), crd = mi.getIndexArray(1);
           int* pp = (int*)pos.getData();
           tbin_array a; a.dtype = 0;

@@ -14,7 +14,8 @@
 //      small read-back, as the reference reads pos[parent] after assemble, src/tensor.cpp:263-292).
 //   3. fill: crd of a level at the head entries, pos of a level at the heads of its parent level, values = the sum of a
 //      run of equal coordinates in sorted (= insertion, the sort is stable) order.
-// Targets: {Dense,Compressed} (CSR), {Compressed,Compressed} (DCSR), {Compressed x3} (CSF), identity mode ordering.
+// Targets: {Dense,Compressed} (CSR; CSC with mode ordering {1,0}), {Compressed,Compressed} (DCSR / DCSC), {Compressed x3}
+// (CSF, any mode ordering): levels are taken in storage order, as the reference's helper receives them.
 // Structure is bit-exact with the reference.  Values are bit-exact when coordinates are distinct; for duplicates the
 // reference's summation order is that of an unstable qsort (unspecified), here it is insertion order.
 #include <cub/device/device_radix_sort.cuh>
@@ -168,9 +169,17 @@ int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo) {
   if (!A || !coo) return fail(TACO_B200_ERR_ARG, "pack: NULL tensor");
   const int order = A->order;
   if (order != coo->order || (order != 2 && order != 3)) return fail(TACO_B200_ERR_UNSUPPORTED, "pack: order 2 or 3 tensors only");
+  // levels are in STORAGE order on both sides (TensorBase::pack permutes the coordinates by the format's mode ordering
+  // before it calls the helper, src/tensor.cpp:393-414): level l holds mode mode_ordering[l], e.g. {1,0} for CSC
+  int ldim[3] = {0, 0, 0};
+  bool seen[3] = {false, false, false};
   for (int l = 0; l < order; l++) {
-    if (A->mode_ordering[l] != l) return fail(TACO_B200_ERR_UNSUPPORTED, "pack: identity mode ordering only");
-    if (A->dimensions[l] != coo->dimensions[l] || A->dimensions[l] <= 0) return fail(TACO_B200_ERR_ARG, "pack: bad dimension of mode %d", l);
+    const int m = A->mode_ordering[l];
+    if (m < 0 || m >= order || seen[m]) return fail(TACO_B200_ERR_ARG, "pack: bad mode ordering");
+    seen[m] = true;
+    if (coo->mode_ordering[l] != m) return fail(TACO_B200_ERR_ARG, "pack: coordinate buffer and result disagree on the mode ordering");
+    if (A->dimensions[m] != coo->dimensions[m] || A->dimensions[m] <= 0) return fail(TACO_B200_ERR_ARG, "pack: bad dimension of mode %d", m);
+    ldim[l] = A->dimensions[m];
   }
   enum { CSR, DCSR, CSF } kind;
   if (order == 2 && A->mode_types[0] == taco_mode_dense && A->mode_types[1] == taco_mode_sparse) kind = CSR;
@@ -188,8 +197,8 @@ int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo) {
   const long long n = (long long)n32 - first;
   if (first != 0 || n < 0 || n > INT32_MAX - 65536) return fail(TACO_B200_ERR_ARG, "pack: bad coordinate count");
   const size_t es = dsize(dt);
-  const int rows = A->dimensions[0];
-  const int b1 = bits_for(A->dimensions[1]), b0 = bits_for(A->dimensions[0]);
+  const int rows = ldim[0];
+  const int b1 = bits_for(ldim[1]), b0 = bits_for(ldim[0]);
 
   int *d_pos_top = nullptr, *d_crd_top = nullptr, *d_pos_mid = nullptr, *d_crd_mid = nullptr, *d_pos_leaf = nullptr, *d_crd_leaf = nullptr;
   void* d_vals = nullptr;
@@ -227,7 +236,7 @@ int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo) {
     if (order == 3) {                          // least significant mode first (stable)
       pack_key32_kernel<<<grid, 256, 0, stream()>>>(c2.as<int>(), n, (unsigned*)key_a, (unsigned*)idx_a);
       TB_TRY(radix_sort_pairs<unsigned>((const unsigned*)key_a, (unsigned*)key_b, (const unsigned*)idx_a, (unsigned*)idx_b, n,
-                                        bits_for(A->dimensions[2])));
+                                        bits_for(ldim[2])));
       perm_in = (const unsigned*)idx_b;
     }
     pack_keys_kernel<<<grid, 256, 0, stream()>>>(c0.as<int>(), c1.as<int>(), perm_in, b1, n, (unsigned long long*)key_a, (unsigned*)idx_a);

@@ -278,10 +278,11 @@ def pack(name, dims, fmt, coords, vals):
     dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
     order = len(dims)
     n = int(vals.numel() if _is_torch(vals) else vals.size)
-    coo = Tensor(name + "_coo", dims, Format([compressed] * order), dt)
-    coo.set_level(0, np.array([0, n], np.int32), coords[0])
-    for m in range(1, order):
-        coo.set_level(m, None, coords[m])
+    fmt = fmt if isinstance(fmt, Format) else Format(fmt)
+    coo = Tensor(name + "_coo", dims, Format([compressed] * order, fmt.ordering), dt)
+    coo.set_level(0, np.array([0, n], np.int32), coords[fmt.ordering[0]])       # level l holds mode ordering[l]
+    for l in range(1, order):
+        coo.set_level(l, None, coords[fmt.ordering[l]])
     coo.set_vals(vals)
     t = Tensor(name, dims, fmt, dt)
     check(lib.taco_b200_pack(t.ptr, coo.ptr))

@@ -176,7 +176,7 @@ def main():
         tag = "int" if integer else "frac"
         for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
             rng = np.random.default_rng(66001 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
-            for kind, dims, n in (("csr", (57, 43), 700), ("csr", (300, 7), 90), ("dcsr", (200, 61), 400),
+            for kind, dims, n in (("csr", (57, 43), 700), ("csr", (300, 7), 90), ("dcsr", (200, 61), 400), ("csc", (45, 71), 600),
                                   ("csf3", (23, 17, 29), 1500), ("csf3", (90, 5, 40), 300)):
                 cs = [rng.integers(0, d, n).astype(np.int32) for d in dims]
                 if kind != "csf3":

@@ -616,7 +616,7 @@ def test_bspmm_empty_and_errors():
 # ---------------------------------------------------------------------------------------------------------
 # pack(): COO -> CSR / DCSR / CSF on the device, src/tensor.cpp:295-463
 # ---------------------------------------------------------------------------------------------------------
-_PACK_FMT = {"csr": tb.CSR, "dcsr": tb.DCSR, "csf3": tb.CSF3}
+_PACK_FMT = {"csr": tb.CSR, "dcsr": tb.DCSR, "csf3": tb.CSF3, "csc": tb.Format([tb.dense, tb.compressed], [1, 0])}
 
 
 def _pack_levels(t, kind):
@@ -658,7 +658,7 @@ def test_golden_pack(name, space):
 
 @pytest.mark.parametrize("space", SPACES)
 @pytest.mark.parametrize("kind,dims,n", [("csr", (100_000, 70_000), 1_500_000), ("dcsr", (1 << 20, 1 << 18), 300_000),
-                                         ("csf3", (3_000, 500, 2_000), 2_000_000), ("csr", (50, 40), 100_000),
+                                         ("csf3", (3_000, 500, 2_000), 2_000_000), ("csr", (50, 40), 100_000), ("csc", (300, 500), 90_000),
                                          ("csf3", (7, 5, 3), 4_000)])
 def test_oracle_pack(space, kind, dims, n):
     # unsorted coordinates with duplicates (heavily duplicated in the small-dimension cases); integer values keep the

@@ -33,7 +33,11 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
 def raw_page(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    csv_path = path[: -len(".ncu-rep")] + ".raw.csv"
+    if os.path.exists(csv_path) and (not os.path.exists(path) or os.path.getmtime(csv_path) >= os.path.getmtime(path)):
+        out = open(csv_path).read()            # exported on the GPU box by tools/gpu_prof.sh (the .ncu-rep stays there)
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return [(dict(zip(hdr, r)), dict(zip(hdr, units))) for r in rows[2:]]
@@ -56,7 +60,7 @@ def main():
         rep = os.path.join(ROOT, "gpurun_out", f"ncu_{wl}.ncu-rep")
         lst = os.path.join(ROOT, "gpurun_out", f"launches_{wl}.csv")
         lines = [f"# {tag} — {wl}: ncu summary (B200, `--set full --clock-control none`, one launch of the dominant kernel)", ""]
-        if os.path.exists(rep):
+        if os.path.exists(rep) or os.path.exists(rep[: -len(".ncu-rep")] + ".raw.csv"):
             for d, u in raw_page(rep):
                 lines += [f"Kernel: `{d.get('Kernel Name', '')}`  grid {d.get('Grid Size')} block {d.get('Block Size')}", "",
                           "| metric | value | unit |", "|---|---|---|"]
