@@ -178,6 +178,8 @@ void scratch_free(void* p) {
   if (p) cudaFreeAsync(p, g.cur_stream);
 }
 
+int d2h_fresh(void* dst, const void* src, size_t bytes);
+int h2d_pageable(void* dst, const void* src, size_t bytes);
 In::~In() { scratch_free(owned); }
 int In::acquire(const void* p, size_t bytes) {
   if (p == nullptr) return fail(TACO_B200_ERR_ARG, "NULL operand array");
@@ -190,6 +192,7 @@ int In::acquire(const void* p, size_t bytes) {
   }
   TB_TRY(scratch_alloc(&owned, bytes));
   dptr = owned;
+  if (bytes >= (8u << 20) && m == Mem::Host) return h2d_pageable(owned, p, bytes);     // pageable operand (taco's malloc'ed arrays)
   if (bytes) TB_CUDA(cudaMemcpyAsync(owned, p, bytes, cudaMemcpyHostToDevice, g.cur_stream));
   return TACO_B200_OK;
 }
@@ -206,6 +209,9 @@ int Out::acquire(void* p, size_t nbytes) {
 }
 int Out::commit() {
   if (host_dst && bytes) {
+    // pageable destination (taco's own malloc'ed result arrays): pinned staging + parallel host copies instead of the
+    // driver's single-threaded staged copy (and its page faults, if the array was never touched)
+    if (bytes >= (4u << 20) && classify(host_dst) == Mem::Host) return d2h_fresh(host_dst, dptr, bytes);
     TB_CUDA(cudaMemcpyAsync(host_dst, dptr, bytes, cudaMemcpyDeviceToHost, g.cur_stream));
     g_need_sync = true;
   }
@@ -261,6 +267,44 @@ int d2h_fresh(void* dst, const void* src, size_t bytes) {
     if (c >= 1) TB_TRY(drain(c - 1));           // stage[b ^ 1] is free again before chunk c + 1 is issued into it
   }
   return drain(nchunks - 1);
+}
+
+// Pageable host array -> device: a few host threads copy chunk c into one of two pinned buffers while the DMA of chunk c-1 runs
+// (the driver's own staged copy is single-threaded: ~14 GB/s measured against 55 GB/s from pinned memory).
+int h2d_pageable(void* dst, const void* src, size_t bytes) {
+  constexpr size_t CH = 16u << 20;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  static char* stage[2] = {nullptr, nullptr};
+  static cudaEvent_t ev[2];
+  if (!stage[0]) {
+    for (int b = 0; b < 2; b++) {
+      TB_CUDA(cudaHostAlloc((void**)&stage[b], CH, cudaHostAllocDefault));
+      TB_CUDA(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+      TB_CUDA(cudaEventRecord(ev[b], g.cur_stream));
+    }
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int nthreads = hw >= 8 ? 8 : (hw > 1 ? (int)hw : 1);
+  const size_t nchunks = (bytes + CH - 1) / CH;
+  for (size_t c = 0; c < nchunks; c++) {
+    const int b = (int)(c & 1);
+    const size_t off = c * CH, len = bytes - off < CH ? bytes - off : CH;
+    TB_CUDA(cudaEventSynchronize(ev[b]));       // the DMA that last read stage[b] has finished
+    const size_t per = ((len + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; t++) {
+      const size_t a = (size_t)t * per;
+      if (a >= len) break;
+      const size_t n = len - a < per ? len - a : per;
+      th.emplace_back([=] { memcpy(stage[b] + a, (const char*)src + off + a, n); });
+    }
+    memcpy(stage[b], (const char*)src + off, len < per ? len : per);
+    for (auto& x : th) x.join();
+    TB_CUDA(cudaMemcpyAsync((char*)dst + off, stage[b], len, cudaMemcpyHostToDevice, g.cur_stream));
+    TB_CUDA(cudaEventRecord(ev[b], g.cur_stream));
+  }
+  return TACO_B200_OK;
 }
 
 // Device result arrays come from the stream-ordered pool (release threshold = never trim), so a loop of

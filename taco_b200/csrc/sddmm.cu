@@ -14,6 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tb {
@@ -296,9 +299,23 @@ static int clone_to_result(const void* src, size_t bytes, void** out) {
   *out = dst;
   if (bytes == 0) return TACO_B200_OK;
   bool sdev = classify(src) == Mem::Device, ddev = result_space() == TACO_B200_SPACE_DEVICE;
-  if (!sdev && !ddev) { memcpy(dst, src, bytes); return TACO_B200_OK; }
+  if (!sdev && !ddev) {                          // host -> fresh host array: parallel copy (takes the page faults in parallel)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = bytes < (8u << 20) ? 1 : (hw >= 8 ? 8 : (hw > 1 ? (int)hw : 1));
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) {
+      const size_t a = (size_t)t * per;
+      if (a >= bytes) break;
+      const size_t n = bytes - a < per ? bytes - a : per;
+      th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, n); });
+    }
+    memcpy(dst, src, bytes < per ? bytes : per);
+    for (auto& x : th) x.join();
+    return TACO_B200_OK;
+  }
+  if (sdev && !ddev) return d2h_fresh(dst, src, bytes);
   TB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream()));
-  if (!ddev) TB_CUDA(cudaStreamSynchronize(stream()));
   return TACO_B200_OK;
 }
 
