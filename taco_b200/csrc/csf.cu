@@ -16,6 +16,7 @@
 // Algorithmic bytes: nnz*(4+sizeof T) + 8*nfib + 8*nslice + sizeof T*R*(K + L + I).
 #include <climits>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -288,6 +289,9 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
 struct CsfCall {
   Csf3View B; DType dt; int32_t nslices, nfib, nnz;
   In p1, c1, p2, c2, p3, c3, vals;
+  bool host_described = false;       // every level array and the values live in host memory (read directly by the host)
+  bool uploaded = false;
+  int upload();                      // make the level arrays visible to the device (staging copies for host arrays)
 };
 
 static int csf_prepare(taco_tensor_t* Bt, CsfCall* cc) {
@@ -303,6 +307,20 @@ static int csf_prepare(taco_tensor_t* Bt, CsfCall* cc) {
   if (classify(cc->B.pos[2]) == Mem::Device && Bt->vals_size > 0) cc->nnz = Bt->vals_size;
   else TB_TRY(read_i32(cc->B.pos[2] + cc->nfib, &cc->nnz));
   if (cc->nslices < 0 || cc->nfib < 0 || cc->nnz < 0) return fail(TACO_B200_ERR_ARG, "csf: corrupt pos arrays");
+  cc->host_described = true;
+  for (int l = 0; l < 3; l++) {
+    if (classify(cc->B.pos[l]) == Mem::Device) cc->host_described = false;
+    if (cc->B.crd[l] && classify(cc->B.crd[l]) == Mem::Device) cc->host_described = false;
+  }
+  if (!cc->B.vals || classify(cc->B.vals) == Mem::Device) cc->host_described = false;
+  if (cc->host_described && is_resident(cc->B.vals, dsize(cc->dt) * (size_t)cc->nnz)) cc->host_described = false;   // already in HBM
+  return TACO_B200_OK;
+}
+
+int CsfCall::upload() {
+  if (uploaded) return TACO_B200_OK;
+  uploaded = true;
+  CsfCall* cc = this;
   void* dummy = (void*)cc->B.pos[0];
   TB_TRY(cc->p1.acquire(cc->B.pos[0], sizeof(int32_t) * 2));
   TB_TRY(cc->c1.acquire(cc->B.crd[0] ? (void*)cc->B.crd[0] : dummy, sizeof(int32_t) * (size_t)cc->nslices));
@@ -370,6 +388,125 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
   count_launch(2);
   scratch_free(slot_slices);
   TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-operand pipeline for MTTKRP (the e2e path: B and A in host memory).  Mode-0 slices are independent, so the call is
+// cut into slice chunks, each a self-contained sub-problem over its own row range of A:
+//   upload stream : level arrays and values of chunk c (C and D were uploaded before the loop)
+//   compute stream: rebase the chunk's pos / row ids to chunk-local numbering, then the ordinary slot kernel on it
+//   download stream: the chunk's rows of A
+// Uploads of later chunks overlap kernels and downloads of earlier ones (PCIe is full duplex).  Values are bit-identical
+// to the unpipelined call: the kernel and the per-slice order are the same.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) csf_rebase_kernel(int* __restrict__ a, long long n, int off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] -= off;
+}
+
+static size_t csf_pipeline_min_bytes() {
+  const char* e = getenv("TACO_B200_PIPELINE_MIN_BYTES");
+  return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)64 << 20);
+}
+
+template <typename T>
+static int mttkrp_compute_pipelined(CsfCall& cc, const T* C, const T* D, T* hostA, int R) {
+  const size_t es = sizeof(T);
+  const int I = cc.B.dim[0], ns = cc.nslices, nf = cc.nfib, nz = cc.nnz;
+  const int32_t *h_c1 = cc.B.crd[0], *h_p2 = cc.B.pos[1], *h_c2 = cc.B.crd[1], *h_p3 = cc.B.pos[2], *h_c3 = cc.B.crd[2];
+  const T* h_vals = (const T*)cc.B.vals;
+  const int s_base = cc.B.pos[0][0];
+  cudaStream_t main = stream(), up = aux_stream(0), down = aux_stream(1);
+  const int nchunks = 16;
+  void *d_p1 = nullptr, *d_c1 = nullptr, *d_p2 = nullptr, *d_c2 = nullptr, *d_p3 = nullptr, *d_c3 = nullptr, *d_vals = nullptr, *dA = nullptr;
+  TB_TRY(scratch_alloc(&d_p1, sizeof(int) * 2 * nchunks));
+  TB_TRY(scratch_alloc(&d_c1, sizeof(int) * (size_t)ns));
+  TB_TRY(scratch_alloc(&d_p2, sizeof(int) * ((size_t)ns + nchunks)));       // chunk c lives at offset s0 + c (own closing entry)
+  TB_TRY(scratch_alloc(&d_c2, sizeof(int) * (size_t)nf));
+  TB_TRY(scratch_alloc(&d_p3, sizeof(int) * ((size_t)nf + nchunks)));
+  TB_TRY(scratch_alloc(&d_c3, sizeof(int) * (size_t)nz));
+  TB_TRY(scratch_alloc(&d_vals, es * (size_t)nz));
+  TB_TRY(scratch_alloc(&dA, es * (size_t)I * R));
+  cudaEvent_t ready, done_all;
+  TB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  TB_CUDA(cudaEventCreateWithFlags(&done_all, cudaEventDisableTiming));
+  TB_CUDA(cudaEventRecord(ready, main));            // pool allocations and the C / D uploads are ordered on the compute stream
+  TB_CUDA(cudaStreamWaitEvent(up, ready, 0));
+  TB_CUDA(cudaStreamWaitEvent(down, ready, 0));
+  // chunk boundaries balanced by transferred bytes: leaves and fibers up, rows of A down
+  auto weight = [&](int s) -> double {               // bytes moved for slices [0, s)
+    const int f = h_p2[s_base + s];
+    const double rows = s < ns ? (double)h_c1[s_base + s] : (double)I;
+    return (4.0 + es) * h_p3[f] + 8.0 * f + (double)R * es * rows;
+  };
+  const double total = weight(ns);
+  std::vector<int> hp1(2 * nchunks, 0);
+  int s0 = 0, rc = TACO_B200_OK;
+  std::vector<int> bounds;
+  bounds.push_back(0);
+  for (int c = 0; c < nchunks - 1; c++) {
+    const double target = total * (c + 1) / nchunks;
+    int lo = bounds.back(), hi = ns;
+    while (lo < hi) { const int mid = lo + (hi - lo) / 2; if (weight(mid) >= target) hi = mid; else lo = mid + 1; }
+    bounds.push_back(lo);
+  }
+  bounds.push_back(ns);
+  for (int c = 0; c < nchunks; c++) hp1[2 * c + 1] = bounds[c + 1] - bounds[c];
+  TB_CUDA(cudaMemcpyAsync(d_p1, hp1.data(), sizeof(int) * 2 * nchunks, cudaMemcpyHostToDevice, up));
+  TB_CUDA(cudaStreamSynchronize(up));                // hp1 is a local: its copy must not outlive it (tiny)
+  for (int c = 0; c < nchunks && rc == TACO_B200_OK; c++) {
+    s0 = bounds[c];
+    const int s1 = bounds[c + 1];
+    const int row0 = c == 0 ? 0 : h_c1[s_base + s0];
+    const int row1 = s1 < ns ? h_c1[s_base + s1] : I;
+    if (s1 == s0 && row1 == row0) continue;
+    const int f0 = h_p2[s_base + s0], f1 = h_p2[s_base + s1], l0 = h_p3[f0], l1 = h_p3[f1];
+    int* c1 = (int*)d_c1 + s0; int* p2 = (int*)d_p2 + s0 + c; int* c2 = (int*)d_c2 + f0; int* p3 = (int*)d_p3 + f0 + c;
+    int* c3 = (int*)d_c3 + l0; T* vv = (T*)d_vals + l0;
+    cudaEvent_t e_up, e_done;
+    TB_CUDA(cudaEventCreateWithFlags(&e_up, cudaEventDisableTiming));
+    TB_CUDA(cudaEventCreateWithFlags(&e_done, cudaEventDisableTiming));
+    if (s1 > s0) {
+      TB_CUDA(cudaMemcpyAsync(c1, h_c1 + s_base + s0, sizeof(int) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, up));
+      TB_CUDA(cudaMemcpyAsync(p2, h_p2 + s_base + s0, sizeof(int) * (size_t)(s1 - s0 + 1), cudaMemcpyHostToDevice, up));
+      TB_CUDA(cudaMemcpyAsync(p3, h_p3 + f0, sizeof(int) * (size_t)(f1 - f0 + 1), cudaMemcpyHostToDevice, up));
+      if (f1 > f0) TB_CUDA(cudaMemcpyAsync(c2, h_c2 + f0, sizeof(int) * (size_t)(f1 - f0), cudaMemcpyHostToDevice, up));
+      if (l1 > l0) {
+        TB_CUDA(cudaMemcpyAsync(c3, h_c3 + l0, sizeof(int) * (size_t)(l1 - l0), cudaMemcpyHostToDevice, up));
+        TB_CUDA(cudaMemcpyAsync(vv, h_vals + l0, es * (size_t)(l1 - l0), cudaMemcpyHostToDevice, up));
+      }
+    }
+    TB_CUDA(cudaEventRecord(e_up, up));
+    TB_CUDA(cudaStreamWaitEvent(main, e_up, 0));
+    if (s1 > s0) {
+      csf_rebase_kernel<<<(unsigned)((s1 - s0 + 255) / 256), 256, 0, main>>>(c1, s1 - s0, row0);
+      csf_rebase_kernel<<<(unsigned)((s1 - s0 + 1 + 255) / 256), 256, 0, main>>>(p2, s1 - s0 + 1, f0);
+      csf_rebase_kernel<<<(unsigned)((f1 - f0 + 1 + 255) / 256), 256, 0, main>>>(p3, (long long)f1 - f0 + 1, l0);
+      count_launch(3);
+    }
+    CsfCall sub;
+    sub.B = cc.B; sub.B.dim[0] = row1 - row0; sub.dt = cc.dt;
+    sub.nslices = s1 - s0; sub.nfib = f1 - f0; sub.nnz = l1 - l0;
+    sub.p1.dptr = (int*)d_p1 + 2 * c; sub.c1.dptr = c1; sub.p2.dptr = p2; sub.c2.dptr = c2; sub.p3.dptr = p3; sub.c3.dptr = c3;
+    sub.vals.dptr = vv;
+    T* Achunk = (T*)dA + (size_t)row0 * R;
+    rc = mttkrp_launch<T>(sub, C, D, Achunk, (size_t)(row1 - row0) * R, R);
+    TB_CUDA(cudaEventRecord(e_done, main));
+    TB_CUDA(cudaStreamWaitEvent(down, e_done, 0));
+    if (row1 > row0)
+      TB_CUDA(cudaMemcpyAsync(hostA + (size_t)row0 * R, Achunk, es * (size_t)(row1 - row0) * R, cudaMemcpyDeviceToHost, down));
+    cudaEventDestroy(e_up);
+    cudaEventDestroy(e_done);
+  }
+  TB_CUDA(cudaEventRecord(done_all, down));
+  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));
+  cudaEventDestroy(ready);
+  cudaEventDestroy(done_all);
+  scratch_free(d_p1); scratch_free(d_c1); scratch_free(d_p2); scratch_free(d_c2); scratch_free(d_p3); scratch_free(d_c3);
+  scratch_free(d_vals); scratch_free(dA);
+  TB_TRY(rc);
+  TB_CUDA(cudaStreamSynchronize(main));
   return TACO_B200_OK;
 }
 
@@ -495,6 +632,13 @@ int taco_b200_mttkrp_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* 
   In cin, din; Out aout;
   TB_TRY(cin.acquire(Cv.vals, es * Cv.count()));
   TB_TRY(din.acquire(Dv.vals, es * Dv.count()));
+  if (cc.host_described && classify(Av.vals) != Mem::Device && cc.nslices > 0 && cc.nnz > 0 && R > 0 && cc.nnz <= INT32_MAX - 65536 &&
+      (4 + es) * (size_t)cc.nnz + es * Av.count() >= csf_pipeline_min_bytes()) {
+    if (!Av.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+    if (cc.dt == DType::F64) return mttkrp_compute_pipelined<double>(cc, cin.as<double>(), din.as<double>(), (double*)Av.vals, R);
+    return mttkrp_compute_pipelined<float>(cc, cin.as<float>(), din.as<float>(), (float*)Av.vals, R);
+  }
+  TB_TRY(cc.upload());
   TB_TRY(aout.acquire(Av.vals, es * Av.count()));
   if (cc.dt == DType::F64) TB_TRY(mttkrp_launch<double>(cc, cin.as<double>(), din.as<double>(), aout.as<double>(), Av.count(), R));
   else TB_TRY(mttkrp_launch<float>(cc, cin.as<float>(), din.as<float>(), aout.as<float>(), Av.count(), R));
@@ -516,6 +660,7 @@ int taco_b200_ttv_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* c) 
   TB_TRY(view_dense(c, 1, "c", &cv));
   CsfCall cc;
   TB_TRY(csf_prepare(B, &cc));
+  TB_TRY(cc.upload());
   if (Av.mode_order[0] != 0) return fail(TACO_B200_ERR_FORMAT, "ttv: A must be row-major");
   if (Av.dim[0] != cc.B.dim[0] || Av.dim[1] != cc.B.dim[1] || cv.dim[0] != cc.B.dim[2])
     return fail(TACO_B200_ERR_ARG, "ttv: dimension mismatch");
@@ -544,6 +689,7 @@ int taco_b200_ttm_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C) 
   TB_TRY(view_dense(C, 2, "C", &Cv));
   CsfCall cc;
   TB_TRY(csf_prepare(B, &cc));
+  TB_TRY(cc.upload());
   if (Av.mode_order[0] != 0 || Av.mode_order[1] != 1 || Cv.mode_order[0] != 0)
     return fail(TACO_B200_ERR_FORMAT, "ttm: A and C must be row-major");
   const int R = Av.dim[2];

@@ -276,6 +276,54 @@ def test_oracle_mttkrp_long_fibers_and_gaps():
     assert np.array_equal(A.reshape(5000, 32), want)
 
 
+@pytest.mark.parametrize("dtype,R", [("float64", 32), ("float32", 16), ("float64", 5)])
+def test_oracle_mttkrp_host_pipeline(dtype, R, monkeypatch):
+    # host operands through the slice-chunked upload / rebase / kernel / download pipeline (forced for this small case):
+    # empty slices and rows in between, a hub slice, pageable and pinned buffers; bit-identical to the unpipelined call
+    monkeypatch.setenv("TACO_B200_PIPELINE_MIN_BYTES", "0")
+    w = synth.make("mttkrp", None, I=5_000, K=40, L=3_000, nnz=400_000, R=R, dtype=dtype)
+    keep = np.ones(w["B1_crd"].shape[0], bool)
+    keep[:3] = False                                       # leading rows of A without a slice
+    keep[100:400] = False                                  # a gap
+    keep[-5:] = False                                      # trailing rows without a slice
+    i, k, l, v = formats.csf3_to_coo(w)
+    sel = keep[np.searchsorted(w["B1_crd"], i)]
+    hub = np.arange(2500, dtype=np.int64)                  # one slice with 2500 leaves (> 512: split across slots)
+    i2 = np.concatenate([i[sel], np.full(hub.size, 777)])
+    k2 = np.concatenate([k[sel], hub % 40])
+    l2 = np.concatenate([l[sel], hub % 3000])
+    v2 = np.concatenate([v[sel], np.ones(hub.size, v.dtype)])
+    flat = (i2.astype(np.int64) * 40 + k2) * 3000 + l2
+    _, first = np.unique(flat, return_index=True)
+    t = formats.coo_to_csf3(i2[first], k2[first], l2[first], v2[first])
+    want = oracle.mttkrp(t, w["C"].reshape(40, R), w["D"].reshape(3000, R), 5000)
+    w2 = dict(dims=w["dims"], C=w["C"], D=w["D"], **t)
+    A = G.run("mttkrp", w2).reshape(5000, R)
+    short = np.ones(5000, bool)
+    short[777] = False
+    assert np.array_equal(A[short], want[short])
+    H.assert_close(A.reshape(-1), want.reshape(-1), np.dtype(dtype))
+    wp = {}
+    for key, val in w2.items():
+        if key == "dims":
+            wp[key] = val
+        else:
+            a = tb.pinned_empty(val.shape, val.dtype)
+            a[...] = val
+            wp[key] = a
+    try:
+        A2 = G.run("mttkrp", wp).reshape(5000, R)
+        assert np.array_equal(A2[short], want[short])
+        H.assert_close(A2.reshape(-1), want.reshape(-1), np.dtype(dtype))
+    finally:
+        for key, val in wp.items():
+            if key != "dims":
+                tb.pinned_free(val)
+    monkeypatch.setenv("TACO_B200_PIPELINE_MIN_BYTES", str(1 << 40))          # the unpipelined path on the same operands
+    A3 = G.run("mttkrp", w2).reshape(5000, R)
+    assert np.array_equal(A3[short], A[short])
+
+
 def test_oracle_ttv_ttm():
     w = synth.make("mttkrp", None, I=3_000, K=500, L=800, nnz=200_000, R=16, dtype="float64")
     I, K, L, R = w["dims"]
