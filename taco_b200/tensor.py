@@ -212,6 +212,8 @@ class Tensor:
                 if compressed not in self.format.levels[l + 1:]:          # last compressed level: one node per stored value
                     child = int(self.ct.vals_size) if nnz is None else nnz
                 else:           # an inner compressed level (DCSR / CSF results of pack()): its node count is pos[parent size]
+                    if isinstance(pos, _DeviceArray):
+                        check(lib.taco_b200_synchronize())      # the library's stream wrote it; torch reads on its own stream
                     child = int(self.to_numpy(self._as_user_array(pos))[size])
                 crd = self._adopt((l, 1), crd_ptr, child, np.int32)
                 self.arrays[(l, 0)] = self._as_user_array(pos)
