@@ -66,11 +66,18 @@ __device__ __forceinline__ void spmv_load4(const int* __restrict__ crd, const T*
   }
 }
 
-template <typename T>
+// GV = 0: L1-allocating gather (default), GV = 1: L1::no_allocate (the gathered sectors of a uniform matrix are never re-used
+// inside an SM; measured as TACO_B200_SPMV_VARIANT=3)
+template <typename T, int GV = 0>
 __device__ __forceinline__ T spmv_ld_x(const T* p, uint64_t keep) {
   T r;
-  if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(keep));
-  else asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(keep));
+  if constexpr (GV == 1) {
+    if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(keep));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(keep));
+  } else {
+    if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(keep));
+    else asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(keep));
+  }
   return r;
 }
 
@@ -92,7 +99,7 @@ __device__ __forceinline__ T spmv_block_sum(const T* prod, int a, int b, T* red)
 
 // MAPPED: row r is stored at y[ymap[r]] instead of y[r] (TTV: the rows are the fibers of a CSF tensor and ymap holds their
 // positions in the dense result, csf.cu); the unmapped instantiation is unchanged by the flag.
-template <typename T, int MINB, bool MAPPED>
+template <typename T, int MINB, bool MAPPED, int GV = 0>
 __global__ void __launch_bounds__(SPMV_THREADS, MINB)
 spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
@@ -146,8 +153,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   for (int s = 0; s < SPMV_STEPS; s++) {
     const int q = (s * SPMV_THREADS + tid) * SPMV_VEC;
     if (lo + q < hiov) {
-      const T x0 = spmv_ld_x(x + c[s].x, keep), x1 = spmv_ld_x(x + c[s].y, keep), x2 = spmv_ld_x(x + c[s].z, keep),
-              x3 = spmv_ld_x(x + c[s].w, keep);
+      const T x0 = spmv_ld_x<T, GV>(x + c[s].x, keep), x1 = spmv_ld_x<T, GV>(x + c[s].y, keep), x2 = spmv_ld_x<T, GV>(x + c[s].z, keep),
+              x3 = spmv_ld_x<T, GV>(x + c[s].w, keep);
       T* d = prod + q;
       d[0] = v[s][0] * x0; d[1] = v[s][1] * x1; d[2] = v[s][2] * x2; d[3] = v[s][3] * x3;
     }
@@ -156,8 +163,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   if (tid >= 32 && tid < 32 + SPMV_OV / SPMV_VEC && lo + SPMV_TILE + (tid - 32) * SPMV_VEC < hiov) {
     const int q = SPMV_TILE + (tid - 32) * SPMV_VEC;
     spmv_load4<T>(crd, vals, lo + q, nnz, c[0], v[0]);
-    const T x0 = spmv_ld_x(x + c[0].x, keep), x1 = spmv_ld_x(x + c[0].y, keep), x2 = spmv_ld_x(x + c[0].z, keep),
-            x3 = spmv_ld_x(x + c[0].w, keep);
+    const T x0 = spmv_ld_x<T, GV>(x + c[0].x, keep), x1 = spmv_ld_x<T, GV>(x + c[0].y, keep), x2 = spmv_ld_x<T, GV>(x + c[0].z, keep),
+            x3 = spmv_ld_x<T, GV>(x + c[0].w, keep);
     T* d = prod + q;
     d[0] = v[0][0] * x0; d[1] = v[0][1] * x1; d[2] = v[0][2] * x2; d[3] = v[0][3] * x3;
   }
@@ -239,13 +246,15 @@ static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const 
   static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
   {
     ProfScope ps(prof_name);
-#define TB_SPMV_GO(MINB, MAPPED)                                                                                       \
-  spmv_csr_kernel<T, MINB, MAPPED><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz, (T*)g_spmv_partial, \
-                                                                          g_spmv_flag, g_spmv_epoch, ymap)
-    if (ymap) TB_SPMV_GO(6, true);
-    else if (variant == 1) TB_SPMV_GO(8, false);
-    else if (variant == 2) TB_SPMV_GO(7, false);
-    else TB_SPMV_GO(6, false);
+#define TB_SPMV_GO(MINB, MAPPED, GV)                                                                                   \
+  spmv_csr_kernel<T, MINB, MAPPED, GV><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz,           \
+                                                                              (T*)g_spmv_partial, g_spmv_flag, g_spmv_epoch, ymap)
+    if (ymap && variant == 3) TB_SPMV_GO(6, true, 1);
+    else if (ymap) TB_SPMV_GO(6, true, 0);
+    else if (variant == 1) TB_SPMV_GO(8, false, 0);
+    else if (variant == 2) TB_SPMV_GO(7, false, 0);
+    else if (variant == 3) TB_SPMV_GO(6, false, 1);
+    else TB_SPMV_GO(6, false, 0);
 #undef TB_SPMV_GO
   }
   count_launch(1);

@@ -22,11 +22,11 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-timeout 600 python -m pytest tests -m gpu -q -k "ttv or ttm" 2>&1 | tail -5
+run spmv X=0
+run spmv TACO_B200_SPMV_VARIANT=3
+run spmv X=0
+run spmv TACO_B200_SPMV_VARIANT=3
 run ttv X=0
-run ttm TACO_B200_TTM_VARIANT=1
-run ttm X=0
-ncuq ttv spmv_csr X=0
-ncuq ttm spmm_csr X=0
-} > gpurun_out/exp_11.txt 2>&1
-cat gpurun_out/exp_11.txt
+run ttv TACO_B200_SPMV_VARIANT=3
+} > gpurun_out/exp_12.txt 2>&1
+cat gpurun_out/exp_12.txt
