@@ -491,8 +491,20 @@ static int spmm_mapped_impl(const int* pos, const int* crd, const T* vals, const
     ProfScope ps(prof_name);
     constexpr int WARPS = 8;
     dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-    spmm_csr_kernel<T, VEC, false, 2, WARPS, 8, true><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                       (const int*)slot_rows, rowmap);
+    // (gathers in flight per warp, min CTAs per SM): rows narrower than a full warp fragment (K * sizeof T < 512 bytes) keep
+    // fewer bytes in flight per gather, so deeper unrolling is worth its registers there (TACO_B200_TTM_UNROLL=2..5 to compare)
+    static const int variant = getenv("TACO_B200_TTM_UNROLL") ? atoi(getenv("TACO_B200_TTM_UNROLL")) : 0;
+#define TB_MAPPED_GO(U, MINB)                                                                                              \
+  spmm_csr_kernel<T, VEC, false, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, rg, nslots, \
+                                                                                          (const int*)slot_rows, rowmap)
+    switch (variant) {
+      case 2: TB_MAPPED_GO(4, 6); break;
+      case 3: TB_MAPPED_GO(4, 8); break;
+      case 4: TB_MAPPED_GO(4, 4); break;
+      case 5: TB_MAPPED_GO(8, 4); break;
+      default: TB_MAPPED_GO(2, 8); break;
+    }
+#undef TB_MAPPED_GO
   }
   count_launch(2);
   scratch_free(slot_rows);

@@ -22,11 +22,6 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-run spmv X=0
-run spmv TACO_B200_SPMV_VARIANT=3
-run spmv X=0
-run spmv TACO_B200_SPMV_VARIANT=3
-run ttv X=0
-run ttv TACO_B200_SPMV_VARIANT=3
-} > gpurun_out/exp_12.txt 2>&1
-cat gpurun_out/exp_12.txt
+for v in 0 2 3 4 5; do run ttm TACO_B200_TTM_UNROLL=$v; done
+} > gpurun_out/exp_13.txt 2>&1
+cat gpurun_out/exp_13.txt
