@@ -99,27 +99,28 @@ __device__ __forceinline__ T spmv_block_sum(const T* prod, int a, int b, T* red)
 
 // MAPPED: row r is stored at y[ymap[r]] instead of y[r] (TTV: the rows are the fibers of a CSF tensor and ymap holds their
 // positions in the dense result, csf.cu); the unmapped instantiation is unchanged by the flag.
-template <typename T, int MINB, bool MAPPED, int GV = 0>
+template <typename T, int MINB, bool MAPPED, int GV = 0, int STEPS = SPMV_STEPS>
 __global__ void __launch_bounds__(SPMV_THREADS, MINB)
 spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
                 int* __restrict__ flag, int epoch, const unsigned* __restrict__ ymap) {
-  __shared__ T prod[SPMV_TILE + SPMV_OV];
+  constexpr int TILE = SPMV_THREADS * SPMV_VEC * STEPS;      // nonzeros per CTA (TACO_B200_SPMV_VARIANT=4..6 sweep it)
+  __shared__ T prod[TILE + SPMV_OV];
   __shared__ T red[SPMV_THREADS / 32];
   __shared__ int s_cnt[SPMV_THREADS / 32];
   __shared__ int s_long[4];                        // tail row, its start
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
-  const int lo = b * SPMV_TILE;                    // window [lo, hi), staged [lo, hiov)
-  const int hi = min(lo + SPMV_TILE, nnz);
-  const int hiov = min(lo + SPMV_TILE + SPMV_OV, nnz);
+  const int lo = b * TILE;                    // window [lo, hi), staged [lo, hiov)
+  const int hi = min(lo + TILE, nnz);
+  const int hiov = min(lo + TILE + SPMV_OV, nnz);
   const bool last_tile = (b == (int)gridDim.x - 1);
 
   // ---- (0) window loads: independent of the row structure ------------------------------------------------------
-  int4 c[SPMV_STEPS];
-  T v[SPMV_STEPS][4];
+  int4 c[STEPS];
+  T v[STEPS][4];
 #pragma unroll
-  for (int s = 0; s < SPMV_STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, c[s], v[s]);
+  for (int s = 0; s < STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, c[s], v[s]);
   if (tid == 0) s_long[0] = -1;
 
   // ---- (1) owned rows [r_lo, r_hi): first row with pos[r] >= lo / >= hi.  Warp 0 alone runs two 16-ary searches
@@ -150,7 +151,7 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   // ---- (2) products into shared memory ------------------------------------------------------------------------------
   const uint64_t keep = tbd::policy_evict_last();
 #pragma unroll
-  for (int s = 0; s < SPMV_STEPS; s++) {
+  for (int s = 0; s < STEPS; s++) {
     const int q = (s * SPMV_THREADS + tid) * SPMV_VEC;
     if (lo + q < hiov) {
       const T x0 = spmv_ld_x<T, GV>(x + c[s].x, keep), x1 = spmv_ld_x<T, GV>(x + c[s].y, keep), x2 = spmv_ld_x<T, GV>(x + c[s].z, keep),
@@ -160,8 +161,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     }
   }
   // the overlap into the next window: 16 threads of warp 1
-  if (tid >= 32 && tid < 32 + SPMV_OV / SPMV_VEC && lo + SPMV_TILE + (tid - 32) * SPMV_VEC < hiov) {
-    const int q = SPMV_TILE + (tid - 32) * SPMV_VEC;
+  if (tid >= 32 && tid < 32 + SPMV_OV / SPMV_VEC && lo + TILE + (tid - 32) * SPMV_VEC < hiov) {
+    const int q = TILE + (tid - 32) * SPMV_VEC;
     spmv_load4<T>(crd, vals, lo + q, nnz, c[0], v[0]);
     const T x0 = spmv_ld_x<T, GV>(x + c[0].x, keep), x1 = spmv_ld_x<T, GV>(x + c[0].y, keep), x2 = spmv_ld_x<T, GV>(x + c[0].z, keep),
             x3 = spmv_ld_x<T, GV>(x + c[0].w, keep);
@@ -194,8 +195,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     const int e_head = __ldg(pos + r_lo);          // uniform over the CTA
     if (e_head > lo) {
       const int s_head = __ldg(pos + r_lo - 1);
-      const int b0 = s_head / SPMV_TILE;           // owner tile
-      if (e_head > min((b0 + 1) * SPMV_TILE + SPMV_OV, nnz)) {     // the owner handed this row over
+      const int b0 = s_head / TILE;           // owner tile
+      if (e_head > min((b0 + 1) * TILE + SPMV_OV, nnz)) {     // the owner handed this row over
         if (e_head > hi) {                         // this window lies wholly inside the row
           const T sum = spmv_block_sum(prod, 0, hi - lo, red);
           if (tid == 0) {
@@ -230,7 +231,10 @@ static int g_spmv_epoch = 0;
 template <typename T>
 static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const T* x, T* y, int rows, int nnz, const unsigned* ymap,
                            const char* prof_name) {
-  const int ntiles = nnz > 0 ? (nnz + SPMV_TILE - 1) / SPMV_TILE : 1;
+  static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
+  const int steps = (!ymap && (variant == 4 || variant == 6)) ? 1 : (!ymap && variant == 5) ? 4 : SPMV_STEPS;
+  const int tile = SPMV_THREADS * SPMV_VEC * steps;
+  const int ntiles = nnz > 0 ? (nnz + tile - 1) / tile : 1;
   if (ntiles > g_spmv_cap) {
     if (g_spmv_partial) { cudaFree(g_spmv_partial); cudaFree(g_spmv_flag); }
     g_spmv_cap = ntiles + ntiles / 2 + 1024;
@@ -243,17 +247,19 @@ static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const 
     TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
     g_spmv_epoch = 1;
   }
-  static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
   {
     ProfScope ps(prof_name);
-#define TB_SPMV_GO(MINB, MAPPED, GV)                                                                                   \
-  spmv_csr_kernel<T, MINB, MAPPED, GV><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz,           \
+#define TB_SPMV_GO(MINB, MAPPED, GV, ...)                                                                              \
+  spmv_csr_kernel<T, MINB, MAPPED, GV, ##__VA_ARGS__><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz, \
                                                                               (T*)g_spmv_partial, g_spmv_flag, g_spmv_epoch, ymap)
     if (ymap && variant == 3) TB_SPMV_GO(6, true, 1);
     else if (ymap) TB_SPMV_GO(6, true, 0);
     else if (variant == 1) TB_SPMV_GO(8, false, 0);
     else if (variant == 2) TB_SPMV_GO(7, false, 0);
     else if (variant == 3) TB_SPMV_GO(6, false, 1);
+    else if (variant == 4) TB_SPMV_GO(6, false, 0, 1);       // 1024-nonzero tiles
+    else if (variant == 5) TB_SPMV_GO(6, false, 0, 4);       // 4096-nonzero tiles
+    else if (variant == 6) TB_SPMV_GO(8, false, 0, 1);       // 1024-nonzero tiles, 8 CTAs per SM
     else TB_SPMV_GO(6, false, 0);
 #undef TB_SPMV_GO
   }

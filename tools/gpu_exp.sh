@@ -22,6 +22,9 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-for v in 0 2 3 4 5; do run ttm TACO_B200_TTM_UNROLL=$v; done
-} > gpurun_out/exp_13.txt 2>&1
-cat gpurun_out/exp_13.txt
+for v in 4 5 6; do
+echo "== parity TACO_B200_SPMV_VARIANT=$v"; TACO_B200_SPMV_VARIANT=$v timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "spmv" 2>&1 | tail -1
+done
+for v in 0 4 5 6 0 4 6; do run spmv TACO_B200_SPMV_VARIANT=$v; done
+} > gpurun_out/exp_14.txt 2>&1
+cat gpurun_out/exp_14.txt
