@@ -23,6 +23,7 @@
 // Algorithmic bytes per launch: 4(Mb+1) + nnzb*(4 + br*bc*es) + es*K*(Nb*bc + Mb*br).
 #include <cuda.h>
 
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -509,7 +510,9 @@ static int bspmm_launch(const BcsrView& A, const int* pos, const int* crd, const
   if (A.Mb == 0 || K == 0) return TACO_B200_OK;
   ProfScope ps("bspmm_bcsr");
   if constexpr (sizeof(T) == 4) {
-    const bool aligned = (K % 4 == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)vals & 15) == 0);
+    const bool aligned = (K % 4 == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)vals & 15) == 0) &&
+                         (long long)A.Nb * A.bc <= INT32_MAX && (K + 127) / 128 <= 65535;   // TMA row coordinates are int32; grid.y
+
     static const int variant = getenv("TACO_B200_BSPMM_VARIANT") ? atoi(getenv("TACO_B200_BSPMM_VARIANT")) : 0;
     if (tc_enabled() && aligned) {
       // (raw stages, lo stages, converter warps, CTAs per SM); measured 1.59 / 2.00 / 1.93 / 1.60 ms for variants 0, 11, 12,
