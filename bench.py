@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the taco GPU hot path on B200, next to the reference's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm|ttv|ttm|pack]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload spmm|spmv|sddmm|mttkrp|spadd|spgemm|bspmm|bspmv|ttv|ttm|pack]
     python bench.py --impl reference ...          # the reference's own C/OpenMP codegen on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU; rank 0 prints the JSON line)
 
@@ -37,6 +37,7 @@ FLOPS = {   # per step, as the reference counts them
     "spadd": lambda s: 1.0 * s["nnzC"],
     "spgemm": lambda s: 2.0 * s["products"],
     "bspmm": lambda s: 2.0 * s["nnzb"] * s["br"] * s["bc"] * s["K"],
+    "bspmv": lambda s: 2.0 * s["nnzb"] * s["br"] * s["bc"],
     "ttv": lambda s: 2.0 * s["nnz"],
     "ttm": lambda s: 2.0 * s["nnz"] * s["R"],
     "pack": lambda s: 1.0 * s["n"],            # not flops: coordinates packed (metric pack_gcoords, unit Gcoord/s)
@@ -46,7 +47,7 @@ FLOPS = {   # per step, as the reference counts them
 def metric_of(wl):
     return (f"{wl}_gcoords", "Gcoord/s") if wl == "pack" else (f"{wl}_gflops", "GFLOP/s")
 DOMINANT = {"spmv": "spmv_csr", "spmm": "spmm_csr", "sddmm": "sddmm_csr", "mttkrp": "mttkrp_csf",
-            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr", "ttv": "ttv_csf", "ttm": "ttm_csf", "pack": "pack_coo"}
+            "spadd": "spadd_numeric", "spgemm": "spgemm_numeric", "bspmm": "bspmm_bcsr", "bspmv": "bspmv_bcsr", "ttv": "ttv_csf", "ttm": "ttm_csf", "pack": "pack_coo"}
 
 
 def algorithmic_bytes(wl, s):
@@ -70,6 +71,8 @@ def algorithmic_bytes(wl, s):
         return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * (s["Ld"] + s["I"] * s["Kd"])
     if wl == "ttm":        # + every row of C and of the (I*K x R) result touched once
         return s["nnz"] * (4 + e) + 8 * s["nfib"] + 8 * s["nslices"] + e * s["R"] * (s["Ld"] + s["I"] * s["Kd"])
+    if wl == "bspmv":      # blocks streamed once, c and a touched once
+        return 4 * (s["Mb"] + 1) + s["nnzb"] * (4 + e * s["br"] * s["bc"]) + e * (s["Nb"] * s["bc"] + s["Mb"] * s["br"])
     if wl == "bspmm":      # blocks streamed once, every row of B and C touched once
         return 4 * (s["Mb"] + 1) + s["nnzb"] * (4 + e * s["br"] * s["bc"]) + e * s["K"] * (s["Nb"] * s["bc"] + s["Mb"] * s["br"])
     raise KeyError(wl)
@@ -92,6 +95,8 @@ def sizes_of(wl, w, extra=None):
     elif wl in ("ttv", "ttm"):
         s.update(I=d[0], Kd=d[1], Ld=d[2], R=d[3] if wl == "ttm" else 1, nnz=int(w["B3_crd"].shape[0]),
                  nfib=int(w["B2_crd"].shape[0]), nslices=int(w["B1_crd"].shape[0]))
+    elif wl == "bspmv":
+        s.update(Mb=d[0], Nb=d[1], br=d[2], bc=d[3], K=1, nnzb=int(w["A_crd"].shape[0]))
     elif wl == "bspmm":
         s.update(Mb=d[0], Nb=d[1], br=d[2], bc=d[3], K=d[4], nnzb=int(w["A_crd"].shape[0]))
     else:
@@ -162,7 +167,7 @@ def make_workload(wl, device, rank, scale_down):
     if scale_down:    # quick functional runs (tests); never used for reported numbers
         over = {"spmm": dict(scale=16), "spmv": dict(n=100_000), "sddmm": dict(n=100_000),
                 "mttkrp": dict(I=100_000, K=20_000, L=20_000, nnz=2_000_000), "spadd": dict(n=100_000),
-                "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048), "ttv": dict(I=512, K=512, L=50_000, nnz=2_000_000),
+                "spgemm": dict(n=50_000), "bspmm": dict(Mb=2048), "bspmv": dict(Mb=2048), "ttv": dict(I=512, K=512, L=50_000, nnz=2_000_000),
                 "ttm": dict(I=128, K=128, L=50_000, nnz=1_000_000), "pack": dict(n=50_000, nnz=400_000)}[wl]
     if wl == "bspmm" and os.environ.get("TACO_B200_BENCH_BLOCK"):      # block-shape sweep (experiments only): 16 -> 16x16 blocks,
         b = int(os.environ["TACO_B200_BENCH_BLOCK"])                  # same matrix dimension and number of stored values
@@ -211,12 +216,13 @@ def reference_sample(wl, w, budget_rows):
         h.update(c0=G.to_host(w["c0"][:n]), c1=G.to_host(w["c1"][:n]), vals=G.to_host(w["vals"][:n]))
         dims = [int(x) for x in w["dims"]]
         frac = n / max(int(w["vals"].shape[0]), 1)
-    elif wl == "bspmm":
+    elif wl in ("bspmm", "bspmv"):
         rows = min(budget_rows, int(w["dims"][0]))
         pos = G.to_host(w["A_pos"][: rows + 1])
         nb = int(pos[-1])
         bsz = int(w["dims"][2]) * int(w["dims"][3])
-        h.update(A_pos=pos, A_crd=G.to_host(w["A_crd"][:nb]), A_vals=G.to_host(w["A_vals"][: nb * bsz]), B=G.to_host(w["B"]))
+        h.update(A_pos=pos, A_crd=G.to_host(w["A_crd"][:nb]), A_vals=G.to_host(w["A_vals"][: nb * bsz]))
+        h.update(B=G.to_host(w["B"])) if wl == "bspmm" else h.update(c=G.to_host(w["c"]))
         dims = [rows] + [int(x) for x in w["dims"][1:]]
         frac = nb / max(int(w["A_crd"].shape[0]), 1)
     elif wl == "sddmm":
@@ -286,6 +292,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
         "pack": lambda: oracle.pack("csr", d, [h["c0"], h["c1"]], h["vals"]),
         "ttv": lambda: oracle.ttv(h, h["c"], d[0], d[1]),
         "ttm": lambda: oracle.ttm(h, h["C"].reshape(d[2], -1), d[0], d[1]),
+        "bspmv": lambda: oracle.bspmv(h["A_pos"], h["A_crd"], h["A_vals"].reshape(-1, d[2], d[3]), h["c"].reshape(d[1], d[3]), d[2], d[3]),
         "bspmm": lambda: oracle.bspmm(h["A_pos"], h["A_crd"], h["A_vals"].reshape(-1, d[2], d[3]),
                                       h["B"].reshape(d[1] * d[3], -1), d[2], d[3]),
     }[wl]
@@ -299,7 +306,7 @@ def run_reference_cpu(wl, h, dtype, reps, threads):
 
 
 SAMPLE_ROWS = {"spmm": 1 << 19, "spmv": 1_000_000, "sddmm": 250_000, "mttkrp": 500_000, "spadd": 1_000_000,
-               "spgemm": 200_000, "bspmm": 2048, "ttv": 1024, "ttm": 64, "pack": 2_000_000}
+               "spgemm": 200_000, "bspmm": 2048, "bspmv": 8192, "ttv": 1024, "ttm": 64, "pack": 2_000_000}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -549,6 +556,8 @@ def workload_name(wl, s):
         return f"CSR SpMV fp64 uniform {s['rows']}x{s['cols']} nnz={s['nnz']}"
     if wl == "sddmm":
         return f"CSR SDDMM fp32 uniform {s['rows']}x{s['cols']} nnz={s['nnz']} K={s['K']}"
+    if wl == "bspmv":
+        return (f"BCSR SpMV fp64 {s['Mb'] * s['br']}x{s['Nb'] * s['bc']} in {s['br']}x{s['bc']} blocks, {s['nnzb']} stored blocks")
     if wl == "bspmm":
         return (f"BCSR SpMM fp32 {s['Mb'] * s['br']}x{s['Nb'] * s['bc']} in {s['br']}x{s['bc']} blocks, "
                 f"{s['nnzb']} stored blocks, K={s['K']}")

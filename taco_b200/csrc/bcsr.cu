@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <climits>
+#include <type_traits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -74,6 +75,77 @@ bspmv_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* 
     acc = acc + tl;
   }
   a[t] = acc;
+}
+
+// Staged variant for br <= 32: a warp owns a block row.  Each stored block is read with coalesced 16-byte loads into a padded
+// shared-memory tile (the whole block is one contiguous br*bc run in vals), c(k,:) likewise; lane j then forms tl for its
+// row j in ascending l from shared memory and adds it -- the same operation order as bspmv_kernel and the reference, so the
+// result is bit-identical.  The block stream is the only large array: algorithmic bytes = nnzb*(4 + br*bc*es) + small.
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+bspmv_warp_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
+                  const T* __restrict__ c, T* __restrict__ a, int Mb, int br, int bc) {
+  extern __shared__ __align__(16) unsigned char bspmv_smem[];
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int EPL = 16;                                              // 16-byte pieces of a block per lane (<= 32 x 32 fp64)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = bc + 1;                                               // padded row: lane j reads column l of row j conflict-free
+  T* tile = (T*)bspmv_smem + (size_t)warp * (br * ld + bc);
+  T* sc = tile + br * ld;
+  const int nel = br * bc;
+  // (row, column) of this lane's piece t: incremental, no division in the loop (bc % VEC == 0, so a piece never straddles rows)
+  const int step = 32 * VEC, dr = step / bc, dl = step - dr * bc;
+  const int r0 = (lane * VEC) / bc, l0 = lane * VEC - r0 * bc;
+  using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+  auto load_block = [&](int p, V (&x)[EPL], T& cv) {
+    const T* blk = vals + (size_t)p * nel;
+#pragma unroll
+    for (int t = 0; t < EPL; t++) {
+      const int e = (t * 32 + lane) * VEC;
+      if (e < nel) {
+        if constexpr (sizeof(T) == 4) x[t] = tbd::ldg_stream_f4(blk + e);
+        else x[t] = tbd::ldg_stream_d2(blk + e);
+      }
+    }
+    cv = T(0);
+    const T* cr = c + (size_t)__ldg(crd + p) * bc;
+    if (lane < bc) cv = __ldg(cr + lane);                               // bc <= 32 here; wider blocks take the second load below
+  };
+  for (int i = blockIdx.x * WARPS + warp; i < Mb; i += gridDim.x * WARPS) {
+    T acc = T(0);
+    const int p0 = __ldg(pos + i), p1 = __ldg(pos + i + 1);
+    V cur[EPL], nxt[EPL];
+    T ccur = T(0), cnxt = T(0);
+    if (p0 < p1) load_block(p0, cur, ccur);
+    for (int p = p0; p < p1; p++) {
+      if (p + 1 < p1) load_block(p + 1, nxt, cnxt);                     // the next block is in flight while this one is reduced
+      int r = r0, l = l0;
+#pragma unroll
+      for (int t = 0; t < EPL; t++) {
+        if ((t * 32 + lane) * VEC < nel) {
+          T* d = tile + r * ld + l;
+          if constexpr (sizeof(T) == 4) { d[0] = cur[t].x; d[1] = cur[t].y; d[2] = cur[t].z; d[3] = cur[t].w; }
+          else { d[0] = cur[t].x; d[1] = cur[t].y; }
+        }
+        l += dl; r += dr;
+        if (l >= bc) { l -= bc; r++; }
+      }
+      if (lane < bc) sc[lane] = ccur;
+      if (bc > 32) for (int q = 32 + lane; q < bc; q += 32) sc[q] = __ldg(c + (size_t)__ldg(crd + p) * bc + q);
+      __syncwarp();
+      if (lane < br) {
+        const T* row = tile + lane * ld;
+        T tl = T(0);
+        for (int q = 0; q < bc; q++) tl = tl + row[q] * sc[q];
+        acc = acc + tl;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < EPL; t++) cur[t] = nxt[t];
+      ccur = cnxt;
+    }
+    if (lane < br) a[(size_t)i * br + lane] = acc;
+  }
 }
 
 // CTA = one block row x one tile of TK dense columns.  Warp w owns the rows j = w, w + WARPS, ... (RJ accumulators per
@@ -646,6 +718,30 @@ int taco_b200_bspmv_compute(taco_tensor_t* a, taco_tensor_t* A, taco_tensor_t* c
   const long long rows = (long long)Av.Mb * Av.br;
   if (rows > 0) {
     ProfScope ps("bspmv_bcsr");
+    static const int variant = getenv("TACO_B200_BSPMV_VARIANT") ? atoi(getenv("TACO_B200_BSPMV_VARIANT")) : 0;
+    constexpr int WARPS = 4;
+    const size_t smem = (size_t)WARPS * ((size_t)Av.br * (Av.bc + 1) + Av.bc) * es;
+    const bool staged = variant == 0 && Av.br <= 32 && smem <= 96 * 1024 && ((size_t)Av.bc * es) % 16 == 0 &&
+                        (size_t)Av.br * Av.bc * es <= 16 * 32 * 16 && (((uintptr_t)vals.dptr) & 15) == 0;
+    if (staged) {
+      long long ctas = ((long long)Av.Mb + WARPS - 1) / WARPS;
+      const int g = (int)(ctas < (1 << 20) ? ctas : (1 << 20));
+      if (Av.dt == DType::F32) {
+        static bool cfg = false;
+        if (!cfg) { TB_CUDA(cudaFuncSetAttribute(bspmv_warp_kernel<float, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfg = true; }
+        bspmv_warp_kernel<float, WARPS><<<g, WARPS * 32, smem, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<float>(), cin.as<float>(),
+                                                                           aout.as<float>(), Av.Mb, Av.br, Av.bc);
+      } else {
+        static bool cfg = false;
+        if (!cfg) { TB_CUDA(cudaFuncSetAttribute(bspmv_warp_kernel<double, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfg = true; }
+        bspmv_warp_kernel<double, WARPS><<<g, WARPS * 32, smem, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<double>(), cin.as<double>(),
+                                                                            aout.as<double>(), Av.Mb, Av.br, Av.bc);
+      }
+      count_launch(1);
+      TB_CUDA(cudaGetLastError());
+      TB_TRY(aout.commit());
+      return finish_call();
+    }
     const int grid = (int)((rows + 255) / 256);
     if (Av.dt == DType::F32)
       bspmv_kernel<float><<<grid, 256, 0, stream()>>>(pos.as<int>(), crd.as<int>(), vals.as<float>(), cin.as<float>(), aout.as<float>(),

@@ -318,6 +318,8 @@ FULL = {
     "pack": dict(n=1_000_000, nnz=10_000_000, dtype="float64"),
     # blocked SpMM: 1Mi x 1Mi in 32 x 32 blocks, 16 stored blocks per block row, K = 128
     "bspmm": dict(Mb=32768, deg=16, br=32, bc=32, K=128, dtype="float32"),
+    # blocked SpMV, the reference's `bspmv` statement (tests-expr_storage.cpp:939-960), on the same block structure in fp64
+    "bspmv": dict(Mb=32768, deg=16, br=32, bc=32, dtype="float64"),
 }
 
 
@@ -360,6 +362,12 @@ def make(workload, device=None, **over):
         bp, bc, bv = csr_fixed_degree(xp, p["n"], p["n"], p["deg"], SEED0 + 18, dt)
         dims = (p["n"], p["n"]) if workload == "spadd" else (p["n"], p["n"], p["n"])
         return dict(dims=dims, A_pos=ap, A_crd=ac, A_vals=av, B_pos=bp, B_crd=bc, B_vals=bv)
+    if workload == "bspmv":
+        Mb, br, bc = p["Mb"], p["br"], p["bc"]
+        pos, crd, _ = csr_fixed_degree(xp, Mb, Mb, p["deg"], SEED0 + 20, dt)
+        nnzb = Mb * p["deg"]
+        return dict(dims=(Mb, Mb, br, bc), A_pos=pos, A_crd=crd, A_vals=values(xp, xp.arange(nnzb * br * bc), SEED0 + 21, dt),
+                    c=dense(xp, Mb * bc, 1, SEED0 + 23, dt))
     if workload == "bspmm":
         Mb, br, bc = p["Mb"], p["br"], p["bc"]
         pos, crd, _ = csr_fixed_degree(xp, Mb, Mb, p["deg"], SEED0 + 20, dt)

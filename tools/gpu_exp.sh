@@ -22,9 +22,9 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-for v in 4 5 6; do
-echo "== parity TACO_B200_SPMV_VARIANT=$v"; TACO_B200_SPMV_VARIANT=$v timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "spmv" 2>&1 | tail -1
-done
-for v in 0 4 5 6 0 4 6; do run spmv TACO_B200_SPMV_VARIANT=$v; done
-} > gpurun_out/exp_14.txt 2>&1
-cat gpurun_out/exp_14.txt
+timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "bspmv" 2>&1 | tail -2
+run bspmv X=0
+run bspmv TACO_B200_BSPMV_VARIANT=1
+ncuq bspmv bspmv_warp X=0
+} > gpurun_out/exp_15.txt 2>&1
+cat gpurun_out/exp_15.txt

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi > gpurun_out/smi.txt 2>&1; nproc >> gpurun_out/smi.txt; free -g >> gpurun_out/smi.txt
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 ( time timeout 300 python __graft_entry__.py smoke ) > gpurun_out/smoke.log 2>&1
-for wl in ${WORKLOADS:-spmm spmv sddmm mttkrp spadd spgemm bspmm ttv ttm pack}; do
+for wl in ${WORKLOADS:-spmm spmv sddmm mttkrp spadd spgemm bspmm bspmv ttv ttm pack}; do
   ( time timeout 900 python bench.py --workload $wl ) > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
 done
 OURS='regex:^(spmm|spmv|sddmm|csf3|spadd|spgemm|slot_first|scan_|partition|mttkrp|csr_|csf_|bspm|dcsr)'
