@@ -94,8 +94,6 @@ def main():
             inp = dict(dims=np.array([40, 38, 16], np.int32), B_pos=p, B_crd=c, B_vals=v, C=C, D=D)
             out = run_ref("sddmm", inp, sfx, "default")
             cases[f"sddmm_{tag}_{sfx}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
-            if sfx == "f32":
-                continue
             # ---- mttkrp / ttv / ttm (reference GPU test shape 25 x 25 x 30, rank 32) ---------------------------
             Bt = sparse_fill(rng, (25, 25, 30), 0.1, integer, dtype)
             Bt[3] = 0
@@ -190,8 +188,8 @@ def main():
                 inp = dict(dims=np.array(dims, np.int32), vals=v, **{f"c{m}": c for m, c in enumerate(cs)})
                 out = run_ref("pack_" + kind, inp, sfx, "default")
                 cases[f"pack_{kind}_{tag}_{sfx}_{dims[0]}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
-    only = sys.argv[1] if len(sys.argv) > 1 else ""
-    cases = {k: v for k, v in cases.items() if k.startswith(only)}
+    only = sys.argv[1].split(",") if len(sys.argv) > 1 else [""]          # comma-separated name prefixes
+    cases = {k: v for k, v in cases.items() if any(k.startswith(p) for p in only)}
     for name, arrs in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
     print(f"wrote {len(cases)} golden cases to {OUT}")
