@@ -80,3 +80,19 @@ def d3322a():  # :369-386  -> BCSR (pos, crd, blocks[nnzb,2,2]) of the order-4 f
 
 def d32b():   # :358-367
     return np.array([[10.0, 11.0], [20.0, 21.0], [30.0, 31.0]])
+
+
+def rua32_csr():
+    """The CSR storage the reference expects after reading + packing test/data/rua_32.mtx (32 x 32, 126 entries):
+    /root/reference/test/tests-api.cpp:261-300 (APIMatrixStorageTestData "rua_32.mtx", format CSR).  The file's values encode
+    their coordinates, vals = 100 * (row + 1) + (col + 1), so the known answer is reproduced here from pos / crd alone."""
+    pos = np.array([0, 6, 11, 17, 21, 25, 28, 33, 38, 45, 52, 57, 60, 62, 64, 67, 70, 73, 78, 81, 84, 87, 89, 93, 96, 101, 105,
+                    109, 111, 116, 120, 123, 126], np.int32)
+    crd = np.array([0, 1, 2, 3, 6, 25, 0, 1, 8, 20, 27, 1, 2, 5, 7, 8, 28, 2, 3, 4, 11, 2, 4, 22, 26, 0, 5, 15, 2, 6, 13, 20, 30,
+                    0, 7, 11, 16, 26, 6, 8, 9, 12, 18, 22, 26, 0, 9, 10, 20, 22, 24, 26, 1, 10, 14, 17, 28, 5, 11, 23, 10, 12, 2,
+                    13, 1, 14, 19, 3, 15, 21, 3, 15, 16, 5, 9, 17, 19, 29, 0, 18, 25, 7, 15, 19, 2, 20, 31, 10, 21, 1, 16, 20, 22,
+                    11, 23, 25, 5, 14, 17, 23, 24, 12, 17, 21, 25, 4, 23, 25, 26, 8, 27, 2, 4, 26, 28, 31, 11, 16, 22, 29, 12, 13,
+                    30, 23, 27, 31], np.int32)
+    rows = np.repeat(np.arange(32), np.diff(pos))
+    vals = (100.0 * (rows + 1) + (crd + 1)).astype(np.float64)
+    return pos, crd, vals

@@ -62,6 +62,19 @@ def test_kat_mttkrp():
     assert np.array_equal(A, [[0, 80, 0], [180, 0, 0]])
 
 
+def test_kat_parafac_mttkrp2_mttkrp3():
+    # tests-parafac.cpp:157-187 with the factories of test/expr_factory.cpp:100-124: the mode-J / mode-K MTTKRPs over d333a.
+    # Stored in mode orderings {1,0,2} / {2,0,1}, the level arrays ARE the CSF of the permuted tensor, so each is the
+    # standard MTTKRP over that storage order: A(i,r) = B(k,i,l) C(k,r) D(l,r) and A(i,r) = B(k,l,i) C(k,r) D(l,r).
+    a, b, c, v = H.d333a()
+    A2 = oracle.mttkrp(formats.coo_to_csf3(b, a, c, v), H.d33a(), H.d33b(), 3)                  # B'(i,k,l) = B(k,i,l)
+    want2 = np.zeros((3, 3)); want2[0, 1] = 80; want2[2, 1] = 240
+    assert np.array_equal(A2, want2)
+    A3 = oracle.mttkrp(formats.coo_to_csf3(c, a, b, v), H.d33a(), H.d33b(), 3)                  # B''(i,k,l) = B(k,l,i)
+    want3 = np.zeros((3, 3)); want3[0, 1] = 80; want3[1, 1] = 120; want3[2, 1] = 240
+    assert np.array_equal(A3, want3)
+
+
 def test_kat_tensor_vector_mul():
     # tests-expr_storage.cpp:1056-1072: d333a(i,j,k) * d3b(k) == {4,0,12, 0,0,33, 0,24,0}
     t = formats.coo_to_csf3(*H.d333a())
@@ -203,3 +216,14 @@ def test_golden_pack(name):
             assert np.array_equal(got[k], want), k
     # integer-valued cases (with duplicates) are exact in any order; fractional cases have distinct coordinates
     assert np.array_equal(got["A_vals"], outs["A_vals"])
+
+
+def test_kat_pack_rua32():
+    # tests-api.cpp:261-300: the coordinates of rua_32.mtx in file (column-major) order and in a shuffled order both pack to
+    # exactly the CSR arrays the reference's own storage test expects
+    pos, crd, vals = H.rua32_csr()
+    assert vals[0] == 101.0 and vals[5] == 126.0 and vals[-1] == 3232.0 and pos[-1] == crd.size == 126
+    rows = np.repeat(np.arange(32), np.diff(pos)).astype(np.int32)
+    for order in (np.lexsort((rows, crd)), np.random.default_rng(5).permutation(126)):
+        got = oracle.pack("csr", [32, 32], [rows[order], crd[order]], vals[order])
+        assert np.array_equal(got["A2_pos"], pos) and np.array_equal(got["A2_crd"], crd) and np.array_equal(got["A_vals"], vals)

@@ -70,6 +70,12 @@ def test_kat_mttkrp_ttv_ttm():
     t3 = formats.coo_to_csf3(*H.d333a())
     A = G.run("ttv", dict(dims=[3, 3, 3], c=H.d3b(), **t3))
     assert A.tolist() == [4, 0, 12, 0, 0, 33, 0, 24, 0]
+    # tests-parafac.cpp:157-187 (mttkrp2 / mttkrp3: mode-J and mode-K MTTKRP = the standard kernel over the permuted storage)
+    a, b, c, v = H.d333a()
+    A = G.run("mttkrp", dict(dims=[3, 3, 3, 3], C=H.d33a().reshape(-1), D=H.d33b().reshape(-1), **formats.coo_to_csf3(b, a, c, v)))
+    assert A.tolist() == [0, 80, 0, 0, 0, 0, 0, 240, 0]
+    A = G.run("mttkrp", dict(dims=[3, 3, 3, 3], C=H.d33a().reshape(-1), D=H.d33b().reshape(-1), **formats.coo_to_csf3(c, a, b, v)))
+    assert A.tolist() == [0, 80, 0, 0, 120, 0, 0, 240, 0]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -689,6 +695,16 @@ def _run_pack(kind, dims, coords, vals, space):
         return {k: np.array(v) for k, v in _pack_levels(t, kind).items()}
     finally:
         tb.set_result_space("host")
+
+
+@pytest.mark.parametrize("space", SPACES)
+def test_kat_pack_rua32(space):
+    # the reference's storage KAT for test/data/rua_32.mtx (tests-api.cpp:261-300): file order and a shuffled order
+    pos, crd, vals = H.rua32_csr()
+    rows = np.repeat(np.arange(32), np.diff(pos)).astype(np.int32)
+    for order in (np.lexsort((rows, crd)), np.random.default_rng(5).permutation(126)):
+        got = _run_pack("csr", [32, 32], [rows[order].copy(), crd[order].copy()], vals[order].copy(), space)
+        assert np.array_equal(got["A2_pos"], pos) and np.array_equal(got["A2_crd"], crd) and np.array_equal(got["A_vals"], vals)
 
 
 @pytest.mark.parametrize("space", SPACES)
