@@ -660,6 +660,8 @@ int taco_b200_ttv_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* c) 
   TB_TRY(view_dense(c, 1, "c", &cv));
   CsfCall cc;
   TB_TRY(csf_prepare(B, &cc));
+  for (int l = 0; l < 3; l++)
+    if (B->mode_ordering[l] != l) return fail(TACO_B200_ERR_FORMAT, "B must be stored in mode ordering 0,1,2 for this statement");
   TB_TRY(cc.upload());
   if (Av.mode_order[0] != 0) return fail(TACO_B200_ERR_FORMAT, "ttv: A must be row-major");
   if (Av.dim[0] != cc.B.dim[0] || Av.dim[1] != cc.B.dim[1] || cv.dim[0] != cc.B.dim[2])
@@ -689,6 +691,8 @@ int taco_b200_ttm_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C) 
   TB_TRY(view_dense(C, 2, "C", &Cv));
   CsfCall cc;
   TB_TRY(csf_prepare(B, &cc));
+  for (int l = 0; l < 3; l++)
+    if (B->mode_ordering[l] != l) return fail(TACO_B200_ERR_FORMAT, "B must be stored in mode ordering 0,1,2 for this statement");
   TB_TRY(cc.upload());
   if (Av.mode_order[0] != 0 || Av.mode_order[1] != 1 || Cv.mode_order[0] != 0)
     return fail(TACO_B200_ERR_FORMAT, "ttm: A and C must be row-major");

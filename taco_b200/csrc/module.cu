@@ -28,6 +28,7 @@ struct Family {
   const char* formats[4];             // required level formats per tensor, in argument order ("d","ds","sss",...)
   int nargs;
   void* assemble; void* compute; void* evaluate;
+  const char* arg1_ordering = nullptr;   // mode ordering the sparse operand (argument 1) must be stored in; null = identity
 };
 
 #define TB_FAM3(n) (void*)taco_b200_##n##_assemble, (void*)taco_b200_##n##_compute, (void*)taco_b200_##n##_evaluate
@@ -40,6 +41,11 @@ static const Family kFamilies[] = {
     {"spadd",  "T0(a,b)=T1(a,b)+T2(a,b)",             {"ds", "ds", "ds", ""},    3, TB_FAM3(spadd)},
     {"sddmm",  "T0(a,b)=T1(a,b)*T2(a,c)*T3(b,c)",     {"ds", "ds", "dd", "dd"},  4, TB_FAM3(sddmm)},
     {"mttkrp", "T0(a,b)=T1(a,c,d)*T2(c,b)*T3(d,b)",   {"dd", "sss", "dd", "dd"}, 4, TB_FAM3(mttkrp)},
+    // mode-J / mode-K MTTKRP of a CP-ALS sweep (the reference's parafac tests, test/tests-parafac.cpp:157-187, factories
+    // test/expr_factory.cpp:100-124): with B stored in the mode ordering that puts the result's mode first, its level arrays
+    // are the CSF of the permuted tensor and the statement is the standard MTTKRP over the storage order
+    {"mttkrp", "T0(a,b)=T1(c,a,d)*T2(c,b)*T3(d,b)",   {"dd", "sss", "dd", "dd"}, 4, TB_FAM3(mttkrp), "1,0,2"},
+    {"mttkrp", "T0(a,b)=T1(c,d,a)*T2(c,b)*T3(d,b)",   {"dd", "sss", "dd", "dd"}, 4, TB_FAM3(mttkrp), "2,0,1"},
     {"ttv",    "T0(a,b)=T1(a,b,c)*T2(c)",             {"dd", "sss", "d", ""},    3, TB_FAM3(ttv)},
     {"ttm",    "T0(a,b,c)=T1(a,b,d)*T2(d,c)",         {"ddd", "sss", "dd", ""},  3, TB_FAM3(ttm)},
     {"bspmv",  "T0(a,b)=T1(a,c,b,d)*T2(c,d)",         {"dd", "dsdd", "dd", ""},  3, TB_FAM3(bspmv)},
@@ -165,6 +171,10 @@ taco_b200_module_t* taco_b200_module_open(const char* expr, const char* formats,
       std::string lv = it == fm.end() ? std::string(strlen(f.formats[a]), 'd') : it->second.first;
       if (it == fm.end() && lv != f.formats[a]) ok = false;        // unlisted tensors are dense
       else if (lv != f.formats[a]) ok = false;
+      if (ok && a == 1 && f.arg1_ordering) {       // this family needs the sparse operand in a specific (non-identity) ordering
+        if (it == fm.end() || it->second.second != f.arg1_ordering) ok = false;
+        continue;
+      }
       if (ok && it != fm.end() && !it->second.second.empty()) {
         // only the spmm result may carry a non-identity mode ordering (the reference GPU test's column-major C)
         std::string ident;

@@ -46,10 +46,15 @@ int view_csr(const taco_tensor_t* t, const char* name, CsrView* v) {
 int view_csf3(const taco_tensor_t* t, const char* name, Csf3View* v) {
   if (!t) return fail(TACO_B200_ERR_ARG, "%s: NULL tensor", name);
   if (t->order != 3) return fail(TACO_B200_ERR_FORMAT, "%s: expected an order-3 CSF tensor", name);
+  bool seen[3] = {false, false, false};
   for (int l = 0; l < 3; l++) {
-    if (t->mode_types[l] != taco_mode_sparse || t->mode_ordering[l] != l)
-      return fail(TACO_B200_ERR_FORMAT, "%s: expected CSF ({Compressed x3}, mode ordering 0,1,2)", name);
-    v->dim[l] = t->dimensions[l];
+    // any mode ordering: level l stores mode mode_ordering[l]; the kernels work in STORAGE order (the module classifier
+    // only pairs a permuted ordering with the statement whose result mode comes first in storage, module.cu)
+    const int m = t->mode_ordering[l];
+    if (t->mode_types[l] != taco_mode_sparse || m < 0 || m > 2 || seen[m])
+      return fail(TACO_B200_ERR_FORMAT, "%s: expected CSF ({Compressed x3}, a permutation as mode ordering)", name);
+    seen[m] = true;
+    v->dim[l] = t->dimensions[m];
     v->pos[l] = (int32_t*)t->indices[l][0];
     v->crd[l] = (int32_t*)t->indices[l][1];
     if (!v->pos[l]) return fail(TACO_B200_ERR_ARG, "%s: level %d has no pos array", name, l);

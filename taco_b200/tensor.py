@@ -251,11 +251,12 @@ def makeDense(name, dims, vals, ordering=None):
     return t
 
 
-def makeCSF3(name, dims, arrays):
-    """arrays: dict with B1_pos,B1_crd,B2_pos,B2_crd,B3_pos,B3_crd,B_vals (taco_b200.formats.coo_to_csf3 layout)."""
+def makeCSF3(name, dims, arrays, ordering=None):
+    """arrays: dict with B1_pos,B1_crd,B2_pos,B2_crd,B3_pos,B3_crd,B_vals (taco_b200.formats.coo_to_csf3 layout).
+    `dims` are indexed by mode; with a mode `ordering` (e.g. [1, 0, 2]) level l of the arrays stores mode ordering[l]."""
     vals = arrays["B_vals"]
     dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
-    t = Tensor(name, dims, CSF3, dt)
+    t = Tensor(name, dims, CSF3 if ordering is None else Format([compressed] * 3, ordering), dt)
     for l in range(3):
         t.set_level(l, arrays[f"B{l + 1}_pos"], arrays[f"B{l + 1}_crd"])
     t.set_vals(vals)

@@ -52,6 +52,8 @@ CASES = [
     ("C(i,j) = A(i,j) + B(i,j)", "A:ds,B:ds,C:ds", "spadd"),
     ("A(i,j) = B(i,j) * C(i,k) * D(j,k)", "A:ds,B:ds,C:dd,D:dd", "sddmm"),
     ("A(i,j) = B(i,k,l) * C(k,j) * D(l,j)", "B:sss", "mttkrp"),
+    ("A(i,j) = B(k,i,l) * C(k,j) * D(l,j)", "B:sss:1,0,2", "mttkrp"),       # parafac mode-J MTTKRP over the permuted storage
+    ("A(i,j) = B(k,l,i) * C(k,j) * D(l,j)", "B:sss:2,0,1", "mttkrp"),       # mode-K
     ("A(i,j) = B(i,j,k) * c(k)", "B:sss", "ttv"),
     ("A(i,j,l) = B(i,j,k) * C(k,l)", "B:sss", "ttm"),
     ("a(i,j) = B(i,k,j,l) * c(k,l)", "B:dsdd", "bspmv"),                 # the reference's blocked SpMV statement
@@ -77,6 +79,8 @@ def test_module_classifier(expr, fmts, family):
     ("C(i,j) = A(i,j) - B(i,j)", "A:ds,B:ds,C:ds"),
     ("C(i,k) = A(i,j) * B(j,k)", "A:ds,B:dd:1,0,C:dd"),
     ("a = B(i,j)", "B:ds"),
+    ("A(i,j) = B(k,i,l) * C(k,j) * D(l,j)", "B:sss"),                       # mode-J MTTKRP needs B stored with mode 1 first
+    ("A(i,j) = B(i,j,k) * c(k)", "B:sss:1,0,2"),
 ])
 def test_module_refuses_everything_else(expr, fmts):
     assert not _lib.lib.taco_b200_module_open(expr.encode(), fmts.encode(), b"f64")

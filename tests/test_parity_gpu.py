@@ -330,6 +330,42 @@ def test_oracle_mttkrp_host_pipeline(dtype, R, monkeypatch):
     assert np.array_equal(A3[short], A[short])
 
 
+@pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_mttkrp_mode_j_and_k_over_permuted_storage(space, mode):
+    # the other two MTTKRPs of a CP-ALS sweep (tests-parafac.cpp:157-187): B stored with the result's mode first
+    rng = np.random.default_rng(40 + mode)
+    dims, R = (37, 23, 29), 8
+    n = 4000
+    c = [rng.integers(0, d, n) for d in dims]
+    flat = np.ravel_multi_index(c, dims)
+    _, first = np.unique(flat, return_index=True)
+    c = [x[first] for x in c]
+    v = np.floor(rng.random(first.size) * 5 + 1)
+    ordering = [1, 0, 2] if mode == 1 else [2, 0, 1]
+    t = formats.coo_to_csf3(c[ordering[0]], c[ordering[1]], c[ordering[2]], v)           # CSF of the permuted tensor
+    Cm = np.floor(rng.random((dims[ordering[1]], R)) * 4)
+    Dm = np.floor(rng.random((dims[ordering[2]], R)) * 4)
+    dense = np.zeros(dims)
+    dense[tuple(c)] = v
+    want = np.einsum("kil,kr,lr->ir" if mode == 1 else "kli,kr,lr->ir", dense, Cm, Dm)
+    arrs = place(dict(C=Cm.reshape(-1), D=Dm.reshape(-1), **t), space)
+    tb.set_result_space("device" if space == "device" else "host")
+    try:
+        B = tb.makeCSF3("B", list(dims), arrs, ordering)
+        Ct = tb.makeDense("C", [dims[ordering[1]], R], arrs["C"])
+        Dt = tb.makeDense("D", [dims[ordering[2]], R], arrs["D"])
+        A = tb.Tensor("A", [dims[mode], R], tb.Format([tb.dense, tb.dense]), np.float64)
+        expr = "A(i,j) = B(k,i,l) * C(k,j) * D(l,j)" if mode == 1 else "A(i,j) = B(k,l,i) * C(k,j) * D(l,j)"
+        tb.compile(expr, A, B, Ct, Dt)(A, B, Ct, Dt)
+        if space == "device":
+            tb.synchronize()
+        got = G.to_host(A.vals()).reshape(dims[mode], R)
+    finally:
+        tb.set_result_space("host")
+    assert np.array_equal(got, want)
+
+
 def test_oracle_ttv_ttm():
     w = synth.make("mttkrp", None, I=3_000, K=500, L=800, nnz=200_000, R=16, dtype="float64")
     I, K, L, R = w["dims"]
