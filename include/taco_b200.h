@@ -122,6 +122,12 @@ int taco_b200_sddmm_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* 
 int taco_b200_sddmm_compute (taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 int taco_b200_sddmm_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
 
+/* A(i,k) = B(i,k) * C(i,j) * D(j,k)   B CSR; A, C, D dense row-major, D indexed (contraction, column): the statement of the
+ * reference's sddmmGPU test (test/tests-scheduling-eval.cpp:1360-1418, dense result); replaces scheduleSDDMMGPU (:270-287) */
+int taco_b200_sddmm_dense_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
+int taco_b200_sddmm_dense_compute (taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
+int taco_b200_sddmm_dense_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
+
 /* A(i,j) = B(i,k,l) * C(k,j) * D(l,j)   B CSF {Compressed x3}; A, C, D dense row-major
  * replaces scheduleMTTKRPGPU (:327-342) */
 int taco_b200_mttkrp_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D);
@@ -208,6 +214,7 @@ int _shim_taco_b200_spmv_assemble(void** p);   int _shim_taco_b200_spmv_compute(
 int _shim_taco_b200_spmm_assemble(void** p);   int _shim_taco_b200_spmm_compute(void** p);   int _shim_taco_b200_spmm_evaluate(void** p);
 int _shim_taco_b200_spmm_dcsr_assemble(void** p); int _shim_taco_b200_spmm_dcsr_compute(void** p); int _shim_taco_b200_spmm_dcsr_evaluate(void** p);
 int _shim_taco_b200_sddmm_assemble(void** p);  int _shim_taco_b200_sddmm_compute(void** p);  int _shim_taco_b200_sddmm_evaluate(void** p);
+int _shim_taco_b200_sddmm_dense_assemble(void** p); int _shim_taco_b200_sddmm_dense_compute(void** p); int _shim_taco_b200_sddmm_dense_evaluate(void** p);
 int _shim_taco_b200_mttkrp_assemble(void** p); int _shim_taco_b200_mttkrp_compute(void** p); int _shim_taco_b200_mttkrp_evaluate(void** p);
 int _shim_taco_b200_ttv_assemble(void** p);    int _shim_taco_b200_ttv_compute(void** p);    int _shim_taco_b200_ttv_evaluate(void** p);
 int _shim_taco_b200_ttm_assemble(void** p);    int _shim_taco_b200_ttm_compute(void** p);    int _shim_taco_b200_ttm_evaluate(void** p);

@@ -87,6 +87,20 @@ def spmm_dcsr(n, pos1, crd1, pos2, crd2, vals, B):
     return C
 
 
+def sddmm_dense(pos, crd, bvals, C, D):
+    """A(i,k) = B(i,k) * C(i,j) * D(j,k) with a dense result; C is (n, J), D is (J, m).  Returns A (n, m)."""
+    pos, crd = _i32(pos), _i32(crd)
+    bvals = np.ascontiguousarray(bvals)
+    C = np.ascontiguousarray(C, dtype=bvals.dtype)
+    D = np.ascontiguousarray(D, dtype=bvals.dtype)
+    n, J = C.shape
+    m = D.shape[1]
+    A = np.empty((n, m), dtype=bvals.dtype)
+    getattr(lib(), "oracle_sddmm_dense_" + _sfx(bvals.dtype))(ctypes.c_int32(n), ctypes.c_int32(m), ctypes.c_int32(J), _p(pos),
+                                                              _p(crd), _p(bvals), _p(C), _p(D), _p(A))
+    return A
+
+
 def sddmm(pos, crd, bvals, C, D):
     """returns (A_pos, A_crd, A_vals)"""
     pos, crd = _i32(pos), _i32(crd)

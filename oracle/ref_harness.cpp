@@ -10,7 +10,7 @@
 //
 // usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
 //                         [--threads N] [--reps R]
-//   kernel in {spmv, spmm, spmm_dcsr, sddmm, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm, pack_csr, pack_dcsr, pack_csf3}
+//   kernel in {spmv, spmm, spmm_dcsr, sddmm, sddmm_dense, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm, pack_csr, pack_dcsr, pack_csf3}
 // Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
 //
 // Input arrays (tbin.h): dims (int32), and per kernel
@@ -220,6 +220,26 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
         tbin_array a; strcpy(a.name, "A_pos"); a.dtype = 0; a.count = n + 1; a.data = pos; outs.push_back(a);
         strcpy(a.name, "A_crd"); a.dtype = 0; a.count = pos[n]; a.data = crd; outs.push_back(a);
         strcpy(a.name, "A_vals"); a.dtype = tbin_dtype<T>(); a.count = pos[n]; a.data = vals; outs.push_back(a);
+        tbin_write(outPath, outs.data(), outs.size());
+      }
+    } else if (kernel == "sddmm_dense") {
+      // the statement of the reference's sddmmGPU test (test/tests-scheduling-eval.cpp:1360-1418): dense result, D indexed
+      // (contraction, column):  A(i,k) = B(i,k) * C(i,j) * D(j,k);  dims = I K J
+      int n = dims[0], m = dims[1], J = dims[2];
+      Tensor<T> B = attachCSR<T>("B", {n, m}, in, "B");
+      Tensor<T> C = attachDense<T>("C", {n, J}, (T*)need(in, "C")->data);
+      Tensor<T> D = attachDense<T>("D", {J, m}, (T*)need(in, "D")->data);
+      Tensor<T> A("A", {n, m}, Format({Dense, Dense}));
+      A(i, k) = B(i, k) * C(i, j) * D(j, k);
+      double t0 = now_ms(); A.compile();
+      double t1 = now_ms(); dumpSource(A); A.assemble();
+      double t2 = now_ms(); A.compute();
+      double t3 = now_ms();
+      if (rep == 0) tm.compile = t1 - t0;
+      tm.assemble.push_back(t2 - t1); tm.compute.push_back(t3 - t2);
+      if (last) {
+        tbin_array a; strcpy(a.name, "A"); a.dtype = tbin_dtype<T>(); a.count = (uint64_t)n * m;
+        a.data = A.getStorage().getValues().getData(); outs.push_back(a);
         tbin_write(outPath, outs.data(), outs.size());
       }
     } else if (kernel == "mttkrp" || kernel == "ttv" || kernel == "ttm") {

@@ -79,6 +79,22 @@ static int cmp_i32(const void* a, const void* b) { /* reference prelude `cmp`, s
       }                                                                                                                \
     }                                                                                                                  \
   }                                                                                                                    \
+  /* A(i,k) = B(i,k) * C(i,j) * D(j,k), A dense, D indexed (contraction, column): the statement of the reference's      \
+     sddmmGPU test (test/tests-scheduling-eval.cpp:1360-1418).  Generated code (dumped through oracle/ref_harness.cpp):    \
+     zero A; for i, for j (ascending), for kB in row i of B: A[i,k] = A[i,k] + (B[kB] * C[i,j]) * D[j,k]. */              \
+  void oracle_sddmm_dense_##S(int32_t n, int32_t m, int32_t J, const int32_t* pos, const int32_t* crd, const T* Bvals,  \
+                              const T* C, const T* D, T* A) {                                                          \
+    _Pragma("omp parallel for schedule(static)") for (int64_t q = 0; q < (int64_t)n * m; q++) A[q] = 0;                \
+    _Pragma("omp parallel for schedule(static)") for (int32_t i = 0; i < n; i++) {                                     \
+      for (int32_t j = 0; j < J; j++) {                                                                                \
+        const T cij = C[(size_t)i * J + j];                                                                            \
+        for (int32_t p = pos[i]; p < pos[i + 1]; p++) {                                                                \
+          const size_t a = (size_t)i * m + crd[p];                                                                     \
+          A[a] = A[a] + (Bvals[p] * cij) * D[(size_t)j * m + crd[p]];                                                  \
+        }                                                                                                              \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }                                                                                                                    \
   /* A(i,j) = B(i,j) * C(i,k) * D(j,k), A and B CSR (A has B's structure), C, D row-major.                       \
      tkA += (B[p] * C[i,k]) * D[j,k], k ascending, scalar accumulator; A_vals[jA++] = tkA. */                     \
   void oracle_sddmm_##S(int32_t n, int32_t K, const int32_t* pos, const int32_t* crd, const T* Bvals, const T* C, \

@@ -29,6 +29,8 @@ int  oracle_get_max_threads(void);
                        T* C);                                                                                      \
   void oracle_spmm_dcsr_##S(int32_t n, int32_t K, const int32_t* pos1, const int32_t* crd1, const int32_t* pos2,      \
                             const int32_t* crd2, const T* vals, const T* B, T* C);                                    \
+  void oracle_sddmm_dense_##S(int32_t n, int32_t m, int32_t J, const int32_t* pos, const int32_t* crd, const T* Bvals,  \
+                              const T* C, const T* D, T* A);                                                           \
   void oracle_sddmm_##S(int32_t n, int32_t K, const int32_t* pos, const int32_t* crd, const T* Bvals, const T* C, \
                         const T* D, T* Avals);                                                                     \
   void oracle_mttkrp_##S(int32_t R, const int32_t* B1_pos, const int32_t* B1_crd, const int32_t* B2_pos,          \

@@ -47,8 +47,8 @@ if not os.path.exists(LIB_PATH):
 
 lib = ctypes.CDLL(LIB_PATH)
 
-FAMILIES = ("spmv", "spmm", "spmm_dcsr", "sddmm", "mttkrp", "ttv", "ttm", "spadd", "spgemm", "bspmv", "bspmm")
-NARGS = {"spmv": 3, "spmm": 3, "spmm_dcsr": 3, "sddmm": 4, "mttkrp": 4, "ttv": 3, "ttm": 3, "spadd": 3, "spgemm": 3, "bspmv": 3,
+FAMILIES = ("spmv", "spmm", "spmm_dcsr", "sddmm", "sddmm_dense", "mttkrp", "ttv", "ttm", "spadd", "spgemm", "bspmv", "bspmm")
+NARGS = {"spmv": 3, "spmm": 3, "spmm_dcsr": 3, "sddmm": 4, "sddmm_dense": 4, "mttkrp": 4, "ttv": 3, "ttm": 3, "spadd": 3, "spgemm": 3, "bspmv": 3,
          "bspmm": 3}
 PHASES = ("assemble", "compute", "evaluate")
 

@@ -40,6 +40,7 @@ static const Family kFamilies[] = {
     {"spgemm", "T0(a,b)=T1(a,c)*T2(c,b)",             {"ds", "ds", "ds", ""},    3, TB_FAM3(spgemm)},
     {"spadd",  "T0(a,b)=T1(a,b)+T2(a,b)",             {"ds", "ds", "ds", ""},    3, TB_FAM3(spadd)},
     {"sddmm",  "T0(a,b)=T1(a,b)*T2(a,c)*T3(b,c)",     {"ds", "ds", "dd", "dd"},  4, TB_FAM3(sddmm)},
+    {"sddmm_dense", "T0(a,b)=T1(a,b)*T2(a,c)*T3(c,b)", {"dd", "ds", "dd", "dd"},  4, TB_FAM3(sddmm_dense)},
     {"mttkrp", "T0(a,b)=T1(a,c,d)*T2(c,b)*T3(d,b)",   {"dd", "sss", "dd", "dd"}, 4, TB_FAM3(mttkrp)},
     // mode-J / mode-K MTTKRP of a CP-ALS sweep (the reference's parafac tests, test/tests-parafac.cpp:157-187, factories
     // test/expr_factory.cpp:100-124): with B stored in the mode ordering that puts the result's mode first, its level arrays
@@ -275,7 +276,7 @@ const char* taco_b200_module_stub_source(taco_b200_module_t* m) {
   }
 #define TB_SHIMS3(n) TB_SHIM3(n, assemble) TB_SHIM3(n, compute) TB_SHIM3(n, evaluate)
 #define TB_SHIMS4(n) TB_SHIM4(n, assemble) TB_SHIM4(n, compute) TB_SHIM4(n, evaluate)
-TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS3(spmm_dcsr) TB_SHIMS4(sddmm) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm) TB_SHIMS3(bspmv) TB_SHIMS3(bspmm)
+TB_SHIMS3(spmv) TB_SHIMS3(spmm) TB_SHIMS3(spmm_dcsr) TB_SHIMS4(sddmm) TB_SHIMS4(sddmm_dense) TB_SHIMS4(mttkrp) TB_SHIMS3(ttv) TB_SHIMS3(ttm) TB_SHIMS3(spadd) TB_SHIMS3(spgemm) TB_SHIMS3(bspmv) TB_SHIMS3(bspmm)
 
 }  // extern "C"
 

@@ -319,11 +319,124 @@ static int clone_to_result(const void* src, size_t bytes, void** out) {
   return TACO_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dense-result form, the statement of the reference's sddmmGPU test (test/tests-scheduling-eval.cpp:1360-1418, schedule
+// scheduleSDDMMGPU :270-287):  A(i,k) = B(i,k) * C(i,j) * D(j,k)  with A {Dense,Dense} and D stored (contraction, column).
+// D is transposed once on the device (tiled through shared memory) so that the sampled dot products read contiguous rows
+// and the tuned CSR kernel runs on it; its values are then scattered into the zero-filled dense result.
+// Reference order per entry: j ascending, (B*C)*D -- the kernel's lane-parallel dot product stays within the tolerance.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int rows, int cols) {
+  __shared__ T tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < rows && bx + tx < cols) tile[r][tx] = __ldg(in + (size_t)(by + r) * cols + bx + tx);
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < cols && by + tx < rows) out[(size_t)(bx + r) * rows + by + tx] = tile[tx][r];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int* __restrict__ pos, const int* __restrict__ crd,
+                                                           const T* __restrict__ vals, T* __restrict__ A, int rows, int cols) {
+  const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int p1 = __ldg(pos + warp + 1);
+  for (int p = __ldg(pos + warp) + lane; p < p1; p += 32) A[(size_t)warp * cols + __ldg(crd + p)] = vals[p];
+}
+
+template <typename T>
+static int sddmm_dense_run(const int* pos, const int* crd, const T* bvals, const T* C, const T* D, T* A, int rows, int cols, int J,
+                           int nnz) {
+  TB_CUDA(cudaMemsetAsync(A, 0, sizeof(T) * (size_t)rows * cols, stream()));
+  count_launch(1);
+  if (nnz == 0 || rows == 0) return TACO_B200_OK;
+  void *Dt = nullptr, *vals = nullptr;
+  TB_TRY(scratch_alloc(&Dt, sizeof(T) * (size_t)J * cols));
+  TB_TRY(scratch_alloc(&vals, sizeof(T) * (size_t)nnz));
+  if (J > 0) {
+    dim3 grid((cols + 31) / 32, (J + 31) / 32);
+    transpose_kernel<T><<<grid, 256, 0, stream()>>>(D, (T*)Dt, J, cols);       // D (J x cols) -> Dt (cols x J)
+    count_launch(1);
+  }
+  int rc = sddmm_launch<T>(pos, crd, bvals, C, (const T*)Dt, (T*)vals, rows, J, nnz);
+  if (rc == TACO_B200_OK) {
+    const size_t threads = (size_t)rows * 32;
+    scatter_rows_kernel<T><<<(unsigned)((threads + 255) / 256), 256, 0, stream()>>>(pos, crd, (const T*)vals, A, rows, cols);
+    count_launch(1);
+  }
+  scratch_free(Dt);
+  scratch_free(vals);
+  TB_TRY(rc);
+  TB_CUDA(cudaGetLastError());
+  return TACO_B200_OK;
+}
+
+struct SddmmDenseViews { DenseView A, C, D; CsrView B; };
+static int sddmm_dense_views(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D, SddmmDenseViews* v) {
+  TB_TRY(ensure_init());
+  TB_TRY(view_dense(A, 2, "A", &v->A));
+  TB_TRY(view_csr(B, "B", &v->B));
+  TB_TRY(view_dense(C, 2, "C", &v->C));
+  TB_TRY(view_dense(D, 2, "D", &v->D));
+  if (v->A.mode_order[0] != 0 || v->C.mode_order[0] != 0 || v->D.mode_order[0] != 0)
+    return fail(TACO_B200_ERR_FORMAT, "sddmm_dense: A, C and D must be row-major {Dense,Dense}");
+  if (v->A.dim[0] != v->B.rows || v->A.dim[1] != v->B.cols || v->C.dim[0] != v->B.rows || v->D.dim[1] != v->B.cols ||
+      v->C.dim[1] != v->D.dim[0])
+    return fail(TACO_B200_ERR_ARG, "sddmm_dense: dimension mismatch A[%d x %d] = B[%d x %d] * C[%d x %d] * D[%d x %d]", v->A.dim[0],
+                v->A.dim[1], v->B.rows, v->B.cols, v->C.dim[0], v->C.dim[1], v->D.dim[0], v->D.dim[1]);
+  if (v->A.dt != v->B.dt || v->C.dt != v->B.dt || v->D.dt != v->B.dt)
+    return fail(TACO_B200_ERR_FORMAT, "sddmm_dense: mixed component types");
+  return TACO_B200_OK;
+}
+
 }  // namespace tb
 
 using namespace tb;
 
 extern "C" {
+
+int taco_b200_sddmm_dense_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  SddmmDenseViews v;
+  TB_TRY(sddmm_dense_views(A, B, C, D, &v));
+  void* p = result_alloc(v.A.count() * dsize(v.A.dt));
+  if (!p) return fail(TACO_B200_ERR_ALLOC, "sddmm_dense: cannot allocate result");
+  A->vals = (uint8_t*)p;
+  return TACO_B200_OK;
+}
+
+int taco_b200_sddmm_dense_compute(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  SddmmDenseViews v;
+  TB_TRY(sddmm_dense_views(A, B, C, D, &v));
+  if (!v.A.vals) return fail(TACO_B200_ERR_ARG, "NULL result array (call assemble first)");
+  int32_t nnz = 0;
+  TB_TRY(csr_nnz(v.B, B->vals_size, &nnz));
+  if (nnz < 0) return fail(TACO_B200_ERR_ARG, "sddmm_dense: negative nnz");
+  const int J = v.C.dim[1];
+  const size_t es = dsize(v.B.dt);
+  In pos, crd, bvals, cin, din; Out aout;
+  TB_TRY(pos.acquire(v.B.pos, sizeof(int32_t) * ((size_t)v.B.rows + 1)));
+  TB_TRY(crd.acquire(v.B.crd ? (void*)v.B.crd : (void*)v.B.pos, sizeof(int32_t) * (size_t)nnz));
+  TB_TRY(bvals.acquire(v.B.vals ? v.B.vals : (void*)v.B.pos, es * (size_t)nnz));
+  TB_TRY(cin.acquire(v.C.vals, es * (size_t)v.B.rows * J));
+  TB_TRY(din.acquire(v.D.vals, es * (size_t)J * v.B.cols));
+  TB_TRY(aout.acquire(v.A.vals, es * v.A.count()));
+  ProfScope ps("sddmm_dense");
+  if (v.B.dt == DType::F32)
+    TB_TRY(sddmm_dense_run<float>(pos.as<int>(), crd.as<int>(), bvals.as<float>(), cin.as<float>(), din.as<float>(), aout.as<float>(),
+                                  v.B.rows, v.B.cols, J, nnz));
+  else
+    TB_TRY(sddmm_dense_run<double>(pos.as<int>(), crd.as<int>(), bvals.as<double>(), cin.as<double>(), din.as<double>(),
+                                   aout.as<double>(), v.B.rows, v.B.cols, J, nnz));
+  TB_TRY(aout.commit());
+  return finish_call();
+}
+
+int taco_b200_sddmm_dense_evaluate(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
+  TB_TRY(taco_b200_sddmm_dense_assemble(A, B, C, D));
+  return taco_b200_sddmm_dense_compute(A, B, C, D);
+}
 
 int taco_b200_sddmm_assemble(taco_tensor_t* A, taco_tensor_t* B, taco_tensor_t* C, taco_tensor_t* D) {
   SddmmViews v;

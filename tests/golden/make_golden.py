@@ -168,6 +168,21 @@ def main():
                 inp = dict(dims=np.array([n, m, K], np.int32), B=B, **d)
                 out = run_ref("spmm_dcsr", inp, sfx, "default")
                 cases[f"dcsr_spmm_{tag}_{sfx}_{n}x{K}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
+    # ---- SDDMM with a dense result and D indexed (contraction, column): the reference's sddmmGPU statement
+    #      (tests-scheduling-eval.cpp:1360-1418; its shape 102 x 103, contraction 128, sparsity .3) ---------------------
+    for integer in (True, False):
+        tag = "int" if integer else "frac"
+        for dtype, sfx in ((np.float64, "f64"), (np.float32, "f32")):
+            rng = np.random.default_rng(44001 + (0 if integer else 1) + (0 if sfx == "f64" else 7))
+            for (n, m, J, sp) in ((102, 103, 128, 0.3), (61, 40, 7, 0.15)):
+                Bm = sparse_fill(rng, (n, m), sp, integer, dtype)
+                Bm[5] = 0
+                p, c, v = formats.csr_from_dense(Bm)
+                C = dense_fill(rng, (n, J), integer, dtype)
+                D = dense_fill(rng, (J, m), integer, dtype)
+                inp = dict(dims=np.array([n, m, J], np.int32), B_pos=p, B_crd=c, B_vals=v, C=C, D=D)
+                out = run_ref("sddmm_dense", inp, sfx, "default")
+                cases[f"densesddmm_{tag}_{sfx}_{n}"] = dict(inp, **{"out_" + k: a for k, a in out.items()})
     # ---- pack(): COO (unsorted; integer-valued cases contain duplicates) -> CSR / DCSR / CSF through the reference's
     #      insert() + pack() (src/tensor.cpp:295-463) ------------------------------------------------------------------
     for integer in (True, False):

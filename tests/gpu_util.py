@@ -14,6 +14,7 @@ EXPR = {
     "spmm": "C(i,k) = A(i,j) * B(j,k)",
     "spmm_dcsr": "C(i,k) = A(i,j) * B(j,k)",
     "sddmm": "A(i,j) = B(i,j) * C(i,k) * D(j,k)",
+    "sddmm_dense": "A(i,k) = B(i,k) * C(i,j) * D(j,k)",
     "mttkrp": "A(i,j) = B(i,k,l) * C(k,j) * D(l,j)",
     "ttv": "A(i,j) = B(i,j,k) * c(k)",
     "ttm": "A(i,j,l) = B(i,j,k) * C(k,l)",
@@ -97,6 +98,13 @@ def build(family, w, colmajor_c=False):
         C = tb.makeDense("C", [d[0], d[2]], w["C"])
         D = tb.makeDense("D", [d[1], d[2]], w["D"])
         A = tb.Tensor("A", d[:2], tb.CSR, dt)
+        ts = [A, B, C, D]
+    elif family == "sddmm_dense":          # dims = (I, K, J): A, B are I x K, C is I x J, D is J x K
+        dt = np_dtype(w["B_vals"])
+        B = tb.makeCSR("B", d[:2], w["B_pos"], w["B_crd"], w["B_vals"])
+        C = tb.makeDense("C", [d[0], d[2]], w["C"])
+        D = tb.makeDense("D", [d[2], d[1]], w["D"])
+        A = tb.Tensor("A", d[:2], tb.Format([tb.dense, tb.dense]), dt)
         ts = [A, B, C, D]
     elif family in ("mttkrp", "ttv", "ttm"):
         dt = np_dtype(w["B_vals"])

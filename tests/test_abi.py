@@ -51,6 +51,7 @@ CASES = [
     ("C(i,k) = A(i,j) * B(j,k)", "A:ds,B:ds,C:ds", "spgemm"),
     ("C(i,j) = A(i,j) + B(i,j)", "A:ds,B:ds,C:ds", "spadd"),
     ("A(i,j) = B(i,j) * C(i,k) * D(j,k)", "A:ds,B:ds,C:dd,D:dd", "sddmm"),
+    ("A(i,k) = B(i,k) * C(i,j) * D(j,k)", "A:dd,B:ds,C:dd,D:dd", "sddmm_dense"),   # the reference's sddmmGPU statement
     ("A(i,j) = B(i,k,l) * C(k,j) * D(l,j)", "B:sss", "mttkrp"),
     ("A(i,j) = B(k,i,l) * C(k,j) * D(l,j)", "B:sss:1,0,2", "mttkrp"),       # parafac mode-J MTTKRP over the permuted storage
     ("A(i,j) = B(k,l,i) * C(k,j) * D(l,j)", "B:sss:2,0,1", "mttkrp"),       # mode-K

@@ -136,6 +136,14 @@ def test_golden_spmm_dcsr(name):
     assert np.array_equal(oracle.spmm(pos, g["A2_crd"], g["A_vals"], g["B"].reshape(m, K)), C)
 
 
+@pytest.mark.parametrize("name", H.golden_cases("densesddmm"))
+def test_golden_sddmm_dense(name):
+    g = H.load_golden(name)
+    n, m, J = [int(x) for x in g["dims"]]
+    A = oracle.sddmm_dense(g["B_pos"], g["B_crd"], g["B_vals"], g["C"].reshape(n, J), g["D"].reshape(J, m))
+    _check_vals(name, A.reshape(-1), g["out_A"])
+
+
 @pytest.mark.parametrize("name", H.golden_cases("sddmm"))
 def test_golden_sddmm(name):
     g = H.load_golden(name)

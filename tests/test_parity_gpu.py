@@ -143,6 +143,18 @@ def test_oracle_spmm_dcsr(space, keep):
 
 
 @pytest.mark.parametrize("space", SPACES)
+@pytest.mark.parametrize("name", H.golden_cases("densesddmm"))
+def test_golden_sddmm_dense(name, space):
+    # the reference's sddmmGPU statement: dense result, D indexed (contraction, column)
+    g = H.load_golden(name)
+    A = G.run("sddmm_dense", place(_inputs(g), space))
+    if "_int_" in name:
+        assert np.array_equal(A, g["out_A"])
+    else:
+        H.assert_close(A, g["out_A"], g["B_vals"].dtype, scale=float(np.abs(g["out_A"]).max()))
+
+
+@pytest.mark.parametrize("space", SPACES)
 @pytest.mark.parametrize("name", H.golden_cases("sddmm"))
 def test_golden_sddmm(name, space):
     g = H.load_golden(name)
