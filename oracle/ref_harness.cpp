@@ -35,6 +35,9 @@
 #include "taco/index_notation/index_notation.h"
 #include "taco/storage/index.h"
 #include "taco/storage/array.h"
+#include "taco/lower/lower.h"
+#include "taco/codegen/module.h"
+#include "taco/cuda.h"
 #include "tbin.h"
 
 using namespace taco;
@@ -439,7 +442,65 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
   return 0;
 }
 
+// `taco_ref_harness emit_cuda <spmv|spmm> <outdir/> <prefix>`: print the CUDA source the REFERENCE generates for its own GPU
+// schedule of the statement (scheduleSpMVGPU / scheduleSpMMGPU, test/tests-scheduling-eval.cpp:193-209, 249-268, same
+// directives and parameters) through the reference's CodeGen_CUDA (Module::compileToSource).  No GPU or CUDA build is
+// needed to GENERATE the text; oracle/Makefile compiles it with nvcc for sm_100a as the "recompiled reference kernel"
+// comparator (tools/ref_cuda_bench.cu).  Output goes to oracle/_ref only.
+template <typename T>
+static int emit_cuda(const std::string& which, const std::string& dir, const std::string& prefix) {
+  set_CUDA_codegen_enabled(true);
+  IndexVar i("i"), j("j"), k("k");
+  const int WARP = 32;
+  IndexStmt stmt;
+  if (which == "spmv") {
+    Tensor<T> A("A", {1024, 1024}, CSR), x("x", {1024}, Format({Dense})), y("y", {1024}, Format({Dense}));
+    IndexExpr pre = A(i, j) * x(j);
+    y(i) = pre;
+    stmt = y.getAssignment().concretize();
+    const int NNZ_PER_THREAD = 8, BLOCK = 256;
+    IndexVar f("f"), fpos("fpos"), fpos1("fpos1"), fpos2("fpos2"), block("block"), warp("warp"), thread("thread"),
+        thread_nz("thread_nz"), thread_nz_pre("thread_nz_pre");
+    TensorVar precomputed("precomputed", Type(type<T>(), {Dimension(thread_nz)}), taco::dense);
+    stmt = stmt.fuse(i, j, f).pos(f, fpos, A(i, j)).split(fpos, block, fpos1, NNZ_PER_THREAD * BLOCK)
+               .split(fpos1, warp, fpos2, NNZ_PER_THREAD * WARP).split(fpos2, thread, thread_nz, NNZ_PER_THREAD)
+               .reorder({block, warp, thread, thread_nz}).precompute(pre, thread_nz, thread_nz_pre, precomputed)
+               .unroll(thread_nz_pre, NNZ_PER_THREAD)
+               .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
+  } else if (which == "spmm") {
+    Tensor<T> A("A", {1024, 1024}, CSR), B("B", {1024, 128}, Format({Dense, Dense})), C("C", {1024, 128}, Format({Dense, Dense}));
+    C(i, k) = A(i, j) * B(j, k);
+    stmt = C.getAssignment().concretize();
+    const int NNZ_PER_WARP = 8, BLOCK = 256;
+    IndexVar f("f"), fpos("fpos"), block("block"), fpos1("fpos1"), warp("warp"), nnz("nnz"), dvu("dense_val_unbounded"),
+        dense_val("dense_val"), thread("thread");
+    stmt = stmt.reorder({i, j, k}).fuse(i, j, f).pos(f, fpos, A(i, j)).split(fpos, block, fpos1, NNZ_PER_WARP * (BLOCK / WARP))
+               .split(fpos1, warp, nnz, NNZ_PER_WARP).split(k, dvu, thread, WARP).reorder({block, warp, thread, dvu, nnz})
+               .bound(dvu, dense_val, 4, BoundType::MaxExact)
+               .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
+  } else {
+    std::cerr << "emit_cuda: spmv | spmm" << std::endl;
+    return 2;
+  }
+  ir::Module module;
+  module.addFunction(lower(stmt, "compute", false, true));
+  module.compileToSource(dir, prefix);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 5 && std::string(argv[1]) == "emit_cuda") {
+    try {
+      return std::string(argv[2]) == "spmm" ? emit_cuda<float>(argv[2], argv[3], argv[4]) : emit_cuda<double>(argv[2], argv[3], argv[4]);
+    } catch (const TacoException& e) {
+      std::cerr << "TacoException: " << e.what() << std::endl;
+      return 3;
+    }
+  }
   if (argc < 4) {
     std::cerr << "usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]"
                  " [--threads N] [--reps R]" << std::endl;

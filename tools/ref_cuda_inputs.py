@@ -1,0 +1,12 @@
+"""Write the sparse operand of the C1 (SpMV) and C2 (SpMM) bench workloads as tbin files for tools/ref_cuda_bench.cu."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from taco_b200 import synth, tbin
+out = sys.argv[1] if len(sys.argv) > 1 else "/dev/shm"
+for wl in ("spmv", "spmm"):
+    w = synth.make(wl, "cuda")
+    h = {k: (np.array(w[k][:2], np.int32) if k == "dims" else w[k].cpu().numpy()) for k in ("dims", "A_pos", "A_crd", "A_vals")}
+    tbin.write(os.path.join(out, f"ref_{wl}.tbin"), h)
+    print(wl, h["dims"], h["A_crd"].shape, h["A_vals"].dtype)
