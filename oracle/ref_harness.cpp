@@ -482,8 +482,23 @@ static int emit_cuda(const std::string& which, const std::string& dir, const std
                .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
                .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
                .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
+  } else if (which == "mttkrp") {           // scheduleMTTKRPGPU, tests-scheduling-eval.cpp:327-342 (rank 32 = one warp of columns)
+    IndexVar l("l");
+    Tensor<T> B("B", {64, 64, 64}, Format({Sparse, Sparse, Sparse})), C("C", {64, 32}, Format({Dense, Dense})),
+        D("D", {64, 32}, Format({Dense, Dense})), A("A", {64, 32}, Format({Dense, Dense}));
+    A(i, j) = B(i, k, l) * C(k, j) * D(l, j);
+    stmt = A.getAssignment().concretize();
+    const int NNZ_PER_WARP = 16, BLOCK = 256;
+    IndexVar kl("kl"), f("f"), fpos("fpos"), block("block"), fpos1("fpos1"), warp("warp"), nnz("nnz"), dvu("dense_val_unbounded"),
+        dense_val("dense_val"), thread("thread");
+    stmt = stmt.reorder({i, k, l, j}).fuse(k, l, kl).fuse(i, kl, f).pos(f, fpos, B(i, k, l))
+               .split(fpos, block, fpos1, NNZ_PER_WARP * (BLOCK / WARP)).split(fpos1, warp, nnz, NNZ_PER_WARP)
+               .split(j, dvu, thread, WARP).bound(dvu, dense_val, 1, BoundType::MaxExact).reorder({block, warp, dense_val, thread, nnz})
+               .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
   } else {
-    std::cerr << "emit_cuda: spmv | spmm" << std::endl;
+    std::cerr << "emit_cuda: spmv | spmm | mttkrp" << std::endl;
     return 2;
   }
   ir::Module module;

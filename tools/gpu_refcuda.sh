@@ -1,14 +1,16 @@
 #!/bin/bash
 # the reference's own generated CUDA (recompiled for sm_100a) on the bench operands: whole-call times + ncu kernel times
+# usage: tools/gpu_refcuda.sh "spmv spmm" | "mttkrp"
 mkdir -p gpurun_out
+KS=${1:-"spmv spmm"}
 {
-timeout 300 python tools/ref_cuda_inputs.py /dev/shm
-for k in spmv spmm; do
+if [ "$KS" = "mttkrp" ]; then timeout 600 python tools/ref_cuda_inputs.py /dev/shm mttkrp | tail -1; else timeout 300 python tools/ref_cuda_inputs.py /dev/shm; fi
+for k in $KS; do
   echo "== reference-generated CUDA $k: compute() wall time per call"
-  timeout 300 oracle/_ref/ref_cuda_$k /dev/shm/ref_$k.tbin 3
+  timeout 600 oracle/_ref/ref_cuda_$k /dev/shm/ref_$k.tbin 2
   echo "== reference-generated CUDA $k: kernel times (ncu)"
-  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6 oracle/_ref/ref_cuda_$k /dev/shm/ref_$k.tbin 1 2>&1 \
+  timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 8 oracle/_ref/ref_cuda_$k /dev/shm/ref_$k.tbin 1 2>&1 \
      | grep -E "computeDeviceKernel|taco_binarySearch|gpu__time|dram__bytes" | head -40
 done
-} > gpurun_out/refcuda.txt 2>&1
-cat gpurun_out/refcuda.txt
+} > gpurun_out/refcuda_$(echo $KS | tr ' ' '_').txt 2>&1
+cat gpurun_out/refcuda_*.txt | tail -40

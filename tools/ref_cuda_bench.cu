@@ -4,6 +4,7 @@
 // structs themselves, in cudaMallocManaged memory.  Test infrastructure: the generated text lives only under oracle/_ref/gen.
 //   ref_cuda_spmv <A.tbin>   y(i) = A(i,j) * x(j)      fp64   (scheduleSpMVGPU)
 //   ref_cuda_spmm <A.tbin>   C(i,k) = A(i,j) * B(j,k)  fp32, K = 128 (scheduleSpMMGPU)
+//   ref_cuda_mttkrp <B.tbin> A(i,j) = B(i,k,l) * C(k,j) * D(l,j)  fp64, rank 32 (scheduleMTTKRPGPU)
 // Prints whole-call wall times of compute(); kernel-only times come from running this binary under
 // `ncu --metrics gpu__time_duration.sum`.
 #include <chrono>
@@ -19,6 +20,7 @@ typedef float val_t;
 #else
 typedef double val_t;
 #endif
+// (REF_MTTKRP is fp64 as well)
 
 template <typename T>
 static T* managed(size_t n) {
@@ -44,6 +46,51 @@ static taco_tensor_t* make_tensor(int order, const int* dims, const taco_mode_t*
   return t;
 }
 
+template <typename T>
+static T* managed_copy(tbin_array* a) {
+  T* p = managed<T>(a->count);
+  memcpy(p, a->data, sizeof(T) * a->count);
+  free(a->data); a->data = nullptr;
+  return p;
+}
+
+#ifdef REF_MTTKRP
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: %s <B.tbin> [reps]\n", argv[0]); return 2; }
+  const int reps = argc > 2 ? atoi(argv[2]) : 2;
+  tbin_file f;
+  if (tbin_read(argv[1], &f) != 0) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+  const int* dims = (const int*)tbin_get(&f, "dims")->data;          // I K L R
+  const int I = dims[0], K = dims[1], L = dims[2], R = 32;
+  const taco_mode_t sss[3] = {taco_mode_sparse, taco_mode_sparse, taco_mode_sparse}, dd[2] = {taco_mode_dense, taco_mode_dense};
+  const int bd[3] = {I, K, L}, cd[2] = {K, R}, ddm[2] = {L, R}, ad[2] = {I, R};
+  taco_tensor_t *B = make_tensor(3, bd, sss), *C = make_tensor(2, cd, dd), *D = make_tensor(2, ddm, dd), *A = make_tensor(2, ad, dd);
+  const char* pn[3] = {"B1_pos", "B2_pos", "B3_pos"};
+  const char* cn[3] = {"B1_crd", "B2_crd", "B3_crd"};
+  for (int l = 0; l < 3; l++) {
+    B->indices[l][0] = (uint8_t*)managed_copy<int32_t>(tbin_get(&f, pn[l]));
+    B->indices[l][1] = (uint8_t*)managed_copy<int32_t>(tbin_get(&f, cn[l]));
+  }
+  const size_t nnz = tbin_get(&f, "B_vals")->count;
+  B->vals = (uint8_t*)managed_copy<double>(tbin_get(&f, "B_vals"));
+  double *c = managed<double>((size_t)K * R), *d = managed<double>((size_t)L * R);
+  for (size_t q = 0; q < (size_t)K * R; q++) c[q] = (double)((q * 2654435761u >> 22) & 1023) / 1024;
+  for (size_t q = 0; q < (size_t)L * R; q++) d[q] = (double)((q * 40503u >> 6) & 1023) / 1024;
+  C->vals = (uint8_t*)c; D->vals = (uint8_t*)d;
+  A->vals = (uint8_t*)managed<double>((size_t)I * R);
+  const double flops = 3.0 * nnz * R;
+  for (int r = 0; r < reps + 1; r++) {
+    auto t0 = std::chrono::steady_clock::now();
+    compute(A, B, C, D);
+    cudaDeviceSynchronize();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"call\": %d, \"compute_wall_ms\": %.3f, \"gflops\": %.2f}\n", r, ms, flops / ms / 1e6);
+    fflush(stdout);
+  }
+  double s = 0; for (int q = 0; q < 1000; q++) s += ((double*)A->vals)[(size_t)q * R]; printf("checksum %.6g\n", s);
+  return 0;
+}
+#else
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: %s <A.tbin> [reps]\n", argv[0]); return 2; }
   const int reps = argc > 2 ? atoi(argv[2]) : 3;
@@ -96,3 +143,4 @@ int main(int argc, char** argv) {
 #endif
   return 0;
 }
+#endif
