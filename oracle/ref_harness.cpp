@@ -497,8 +497,40 @@ static int emit_cuda(const std::string& which, const std::string& dir, const std
                .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
                .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
                .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
+  } else if (which == "ttv") {              // scheduleTTVGPU, tests-scheduling-eval.cpp:308-325
+    Tensor<T> B("B", {64, 64, 64}, Format({Sparse, Sparse, Sparse})), c("c", {64}, Format({Dense})), A("A", {64, 64}, Format({Dense, Dense}));
+    IndexExpr pre = B(i, j, k) * c(k);
+    A(i, j) = pre;
+    stmt = A.getAssignment().concretize();
+    const int NNZ_PER_WARP = 8 * 32, BLOCK = 256;
+    IndexVar jk("jk"), f("f"), fpos("fpos"), block("block"), fpos1("fpos1"), warp("warp"), fpos2("fpos2"), thread("thread"),
+        thread_nz("thread_nz"), thread_nz_pre("thread_nz_pre");
+    TensorVar precomputed("precomputed", Type(type<T>(), {Dimension(thread_nz)}), taco::dense);
+    stmt = stmt.fuse(j, k, jk).fuse(i, jk, f).pos(f, fpos, B(i, j, k)).split(fpos, block, fpos1, NNZ_PER_WARP * (BLOCK / WARP))
+               .split(fpos1, warp, fpos2, NNZ_PER_WARP).split(fpos2, thread, thread_nz, NNZ_PER_WARP / WARP)
+               .reorder({block, warp, thread, thread_nz}).precompute(pre, thread_nz, thread_nz_pre, precomputed)
+               .unroll(thread_nz_pre, NNZ_PER_WARP / WARP)
+               .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
+  } else if (which == "ttm") {              // scheduleTTMGPU, tests-scheduling-eval.cpp:289-306, CO_FACTOR = 1 (32 result columns)
+    IndexVar l("l");
+    Tensor<T> B("B", {64, 64, 64}, Format({Sparse, Sparse, Sparse})), C("C", {64, 32}, Format({Dense, Dense})),
+        A("A", {64, 64, 32}, Format({Dense, Dense, Dense}));
+    A(i, j, l) = B(i, j, k) * C(k, l);
+    stmt = A.getAssignment().concretize();
+    const int NNZ_PER_WARP = 8 * 32, BLOCK = 256, CO_FACTOR = 1;
+    IndexVar jk("jk"), f("f"), fpos("fpos"), block("block"), fpos1("fpos1"), warp("warp"), nnz("nnz"), dvu("dense_val_unbounded"),
+        dense_val("dense_val"), thread("thread");
+    stmt = stmt.reorder({i, j, k, l}).fuse(j, k, jk).fuse(i, jk, f).pos(f, fpos, B(i, j, k))
+               .split(fpos, block, fpos1, NNZ_PER_WARP * (BLOCK / WARP)).split(fpos1, warp, nnz, NNZ_PER_WARP)
+               .split(l, dvu, thread, WARP).bound(dvu, dense_val, CO_FACTOR, BoundType::MaxExact)
+               .reorder({block, warp, nnz, thread, dense_val}).unroll(dense_val, CO_FACTOR)
+               .parallelize(block, ParallelUnit::GPUBlock, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(warp, ParallelUnit::GPUWarp, OutputRaceStrategy::IgnoreRaces)
+               .parallelize(thread, ParallelUnit::GPUThread, OutputRaceStrategy::Atomics);
   } else {
-    std::cerr << "emit_cuda: spmv | spmm | mttkrp" << std::endl;
+    std::cerr << "emit_cuda: spmv | spmm | mttkrp | ttv | ttm" << std::endl;
     return 2;
   }
   ir::Module module;

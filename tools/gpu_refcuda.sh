@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 KS=${1:-"spmv spmm"}
 {
-if [ "$KS" = "mttkrp" ]; then timeout 600 python tools/ref_cuda_inputs.py /dev/shm mttkrp | tail -1; else timeout 300 python tools/ref_cuda_inputs.py /dev/shm; fi
+if [ "$KS" = "spmv spmm" ]; then timeout 300 python tools/ref_cuda_inputs.py /dev/shm; else timeout 600 python tools/ref_cuda_inputs.py /dev/shm $KS; fi
 for k in $KS; do
   echo "== reference-generated CUDA $k: compute() wall time per call"
   timeout 600 oracle/_ref/ref_cuda_$k /dev/shm/ref_$k.tbin 2

@@ -54,7 +54,7 @@ static T* managed_copy(tbin_array* a) {
   return p;
 }
 
-#ifdef REF_MTTKRP
+#if defined(REF_MTTKRP) || defined(REF_TTV) || defined(REF_TTM)
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: %s <B.tbin> [reps]\n", argv[0]); return 2; }
   const int reps = argc > 2 ? atoi(argv[2]) : 2;
@@ -63,8 +63,20 @@ int main(int argc, char** argv) {
   const int* dims = (const int*)tbin_get(&f, "dims")->data;          // I K L R
   const int I = dims[0], K = dims[1], L = dims[2], R = 32;
   const taco_mode_t sss[3] = {taco_mode_sparse, taco_mode_sparse, taco_mode_sparse}, dd[2] = {taco_mode_dense, taco_mode_dense};
-  const int bd[3] = {I, K, L}, cd[2] = {K, R}, ddm[2] = {L, R}, ad[2] = {I, R};
-  taco_tensor_t *B = make_tensor(3, bd, sss), *C = make_tensor(2, cd, dd), *D = make_tensor(2, ddm, dd), *A = make_tensor(2, ad, dd);
+  const int bd[3] = {I, K, L};
+  taco_tensor_t* B = make_tensor(3, bd, sss);
+#if defined(REF_MTTKRP)
+  const int cd[2] = {K, R}, ddm[2] = {L, R}, ad[2] = {I, R};
+  taco_tensor_t *C = make_tensor(2, cd, dd), *D = make_tensor(2, ddm, dd), *A = make_tensor(2, ad, dd);
+#elif defined(REF_TTV)
+  const taco_mode_t d1[1] = {taco_mode_dense};
+  const int cd[1] = {L}, ad[2] = {I, K};
+  taco_tensor_t *C = make_tensor(1, cd, d1), *A = make_tensor(2, ad, dd);
+#else
+  const taco_mode_t ddd[3] = {taco_mode_dense, taco_mode_dense, taco_mode_dense};
+  const int cd[2] = {L, R}, ad[3] = {I, K, R};
+  taco_tensor_t *C = make_tensor(2, cd, dd), *A = make_tensor(3, ad, ddd);
+#endif
   const char* pn[3] = {"B1_pos", "B2_pos", "B3_pos"};
   const char* cn[3] = {"B1_crd", "B2_crd", "B3_crd"};
   for (int l = 0; l < 3; l++) {
@@ -73,15 +85,33 @@ int main(int argc, char** argv) {
   }
   const size_t nnz = tbin_get(&f, "B_vals")->count;
   B->vals = (uint8_t*)managed_copy<double>(tbin_get(&f, "B_vals"));
+#if defined(REF_MTTKRP)
   double *c = managed<double>((size_t)K * R), *d = managed<double>((size_t)L * R);
   for (size_t q = 0; q < (size_t)K * R; q++) c[q] = (double)((q * 2654435761u >> 22) & 1023) / 1024;
   for (size_t q = 0; q < (size_t)L * R; q++) d[q] = (double)((q * 40503u >> 6) & 1023) / 1024;
   C->vals = (uint8_t*)c; D->vals = (uint8_t*)d;
   A->vals = (uint8_t*)managed<double>((size_t)I * R);
   const double flops = 3.0 * nnz * R;
+#elif defined(REF_TTV)
+  double* c = managed<double>((size_t)L);
+  for (size_t q = 0; q < (size_t)L; q++) c[q] = (double)((q * 2654435761u >> 22) & 1023) / 1024;
+  C->vals = (uint8_t*)c;
+  A->vals = (uint8_t*)managed<double>((size_t)I * K);
+  const double flops = 2.0 * nnz;
+#else
+  double* c = managed<double>((size_t)L * R);
+  for (size_t q = 0; q < (size_t)L * R; q++) c[q] = (double)((q * 2654435761u >> 22) & 1023) / 1024;
+  C->vals = (uint8_t*)c;
+  A->vals = (uint8_t*)managed<double>((size_t)I * K * R);
+  const double flops = 2.0 * nnz * R;
+#endif
   for (int r = 0; r < reps + 1; r++) {
     auto t0 = std::chrono::steady_clock::now();
+#if defined(REF_MTTKRP)
     compute(A, B, C, D);
+#else
+    compute(A, B, C);
+#endif
     cudaDeviceSynchronize();
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     printf("{\"call\": %d, \"compute_wall_ms\": %.3f, \"gflops\": %.2f}\n", r, ms, flops / ms / 1e6);
