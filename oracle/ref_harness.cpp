@@ -9,7 +9,7 @@
 // zero-copy (makeCSR, include/taco/tensor.h:774-797; Index/ModeIndex for CSF, include/taco/storage/index.h:20-75).
 //
 // usage: taco_ref_harness <kernel> <in.tbin> <out.tbin> [--dtype f64|f32] [--schedule default|cpu]
-//                         [--threads N] [--reps R]
+//                         [--threads N] [--reps R] [--no-out 1]
 //   kernel in {spmv, spmm, spmm_dcsr, sddmm, sddmm_dense, mttkrp, spadd, spgemm, ttv, ttm, bspmv, bspmm, pack_csr, pack_dcsr, pack_csf3}
 // Prints one JSON line: {"kernel":..., "assemble_ms":[...], "compute_ms":[...], "compile_ms":..., "threads":N}
 //
@@ -143,6 +143,7 @@ static void dumpSource(const TensorBase& t) {
 }
 
 struct Times { std::vector<double> assemble, compute; double compile = 0; };
+static bool g_no_out = false;   // --no-out 1: timing runs skip writing the result file
 
 // Schedules follow the reference's own CPU schedules, test/tests-scheduling-eval.cpp:41-184.
 template <typename T>
@@ -154,7 +155,7 @@ static int run(const std::string& kernel, tbin_file& in, const char* outPath, co
   bool tuned = (schedule == "cpu");
 
   for (int rep = 0; rep < reps; rep++) {
-    bool last = (rep == reps - 1);
+    bool last = (rep == reps - 1) && !g_no_out;
     outs.clear();
     if (kernel == "spmv") {
       int n = dims[0], m = dims[1];
@@ -561,6 +562,7 @@ int main(int argc, char** argv) {
     else if (key == "--schedule") schedule = val;
     else if (key == "--threads") threads = atoi(val.c_str());
     else if (key == "--reps") reps = atoi(val.c_str());
+    else if (key == "--no-out") g_no_out = atoi(val.c_str()) != 0;
   }
   tbin_file in;
   if (tbin_read(argv[2], &in) != 0) { std::cerr << "cannot read " << argv[2] << std::endl; return 2; }

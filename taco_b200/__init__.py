@@ -4,7 +4,7 @@ The product is libtaco_b200.so (include/taco_b200.h, sources in taco_b200/csrc).
 host-side mirror of the reference's tensor/kernel interface used by tests and bench.py; it contains no compute
 fallback -- importing it fails if the library has not been built.
 """
-from . import formats, synth, tbin  # noqa: F401  (pure-python helpers, no GPU needed)
+from . import formats  # noqa: F401  (pure-python helpers, no GPU needed)
 from ._lib import LIB_PATH, TacoError  # noqa: F401
 from .tensor import (BCSR, CSF3, CSR, DCSR, Dense, Format, Kernel, Sparse, Tensor, compile, compressed, dense, launch_count,  # noqa: F401
                      makeBCSR, makeCSF3, makeCSR, makeDCSR, makeDense, pack, partition_pos, pinned_empty, pinned_free, set_result_space,

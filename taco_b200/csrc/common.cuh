@@ -30,7 +30,7 @@ int fail(int code, const char* fmt, ...);   // records thread-local message, ret
 // ---------------------------------------------------------------------------------------------------------
 int ensure_init();
 cudaStream_t stream();
-cudaStream_t aux_stream(int i);                        // 0: upload, 1: download (host-operand pipelines)
+cudaStream_t aux_stream(int i);                        // 0: upload, 1: download (host-operand pipelines), 2: side compute stream
 bool is_resident(const void* host_ptr, size_t bytes);  // registered with taco_b200_make_resident
 int num_sms();
 void count_launch(int n = 1);

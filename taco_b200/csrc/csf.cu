@@ -513,7 +513,7 @@ static int mttkrp_compute_pipelined(CsfCall& cc, const T* C, const T* D, T* host
 // spmv.cu / spmm.cu
 int spmv_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* x, void* y, int rows, int nnz,
                 const unsigned* ymap, const char* prof_name);
-int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int K, int nnz,
+int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int cols, int K, int nnz,
                 const unsigned* rowmap, const char* prof_name);
 
 // fiber_cell[f] = B1_crd[s] * Kdim + B2_crd[f] for every fiber f of slice s: where the fiber's result lives in the dense
@@ -552,7 +552,7 @@ static int ttm_launch(CsfCall& cc, const T* C, T* A, size_t a_count, int R, int 
     void* cell = nullptr;
     TB_TRY(fiber_cells(cc, Kdim, &cell));
     const int rc = spmm_mapped(sizeof(T) == 8 ? DType::F64 : DType::F32, cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, A,
-                               cc.nfib, R, cc.nnz, (const unsigned*)cell, "ttm_csf");
+                               cc.nfib, cc.B.dim[2], R, cc.nnz, (const unsigned*)cell, "ttm_csf");
     scratch_free(cell);
     count_launch(1);
     TB_TRY(rc);
@@ -579,8 +579,7 @@ template <typename T>
 static int ttv_launch(CsfCall& cc, const T* c, T* A, size_t a_count, int Kdim) {
   TB_CUDA(cudaMemsetAsync(A, 0, a_count * sizeof(T), stream()));
   static const int variant = getenv("TACO_B200_TTV_VARIANT") ? atoi(getenv("TACO_B200_TTV_VARIANT")) : 0;
-  const bool aligned = ((((uintptr_t)cc.c3.dptr) | ((uintptr_t)cc.vals.dptr)) & 15) == 0;
-  if (cc.nfib > 0 && variant == 0 && aligned && a_count <= 0xFFFFFFFFull && cc.nnz <= INT32_MAX - 65536) {
+  if (cc.nfib > 0 && variant == 0 && a_count <= 0xFFFFFFFFull && cc.nnz <= INT32_MAX - 65536) {
     void* cell = nullptr;
     TB_TRY(fiber_cells(cc, Kdim, &cell));
     count_launch(1);

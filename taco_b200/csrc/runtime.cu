@@ -51,7 +51,7 @@ struct Context {
   int sms = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t cur_stream = nullptr;
-  cudaStream_t aux[2] = {nullptr, nullptr};   // upload / download streams of the host-operand pipelines
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // upload / download streams of the host-operand pipelines, side compute stream
   int space = TACO_B200_SPACE_HOST;
   long launches = 0;
   std::unordered_map<const void*, Resident> resident;

@@ -5,33 +5,39 @@
 //   reference: grid ceil(nnz/64), warp gets 8 nnz, lane <-> k%32, the binary search is redone for each of 4
 //              `dense_val` passes, ONE GLOBAL atomicAdd PER (nnz, k) (8.2 G atomics at config C2), host-serial
 //              zeroing of the 2 GB result in managed memory, K <= 128 only.
-//   here     : nnz-balanced ROW-ALIGNED slots: warp w owns the rows whose first nonzero lies in [w*W,(w+1)*W)
-//              (one binary search per slot in a pre-pass, the search of taco_binarySearchBeforeBlock,
-//              /root/reference/src/codegen/codegen_cuda.cpp:110-125).  A lane owns 16 bytes of the dense row
-//              (4 fp32 / 2 fp64 columns), so every gathered row of B is one fully coalesced 512-byte warp load
-//              (ld.global.nc, L1-allocating: hot columns of a power-law matrix stay in L1/L2), 8 independent row
-//              gathers are in flight per warp, accumulators live in registers and each C row is written exactly
-//              once with a streaming 128-bit store -- no zero-fill pass, no atomics.  Empty rows are zeroed by
-//              their owner.  Only "hub" rows (longer than LONG nonzeros) are split across the slots they span;
-//              their partial sums are combined with vector red.global.add into a pre-zeroed row.
-//              Inside a row the products are accumulated in ascending position order with separate multiply and
-//              add -- the reference C kernel's order (Appendix A.1) -- so non-hub rows are bit-identical to it.
+//   here     : two cooperating schedules, no atomics anywhere, every C row written exactly once.
+//   (1) rows of at most LONG nonzeros -- nnz-balanced ROW-ALIGNED slots: warp w owns the rows whose first nonzero lies
+//       in [w*W,(w+1)*W) (one binary search per slot in a pre-pass, the search of taco_binarySearchBeforeBlock,
+//       /root/reference/src/codegen/codegen_cuda.cpp:110-125).  A lane owns 16 bytes of the dense row (4 fp32 / 2 fp64
+//       columns), so every gathered row of B is one fully coalesced 512-byte warp load, accumulators live in registers
+//       and each C row is stored once with a streaming 128-bit store.  Empty rows are zeroed by their owner.  Inside a
+//       row the products are accumulated in ascending position order with separate multiply and add -- the reference
+//       C kernel's order (Appendix A.1) -- so these rows are bit-identical to it.
+//   (2) long rows (> LONG nonzeros; 45 % of the nonzeros of the power-law config C2) -- COLUMN-PANEL schedule.  The
+//       columns are cut into P panels; a long row's nonzeros inside one panel form work items of at most CAP
+//       nonzeros.  Items are laid out panel-major and handed out in that order by a ticket, so at any moment the
+//       whole chip gathers rows of B from ONE panel (B panel = cols/P rows, L2-resident): every B row a long row needs
+//       is fetched from HBM about once instead of once per reference.  Each item stores its partial row sum; a combine
+//       kernel adds the partials of a row in ascending column (= position) order.  The plan (long-row list, panel cuts by
+//       binary search, item offsets by prefix sum) is rebuilt on the device every call: no cached inspector state, no
+//       host read-back, results independent of scheduling (run-to-run deterministic, within 1e-5 / 1e-12 of the
+//       sequential order).
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*K*(cols + rows).
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace tb {
 
 constexpr int SPMM_W = 64;          // nonzeros per slot (one warp)
-constexpr int SPMM_LONG = 512;      // rows longer than this are split across slots
 
 template <typename T, int VEC> struct Frag { T v[VEC]; };
 
-// A lane's 16-byte piece of a gathered B row.  L1-allocating (hot columns of a power-law matrix are re-used inside an
-// SM) and tagged evict_last in L2: the dense operand is the only array with re-use, the CSR arrays and C stream by.
+// A lane's 16-byte piece of a gathered B row (L1-allocating: hot columns of a power-law matrix are re-used inside an SM).
 template <typename T, int VEC>
-__device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p, uint64_t keep) {
+__device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p) {
   Frag<T, VEC> f;
   if constexpr (VEC == 4 && sizeof(T) == 4) {
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -48,8 +54,7 @@ __device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p, uint64
 }
 
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f,
-                                          uint64_t strm) {
+__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f) {
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) C[(size_t)(col + e) * rows + row] = f.v[e];
@@ -69,48 +74,15 @@ __device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col
   }
 }
 
-template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void red_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f) {
-  if constexpr (COLMAJOR) {
-#pragma unroll
-    for (int e = 0; e < VEC; e++) atomicAdd(C + (size_t)(col + e) * rows + row, f.v[e]);
-  } else {
-    T* p = C + row * K + col;
-    if constexpr (VEC == 4 && sizeof(T) == 4) {
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
-                   "f"(f.v[3]) : "memory");
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; e++) atomicAdd(p + e, f.v[e]);
-    }
-  }
-}
-
 // A launch covers the row range [r0, r1) = nonzeros [p0, p1) (the whole matrix, or one row chunk of the host-operand
 // pipeline below).
 struct SpmmRange { int r0, r1, p0, p1; };
 
 // Pre-pass: slot_rows[w] = first row whose first nonzero is at or after p0 + w*W; slot_rows[nslots] = r1.
-// Also zeroes the C row of every hub row (done by the slot in which the hub row's first slot boundary falls).
-// RMAP (here and in spmm_csr_kernel): result row r is stored at row rowmap[r] of C (TTM: the rows are the fibers of a CSF
-// tensor, rowmap their cells in the dense (i,j) plane, csf.cu); the unmapped instantiations are unchanged by the flag.
-template <typename T, bool COLMAJOR, bool RMAP = false>
-__global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg, int rows, int nslots, int K,
-                                      int* __restrict__ slot_rows, T* __restrict__ C, const unsigned* __restrict__ rowmap = nullptr) {
+__global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg, int nslots, int* __restrict__ slot_rows) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > nslots) return;
-  if (w == nslots) { slot_rows[w] = rg.r1; return; }
-  int lo = rg.p0 + w * SPMM_W;
-  slot_rows[w] = tbd::search_first_ge(pos, rg.r0, rg.r1, lo);
-  if (lo < rg.p1) {
-    int i = tbd::search_last_le(pos, rg.r0, rg.r1, lo);      // the row that contains nonzero `lo`
-    int s = __ldg(pos + i), e = __ldg(pos + i + 1);
-    if (e - s > SPMM_LONG && lo - s < SPMM_W) {
-      const size_t orow = RMAP ? (size_t)__ldg(rowmap + i) : (size_t)i;
-      if constexpr (COLMAJOR) { for (int k = 0; k < K; k++) C[(size_t)k * rows + orow] = T(0); }
-      else { for (int k = 0; k < K; k++) C[orow * K + k] = T(0); }
-    }
-  }
+  slot_rows[w] = (w == nslots) ? rg.r1 : tbd::search_first_ge(pos, rg.r0, rg.r1, rg.p0 + w * SPMM_W);
 }
 
 // acc += sum over nonzeros p in [a,b) of vals[p] * B[crd[p], col..col+VEC), in ascending p with separate multiply and
@@ -118,8 +90,7 @@ __global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg,
 // broadcast by shuffle; U independent B-row gathers are in flight per warp.
 template <typename T, int VEC, int U>
 __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __restrict__ crd, const T* __restrict__ vals,
-                                                const T* __restrict__ Bcol, int K, int a, int b, int lane, uint64_t keep,
-                                                uint64_t strm) {
+                                                const T* __restrict__ Bcol, int K, int a, int b, int lane) {
   for (int pb = a; pb < b; pb += 32) {
     const int cnt = min(32, b - pb);
     int my_c = 0;
@@ -134,7 +105,7 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const int c = __shfl_sync(0xffffffffu, my_c, j + u);
-        bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K, keep);
+        bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -150,7 +121,7 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
       for (int u = 0; u < U - 1; u++) {
         if (u < rem) {
           const int c = __shfl_sync(0xffffffffu, my_c, j + u);
-          bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K, keep);
+          bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
         }
       }
 #pragma unroll
@@ -165,382 +136,376 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
   }
 }
 
+// Schedule (1): the rows of at most `long_thresh` nonzeros.  RMAP: result row r is stored at row rowmap[r] of C (TTM: the
+// rows are the fibers of a CSF tensor, rowmap their cells in the dense (i,j) plane, csf.cu).
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                const int* __restrict__ slot_rows, const unsigned* __restrict__ rowmap = nullptr) {
+                const int* __restrict__ slot_rows, int long_thresh, const unsigned* __restrict__ rowmap = nullptr) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
-  const int nnz = rg.p1;
-  const int lo = rg.p0 + w * SPMM_W, hi = min(lo + SPMM_W, nnz);
-  // the slot's own window of crd / vals is needed a few dependent loads from now: pull it into L2 meanwhile
+  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
+  if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
+  const int lo = rg.p0 + w * SPMM_W;
+  // the slot's own window of crd / vals is needed two dependent loads from now: pull it into L2 meanwhile
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
   else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
-  const uint64_t keep = 0, strm = 0;     // (L2 eviction-policy hints measured no change in hit rate at C2: not used)
   const int col = (blockIdx.y * 32 + lane) * VEC;
   const bool active = col < K;
   const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
-  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
-
-  // Work items of the slot, all run through ONE copy of the accumulate loop:
-  //   group -1 (optional): the piece [lo, min(hi,e)) of a hub row that started in an earlier slot (added atomically),
-  //   groups 0..: the rows this slot owns, 32 at a time -- empty rows are zeroed, every other row is accumulated in
-  //   registers and written exactly once; a hub row (always the last row a slot owns) contributes its first piece
-  //   atomically into the row the pre-pass zeroed.
-  int tail_e = 0;
-  bool tail = false;
-  if (R0 > rg.r0 && lo < nnz) {
-    const int s = __ldg(pos + R0 - 1);
-    tail_e = __ldg(pos + R0);
-    tail = tail_e > lo && tail_e - s > SPMM_LONG;
-  }
-  for (int rb = tail ? R0 - 32 : R0; rb < R1; rb += 32) {
-    const bool is_tail = rb < R0;
+  for (int rb = R0; rb < R1; rb += 32) {
     const int r = rb + lane;
-    const bool valid = !is_tail && r < R1;
-    int s = valid ? __ldg(pos + r) : 0;
-    int e = valid ? __ldg(pos + r + 1) : 0;
+    const bool valid = r < R1;
+    const int s = valid ? __ldg(pos + r) : 0;
+    const int e = valid ? __ldg(pos + r + 1) : 0;
     unsigned empty = __ballot_sync(0xffffffffu, valid && e == s);
-    unsigned full = __ballot_sync(0xffffffffu, valid && e > s);
-    int rowbase = rb;
-    if (is_tail) { s = lo; e = min(hi, tail_e); full = 1u; rowbase = R0 - 1; }
+    unsigned full = __ballot_sync(0xffffffffu, valid && e > s && e - s <= long_thresh);
     Frag<T, VEC> acc;
 #pragma unroll
     for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
     while (empty) {
       const int h = __ffs(empty) - 1;
       empty &= empty - 1;
-      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, strm);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc);
     }
     while (full) {
       const int h = __ffs(full) - 1;
       full &= full - 1;
       const int hs = __shfl_sync(0xffffffffu, s, h);
-      int he = __shfl_sync(0xffffffffu, e, h);
-      const bool hub = is_tail || he - hs > SPMM_LONG;
-      if (hub) he = min(hi, he);
+      const int he = __shfl_sync(0xffffffffu, e, h);
 #pragma unroll
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      spmm_accumulate<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane, keep, strm);
-      if (active) {
-        const size_t orow = RMAP ? (size_t)__ldg(rowmap + rowbase + h) : (size_t)(rowbase + h);
-        if (hub) red_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc);
-        else store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc, strm);
-      }
+      spmm_accumulate<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Ring kernel (row-major C, 16-byte lane fragments): the same slot/ownership scheme as spmm_csr_kernel, but the B-row
-// gathers no longer land in registers.  Every lane copies ITS 16 bytes of a gathered row with cp.async (LDGSTS) into a
-// per-warp ring of D rows in shared memory and later reads the same 16 bytes back, so no cross-lane synchronisation is
-// needed and D gathers stay in flight per warp at no register cost.  The nonzeros of all non-hub rows a slot owns form
-// ONE flat stream [pos[R0], pos[R1e)): the producer runs D nonzeros ahead of the consumer ACROSS row boundaries, which
-// removes the per-row latency chain (crd -> B row -> store) that bounded the register kernel on short rows (measured:
-// halving the gathered bytes per pass only cut its time by 30 %).  Within a row the products are still accumulated in
-// ascending position order with separate multiply and add, so non-hub rows stay bit-identical to the reference.
+// Schedule (2): long rows, column-panel order.
 // ---------------------------------------------------------------------------------------------------------
-template <bool CA>
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  if constexpr (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+struct SpmmLongCfg {
+  int thresh;       // rows with more nonzeros than this are long
+  int panels;       // column panels (<= 32)
+  int panel_w;      // columns per panel
+  int cap;          // nonzeros per work item
+  int nlong_max;    // capacity of the long-row list: (p1 - p0) / (thresh + 1)
+  long long items_max;
+};
 
-template <typename T, int VEC>
-__device__ __forceinline__ Frag<T, VEC> lds_frag(uint32_t addr) {
-  Frag<T, VEC> f;
-  if constexpr (sizeof(T) == 4) {
-    static_assert(VEC == 4, "ring kernel: 16-byte fragments");
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.v[0]), "=f"(f.v[1]), "=f"(f.v[2]), "=f"(f.v[3]) : "r"(addr) : "memory");
-  } else {
-    static_assert(VEC == 2, "ring kernel: 16-byte fragments");
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(f.v[0]), "=d"(f.v[1]) : "r"(addr) : "memory");
+// counters[0] = number of long rows; counters[1] = ticket of the item kernel (both zeroed by a memset node)
+constexpr int SPMM_FIND_ROWS = 4;      // rows per thread
+__global__ void __launch_bounds__(256)
+spmm_long_find_kernel(const int* __restrict__ pos, SpmmRange rg, SpmmLongCfg cfg, int* __restrict__ long_rows, int* __restrict__ counters) {
+  __shared__ int s_cnt, s_base;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const long long base = (long long)rg.r0 + ((long long)blockIdx.x * blockDim.x) * SPMM_FIND_ROWS;
+  int slot[SPMM_FIND_ROWS];
+#pragma unroll
+  for (int q = 0; q < SPMM_FIND_ROWS; q++) {          // CTA-local slots first: one global atomic per CTA, not per long row
+    const long long r = base + q * blockDim.x + threadIdx.x;
+    slot[q] = -1;
+    if (r < rg.r1 && __ldg(pos + r + 1) - __ldg(pos + r) > cfg.thresh) slot[q] = atomicAdd(&s_cnt, 1);
   }
-  return f;
+  __syncthreads();
+  if (s_cnt == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(counters, s_cnt);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < SPMM_FIND_ROWS; q++) {
+    const int i = s_base + slot[q];
+    if (slot[q] >= 0 && i < cfg.nlong_max) long_rows[i] = (int)(base + q * blockDim.x + threadIdx.x);
+  }
 }
 
-template <typename T, int VEC, int D, int WARPS, int MINB, bool CA>
+// cut[p][li] (p = 0..P) = first position of long row li whose column lies in panel p or later: one binary search per
+// (row, panel boundary).  Rows beyond the number of long rows found get 0 everywhere (empty pairs).
+__global__ void __launch_bounds__(256)
+spmm_long_cut_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const int* __restrict__ long_rows,
+                     const int* __restrict__ counters, SpmmLongCfg cfg, int* __restrict__ cut) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(cfg.panels + 1) * cfg.nlong_max) return;
+  const int p = (int)(idx / cfg.nlong_max), li = (int)(idx % cfg.nlong_max);
+  int q = 0;
+  if (li < min(__ldg(counters), cfg.nlong_max)) {
+    const int r = __ldg(long_rows + li);
+    const int s = __ldg(pos + r), e = __ldg(pos + r + 1);
+    q = (p == 0) ? s : (p == cfg.panels) ? e : tbd::search_first_ge(crd, s, e - 1, p * cfg.panel_w);
+  }
+  cut[idx] = q;
+}
+
+// pair (p, li) = the nonzeros [cut[p][li], cut[p+1][li]) of long row li whose columns lie in panel p, cut into
+// ceil((b-a)/cap) items.  Pairs are numbered panel-major (idx = p * nlong_max + li) so that the prefix sum of the item counts
+// lays the items out in panel order; element `total` closes the scan.
+__global__ void __launch_bounds__(256)
+spmm_long_count_kernel(const int* __restrict__ cut, SpmmLongCfg cfg, int* __restrict__ pair_cnt) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)cfg.panels * cfg.nlong_max;
+  if (idx > total) return;
+  pair_cnt[idx] = idx == total ? 0 : (__ldg(cut + idx + cfg.nlong_max) - __ldg(cut + idx) + cfg.cap - 1) / cfg.cap;
+}
+
+__global__ void __launch_bounds__(256)
+spmm_long_items_kernel(const int* __restrict__ cut, const int* __restrict__ pair_off, SpmmLongCfg cfg, int2* __restrict__ items) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)cfg.panels * cfg.nlong_max) return;
+  const int o = __ldg(pair_off + idx), c = __ldg(pair_off + idx + 1) - o;
+  if (c == 0) return;
+  const int a = __ldg(cut + idx), b = __ldg(cut + idx + cfg.nlong_max);
+  for (int j = 0; j < c; j++) items[o + j] = make_int2(a + j * cfg.cap, min(a + (j + 1) * cfg.cap, b));
+}
+
+// Persistent warps take items in panel order (tickets of SPMM_LONG_CHUNK items) and store one partial row sum per item.
+constexpr int SPMM_LONG_CHUNK = 4;
+template <typename T, int VEC, int U, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-spmm_ring_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
-                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                 const int* __restrict__ slot_rows) {
-  static_assert(D >= 2 && D <= 32 && (D & (D - 1)) == 0, "ring depth: power of two, at most one chunk");
-  extern __shared__ __align__(16) unsigned char ring_raw[];
+spmm_long_kernel(const int* __restrict__ crd, const T* __restrict__ vals, const T* __restrict__ B, int K,
+                 const int2* __restrict__ items, const int* __restrict__ pair_off, long long total_pairs, int* __restrict__ counters,
+                 T* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
-  if (w >= nslots) return;
-  const int nnz = rg.p1;
-  const int lo = rg.p0 + w * SPMM_W, hi = min(lo + SPMM_W, nnz);
-  if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
-  else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
-  const int col = (blockIdx.y * 32 + lane) * VEC;
-  const bool active = col < K;
-  const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
-  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_raw) + (uint32_t)(threadIdx.x >> 5) * (D * 512) + lane * 16;
-  Frag<T, VEC> acc;
-
-  // (a) the piece [lo, min(hi, e)) of a hub row that started in an earlier slot: added atomically (cold path)
-  if (R0 > rg.r0 && lo < nnz) {
-    const int s = __ldg(pos + R0 - 1), e = __ldg(pos + R0);
-    if (e > lo && e - s > SPMM_LONG) {
-#pragma unroll
-      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      spmm_accumulate<T, VEC, 1>(acc, crd, vals, Bcol, K, lo, min(hi, e), lane, 0, 0);
-      if (active) red_row<T, VEC, false>(C, R0 - 1, col, rows, K, acc);
-    }
-  }
-  if (R1 <= R0) return;
-  // (b) empty rows are zeroed by their owner; a hub row (always the last row a slot owns) contributes its first piece
-#pragma unroll
-  for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-  for (int rb = R0; rb < R1; rb += 32) {
-    const int r = rb + lane;
-    const bool valid = r < R1;
-    const int s = valid ? __ldg(pos + r) : 0, e = valid ? __ldg(pos + r + 1) : 1;
-    unsigned empty = __ballot_sync(0xffffffffu, valid && e == s);
-    while (empty) {
-      const int h = __ffs(empty) - 1;
-      empty &= empty - 1;
-      if (active) store_row<T, VEC, false>(C, rb + h, col, rows, K, acc, 0);
-    }
-  }
-  int R1e = R1;
-  {
-    const int s = __ldg(pos + R1 - 1), e = __ldg(pos + R1);
-    if (e - s > SPMM_LONG) {
-      R1e = R1 - 1;
-      spmm_accumulate<T, VEC, 1>(acc, crd, vals, Bcol, K, s, min(hi, e), lane, 0, 0);
-      if (active) red_row<T, VEC, false>(C, R1e, col, rows, K, acc);
-#pragma unroll
-      for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-    }
-  }
-  if (R1e <= R0) return;
-  // (c) the flat stream of the complete rows R0 .. R1e-1
-  const int S = __ldg(pos + R0), E = __ldg(pos + R1e);
-  if (E <= S) return;
-  int crd_k = 0, crd_n = 0;                      // column ids of the chunk being consumed / the next chunk (lane = offset)
-  T val_k = T(0), val_n = T(0);
-  if (S + lane < E) { crd_k = tbd::ldg_stream_i32(crd + S + lane); val_k = __ldg(vals + S + lane); }
-  if (S + 32 + lane < E) { crd_n = tbd::ldg_stream_i32(crd + S + 32 + lane); val_n = __ldg(vals + S + 32 + lane); }
-  // prologue: the first D gathers
-#pragma unroll
-  for (int d = 0; d < D; d++) {
-    const int c = __shfl_sync(0xffffffffu, crd_k, d);
-    if (S + d < E) cp_async16<CA>(ring + d * 512, Bcol + (size_t)c * K);
-    cp_async_commit();
-  }
-  // row cursor: the ends of 32 rows at a time live in `my_e` (lane = row - rb); rows past R1e read as E
-  int rb = R0, row = R0;
-  int my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E;
-  int row_end = __shfl_sync(0xffffffffu, my_e, 0);
-  while (row_end == S) {                          // leading empty rows (already zeroed)
-    row++;
-    if (row - rb == 32) { rb += 32; my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E; }
-    row_end = __shfl_sync(0xffffffffu, my_e, row - rb);
-  }
-  const char* Bbytes = (const char*)Bcol;
-  const unsigned stride = (unsigned)K * (unsigned)sizeof(T);          // bytes between rows of B
-  constexpr uint32_t RMASK = D * 512 - 1;
-  constexpr int G = D >= 4 ? 4 : 2;                                   // nonzeros per fast-path step
-  for (int base = S; base < E; base += 32) {
-    const int cnt = min(32, E - base);
-    int j = 0;
-    while (j < cnt) {
-      const int pc = base + j;
-      const uint32_t off = ((uint32_t)(pc - S) * 512u) & RMASK;
-      const int run = min(row_end - pc, cnt - j);                     // nonzeros left in this row and this chunk
-      if (run >= G && pc + D + G <= E && (((j + D) ^ (j + D + G - 1)) & 32) == 0) {
-        // fast path: G nonzeros of one row; their G refills are all valid and come from one chunk register
-        const int src = (j + D) < 32 ? crd_k : crd_n;
-        cp_async_wait<D - G>();
-        Frag<T, VEC> bv[G];
-        T v[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          bv[g] = lds_frag<T, VEC>(ring + ((off + g * 512u) & RMASK));
-          v[g] = __shfl_sync(0xffffffffu, val_k, j + g);
-        }
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-#pragma unroll
-          for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v[g] * bv[g].v[x];      // mul then add: never fused
-        }
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          const unsigned c = (unsigned)__shfl_sync(0xffffffffu, src, j + D + g);   // source lane is taken modulo 32
-          cp_async16<CA>(ring + ((off + g * 512u) & RMASK), Bbytes + (size_t)c * stride);
-          cp_async_commit();
-        }
-        j += G;
-      } else {
-        const uint32_t slot = ring + off;
-        cp_async_wait<D - 1>();
-        const Frag<T, VEC> b1 = lds_frag<T, VEC>(slot);
-        const T v1 = __shfl_sync(0xffffffffu, val_k, j);
-#pragma unroll
-        for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v1 * b1.v[x];
-        const int jn = j + D;
-        const unsigned c = (unsigned)__shfl_sync(0xffffffffu, jn < 32 ? crd_k : crd_n, jn);
-        if (pc + D < E) cp_async16<CA>(slot, Bbytes + (size_t)c * stride);
-        cp_async_commit();
-        j += 1;
-      }
-      if (base + j == row_end) {
-        if (active) store_row<T, VEC, false>(C, row, col, rows, K, acc, 0);
+  const int nitems = __ldg(pair_off + total_pairs);
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counters + 1, SPMM_LONG_CHUNK);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= nitems) break;
+    const int end = min(base + SPMM_LONG_CHUNK, nitems);
+    for (int it = base; it < end; it++) {
+      const int2 m = __ldg(items + it);
+      for (int c0 = 0; c0 < K; c0 += 32 * VEC) {                 // K <= 32*VEC: one pass (warp-uniform loop)
+        const int col = c0 + lane * VEC;
+        const bool active = col < K;
+        Frag<T, VEC> acc;
 #pragma unroll
         for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-        do {                                      // next non-empty row (rows past R1e read as E: ends with base + j == E)
-          row++;
-          if (row - rb == 32) { rb += 32; my_e = (rb + lane < R1e) ? __ldg(pos + rb + lane + 1) : E; }
-          row_end = __shfl_sync(0xffffffffu, my_e, row - rb);
-        } while (row_end == base + j && row < R1e);
+        spmm_accumulate<T, VEC, U>(acc, crd, vals, B + (active ? col : 0), K, m.x, m.y, lane);
+        if (active) {
+          T* dst = partials + (size_t)it * K + col;
+#pragma unroll
+          for (int x = 0; x < VEC; x++) dst[x] = acc.v[x];
+        }
       }
     }
-    crd_k = crd_n; val_k = val_n;
-    const int nb = base + 64 + lane;
-    if (nb < E) { crd_n = tbd::ldg_stream_i32(crd + nb); val_n = __ldg(vals + nb); }
   }
-  cp_async_wait<0>();
 }
 
-// Launch variants: (gathers in flight per warp, warps per CTA, min CTAs per SM).  TACO_B200_SPMM_VARIANT selects one
-// for tuning runs; the default is the measured best at config C2 (profiles/).
-template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB>
-static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
-                    const int* slot_rows, cudaStream_t st) {
-  dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                 slot_rows);
-}
-
-template <typename T, int VEC, int D, int WARPS, int MINB, bool CA>
-static int spmm_ring_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg,
-                        int nslots, const int* slot_rows, cudaStream_t st) {
-  constexpr int smem = WARPS * D * 512;
-  static bool configured = false;
-  if (!configured) {
-    TB_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TB_CUDA(cudaFuncSetAttribute(spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared));
-    configured = true;
+// One warp per long row: its partials added in ascending panel / item (= position) order, the row of C stored once.
+template <typename T, int VEC, bool COLMAJOR, bool RMAP>
+__global__ void __launch_bounds__(256)
+spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restrict__ counters, const int* __restrict__ pair_off,
+                         SpmmLongCfg cfg, const T* __restrict__ partials, T* __restrict__ C, int rows, int K,
+                         const unsigned* __restrict__ rowmap) {
+  const int lane = threadIdx.x & 31;
+  const int li = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (li >= min(__ldg(counters), cfg.nlong_max)) return;
+  const int r = __ldg(long_rows + li);
+  const size_t orow = RMAP ? (size_t)__ldg(rowmap + r) : (size_t)r;
+  int o = 0, c = 0;
+  if (lane < cfg.panels) {
+    const long long idx = (long long)lane * cfg.nlong_max + li;
+    o = __ldg(pair_off + idx);
+    c = __ldg(pair_off + idx + 1) - o;
   }
-  dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  spmm_ring_kernel<T, VEC, D, WARPS, MINB, CA><<<grid, WARPS * 32, smem, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots, slot_rows);
-  return TACO_B200_OK;
-}
-
-template <typename T, int VEC, bool COLMAJOR>
-static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg) {
-  const int nnz = rg.p1 - rg.p0;
-  int nslots = nnz > 0 ? (nnz + SPMM_W - 1) / SPMM_W : 1;
-  void* slot_rows = nullptr;
-  TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
-  spmm_slot_rows_kernel<T, COLMAJOR><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rg, rows, nslots, K,
-                                                                                     (int*)slot_rows, C);
-  static const int variant = getenv("TACO_B200_SPMM_VARIANT") ? atoi(getenv("TACO_B200_SPMM_VARIANT")) : 0;
-  {
-    ProfScope ps("spmm_csr");
-    const int* sr = (const int*)slot_rows;
-    cudaStream_t st = stream();
-    constexpr bool RING_OK = !COLMAJOR && VEC * sizeof(T) == 16;
-    if constexpr (RING_OK) {
-      switch (variant) {
-        case 10: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 6, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 11: TB_TRY((spmm_ring_go<T, VEC, 16, 8, 3, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 12: TB_TRY((spmm_ring_go<T, VEC, 4, 8, 8, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 13: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 4, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 14: TB_TRY((spmm_ring_go<T, VEC, 8, 4, 12, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 15: TB_TRY((spmm_ring_go<T, VEC, 16, 4, 6, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 16: TB_TRY((spmm_ring_go<T, VEC, 32, 4, 3, false>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 17: TB_TRY((spmm_ring_go<T, VEC, 8, 8, 6, true>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        case 18: TB_TRY((spmm_ring_go<T, VEC, 16, 8, 3, true>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st))); goto launched;
-        default: break;
+  for (int c0 = 0; c0 < K; c0 += 32 * VEC) {
+    const int col = c0 + lane * VEC;
+    const bool active = col < K;
+    Frag<T, VEC> acc;
+#pragma unroll
+    for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
+    for (int p = 0; p < cfg.panels; p++) {
+      const int op = __shfl_sync(0xffffffffu, o, p), cp = __shfl_sync(0xffffffffu, c, p);
+      for (int j = 0; j < cp; j += 4) {             // four partial rows in flight, added in item order
+        Frag<T, VEC> f[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (active && j + u < cp) f[u] = load_row<T, VEC>(partials + (size_t)(op + j + u) * K + col);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (active && j + u < cp) {
+#pragma unroll
+            for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + f[u].v[x];
+          }
       }
     }
-    switch (variant) {
-      case 1: spmm_go<T, VEC, COLMAJOR, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
-      case 2: spmm_go<T, VEC, COLMAJOR, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
-      case 3: spmm_go<T, VEC, COLMAJOR, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
-      default: spmm_go<T, VEC, COLMAJOR, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, st); break;
-    }
-  launched:;
+    if (active) store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc);
   }
-  count_launch(2);
-  scratch_free(slot_rows);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// TACO_B200_SPMM_LONG / _PANELS / _CAP override the defaults (tuning runs); the partial-sum scratch is kept under 4 GiB by
+// halving the panel count, then doubling the threshold.
+static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es) {
+  static const int e_thresh = env_int("TACO_B200_SPMM_LONG", 128), e_panels = env_int("TACO_B200_SPMM_PANELS", 32),
+                   e_cap = env_int("TACO_B200_SPMM_CAP", 256);
+  SpmmLongCfg c;
+  c.thresh = e_thresh < 64 ? 64 : e_thresh;
+  c.panels = e_panels < 1 ? 1 : (e_panels > 32 ? 32 : e_panels);
+  c.cap = e_cap < 32 ? 32 : e_cap;
+  const size_t budget = (size_t)4 << 30;
+  for (;;) {
+    c.nlong_max = nnz / (c.thresh + 1);
+    c.items_max = (long long)nnz / c.cap + 1 + (long long)c.nlong_max * c.panels;
+    if ((size_t)c.items_max * K * es <= budget || c.nlong_max == 0) break;
+    if (c.panels > 1) c.panels /= 2;
+    else c.thresh *= 2;
+  }
+  c.panel_w = (cols + c.panels - 1) / c.panels;
+  if (c.panel_w < 1) c.panel_w = 1;
+  return c;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <typename T, int VEC, int U, int MINB>
+static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const int2* items, const int* pair_off, long long pairs,
+                         int* counters, T* partials, cudaStream_t st) {
+  constexpr int WARPS = 8;
+  spmm_long_kernel<T, VEC, U, WARPS, MINB><<<num_sms() * MINB, WARPS * 32, 0, st>>>(crd, vals, B, K, items, pair_off, pairs, counters, partials);
+}
+
+// Builds the plan on the compute stream, then runs the item kernel and the combine kernel on `run_st` (the compute stream
+// itself, or a side stream so that they overlap the slot kernel: the two are bound by different resources -- the panel-ordered
+// gathers by the L2 -> SM path, the short rows by HBM).  *scratch_out is released by the caller after the streams have joined.
+template <typename T, int VEC, bool COLMAJOR, bool RMAP>
+static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int cols, int K, SpmmRange rg,
+                          const SpmmLongCfg& cfg, const unsigned* rowmap, cudaStream_t run_st, cudaEvent_t fork, void** scratch_out) {
+  const long long pairs = (long long)cfg.panels * cfg.nlong_max;
+  const size_t o_cnt = 0, o_rows = align256(16), o_ab = o_rows + align256(sizeof(int) * (size_t)cfg.nlong_max),
+               o_off = o_ab + align256(sizeof(int) * (size_t)(pairs + cfg.nlong_max)), o_items = o_off + align256(sizeof(int) * (size_t)(pairs + 1)),
+               o_part = o_items + align256(sizeof(int2) * (size_t)cfg.items_max),
+               total = o_part + align256(sizeof(T) * (size_t)cfg.items_max * K);
+  void* buf = nullptr;
+  TB_TRY(scratch_alloc(&buf, total));
+  *scratch_out = buf;
+  char* b = (char*)buf;
+  int* counters = (int*)(b + o_cnt);
+  int* long_rows = (int*)(b + o_rows);
+  int* cut = (int*)(b + o_ab);
+  int* pair_off = (int*)(b + o_off);
+  int2* items = (int2*)(b + o_items);
+  T* partials = (T*)(b + o_part);
+  cudaStream_t st = stream();
+  cudaError_t e = cudaMemsetAsync(counters, 0, 16, st);
+  if (e != cudaSuccess) return fail(TACO_B200_ERR_CUDA, "spmm: memset failed: %s", cudaGetErrorString(e));
+  const int nrows = rg.r1 - rg.r0;
+  spmm_long_find_kernel<<<(nrows + 256 * SPMM_FIND_ROWS - 1) / (256 * SPMM_FIND_ROWS), 256, 0, st>>>(pos, rg, cfg, long_rows, counters);
+  spmm_long_cut_kernel<<<(unsigned)((pairs + cfg.nlong_max + 255) / 256), 256, 0, st>>>(pos, crd, long_rows, counters, cfg, cut);
+  spmm_long_count_kernel<<<(unsigned)((pairs + 1 + 255) / 256), 256, 0, st>>>(cut, cfg, pair_off);
+  TB_TRY(exclusive_scan_i32(pair_off, pair_off, pairs + 1));
+  spmm_long_items_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(cut, pair_off, cfg, items);
+  if (run_st != st) {
+    TB_CUDA(cudaEventRecord(fork, st));
+    TB_CUDA(cudaStreamWaitEvent(run_st, fork, 0));
+  }
+  // (gathers in flight per warp, min CTAs per SM) of the item kernel: items are long runs of one row, so per-warp
+  // parallelism pays more than occupancy here (TACO_B200_SPMM_LONGVAR sweeps it)
+  static const int lvar = env_int("TACO_B200_SPMM_LONGVAR", 0);
+  switch (lvar) {
+    case 1: spmm_long_go<T, VEC, 2, 8>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+    case 2: spmm_long_go<T, VEC, 4, 4>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+    case 3: spmm_long_go<T, VEC, 8, 4>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+    case 4: spmm_long_go<T, VEC, 8, 3>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+    default: spmm_long_go<T, VEC, 4, 6>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+  }
+  spmm_long_combine_kernel<T, VEC, COLMAJOR, RMAP><<<(unsigned)(((long long)cfg.nlong_max * 32 + 255) / 256), 256, 0, run_st>>>(
+      long_rows, counters, pair_off, cfg, partials, C, rows, K, rowmap);
+  count_launch(7);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }
 
-// Row-mapped launch (csf.cu, TTM): C[rowmap[r], :] = sum_p vals[p] * B[crd[p], :] over the rows r of any (pos, crd, vals) level.
-template <typename T, int VEC>
-static int spmm_mapped_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, int nnz,
+// Launch variants of schedule (1): (gathers in flight per warp, warps per CTA, min CTAs per SM).  TACO_B200_SPMM_VARIANT
+// selects one for tuning runs; the default is the measured best at config C2 (profiles/).
+template <typename T, int VEC, bool COLMAJOR, bool RMAP, int U, int WARPS, int MINB>
+static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
+                    const int* slot_rows, int long_thresh, const unsigned* rowmap, cudaStream_t st) {
+  dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
+  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, RMAP><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
+                                                                                       slot_rows, long_thresh, rowmap);
+}
+
+// The whole SpMM launch sequence over a row range: long-row plan + column-panel kernels, then the slot kernel.
+// `variant_env` names the environment variable that selects a launch variant of the slot kernel.
+template <typename T, int VEC, bool COLMAJOR, bool RMAP>
+static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int cols, int K, SpmmRange rg,
                             const unsigned* rowmap, const char* prof_name) {
-  const SpmmRange rg{0, rows, 0, nnz};
+  const int nnz = rg.p1 - rg.p0;
   const int nslots = nnz > 0 ? (nnz + SPMM_W - 1) / SPMM_W : 1;
   void* slot_rows = nullptr;
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
-  spmm_slot_rows_kernel<T, false, true><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rg, rows, nslots, K, (int*)slot_rows, C, rowmap);
-  {
-    ProfScope ps(prof_name);
-    constexpr int WARPS = 8;
-    dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-    // (gathers in flight per warp, min CTAs per SM): rows narrower than a full warp fragment (K * sizeof T < 512 bytes) keep
-    // fewer bytes in flight per gather, so deeper unrolling is worth its registers there (TACO_B200_TTM_UNROLL=2..5 to compare)
-    static const int variant = getenv("TACO_B200_TTM_UNROLL") ? atoi(getenv("TACO_B200_TTM_UNROLL")) : 0;
-#define TB_MAPPED_GO(U, MINB)                                                                                              \
-  spmm_csr_kernel<T, VEC, false, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(pos, crd, vals, B, C, rows, K, rg, nslots, \
-                                                                                          (const int*)slot_rows, rowmap)
-    switch (variant) {
-      case 2: TB_MAPPED_GO(4, 6); break;
-      case 3: TB_MAPPED_GO(4, 8); break;
-      case 4: TB_MAPPED_GO(4, 4); break;
-      case 5: TB_MAPPED_GO(8, 4); break;
-      default: TB_MAPPED_GO(2, 8); break;
-    }
-#undef TB_MAPPED_GO
+  ProfScope ps(prof_name);
+  const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
+  static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 1);
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
+  if (!ev_fork) {
+    TB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    TB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t side = (overlap && cfg.nlong_max > 0) ? aux_stream(2) : stream();
+  void* long_scratch = nullptr;
+  int rc = TACO_B200_OK;
+  if (cfg.nlong_max > 0)
+    rc = spmm_long_rows<T, VEC, COLMAJOR, RMAP>(pos, crd, vals, B, C, rows, cols, K, rg, cfg, rowmap, side, ev_fork, &long_scratch);
+  if (rc != TACO_B200_OK) {
+    if (side != stream()) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(stream(), ev_join, 0); }
+    scratch_free(long_scratch); scratch_free(slot_rows);
+    return rc;
+  }
+  spmm_slot_rows_kernel<<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(pos, rg, nslots, (int*)slot_rows);
+  static const int variant = env_int(RMAP ? "TACO_B200_TTM_UNROLL" : "TACO_B200_SPMM_VARIANT", 0);
+  const int* sr = (const int*)slot_rows;
+  cudaStream_t st = stream();
+  switch (variant) {
+    case 1: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
+    case 2: spmm_go<T, VEC, COLMAJOR, RMAP, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
+    case 3: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
+    case 4: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
+    default: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
   }
   count_launch(2);
+  if (side != stream()) {                 // join: the scratch is released (stream-ordered) only after the side stream is done
+    TB_CUDA(cudaEventRecord(ev_join, side));
+    TB_CUDA(cudaStreamWaitEvent(stream(), ev_join, 0));
+  }
+  scratch_free(long_scratch);
   scratch_free(slot_rows);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
 }
 
-int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int K, int nnz,
+// Row-mapped launch (csf.cu, TTM): C[rowmap[r], :] = sum_p vals[p] * B[crd[p], :] over the rows r of any (pos, crd, vals) level
+// (B has `cols` rows).
+int spmm_mapped(DType dt, const int* pos, const int* crd, const void* vals, const void* B, void* C, int rows, int cols, int K, int nnz,
                 const unsigned* rowmap, const char* prof_name) {
   const bool a16 = (((uintptr_t)B | (uintptr_t)C) & 15) == 0;
+  const SpmmRange rg{0, rows, 0, nnz};
   if (dt == DType::F64) {
-    if (a16 && K % 2 == 0) return spmm_mapped_impl<double, 2>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, K, nnz, rowmap, prof_name);
-    return spmm_mapped_impl<double, 1>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, K, nnz, rowmap, prof_name);
+    if (a16 && K % 2 == 0) return spmm_launch_impl<double, 2, false, true>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, cols, K, rg, rowmap, prof_name);
+    return spmm_launch_impl<double, 1, false, true>(pos, crd, (const double*)vals, (const double*)B, (double*)C, rows, cols, K, rg, rowmap, prof_name);
   }
-  if (a16 && K % 4 == 0) return spmm_mapped_impl<float, 4>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, K, nnz, rowmap, prof_name);
-  return spmm_mapped_impl<float, 1>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, K, nnz, rowmap, prof_name);
+  if (a16 && K % 4 == 0) return spmm_launch_impl<float, 4, false, true>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, cols, K, rg, rowmap, prof_name);
+  return spmm_launch_impl<float, 1, false, true>(pos, crd, (const float*)vals, (const float*)B, (float*)C, rows, cols, K, rg, rowmap, prof_name);
 }
 
 template <typename T>
-static int spmm_launch(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg,
+static int spmm_launch(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int cols, int K, SpmmRange rg,
                        bool colmajor) {
   constexpr int V = 16 / sizeof(T);
-  bool vec_ok = (K % V == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)C & 15) == 0);
-  // TACO_B200_SPMM_SLICE=1: one column per lane, so the launch becomes ceil(K/32) passes over A (grid.y, scheduled one
-  // after the other), each gathering 32-column slices of the rows of B -- a 4x smaller working set per pass in L2
-  static const int sliced = getenv("TACO_B200_SPMM_SLICE") ? atoi(getenv("TACO_B200_SPMM_SLICE")) : 0;
-  if (sliced == 1) vec_ok = false;
-  if constexpr (sizeof(T) == 4) {          // =2: two columns per lane (64-column slices, 256-byte gathers)
-    if (sliced == 2 && vec_ok && !colmajor) return spmm_launch_impl<T, 2, false>(pos, crd, vals, B, C, rows, K, rg);
-  }
+  const bool vec_ok = (K % V == 0) && (((uintptr_t)B & 15) == 0) && (((uintptr_t)C & 15) == 0);
   if (colmajor) {
-    if (vec_ok) return spmm_launch_impl<T, V, true>(pos, crd, vals, B, C, rows, K, rg);
-    return spmm_launch_impl<T, 1, true>(pos, crd, vals, B, C, rows, K, rg);
+    if (vec_ok) return spmm_launch_impl<T, V, true, false>(pos, crd, vals, B, C, rows, cols, K, rg, nullptr, "spmm_csr");
+    return spmm_launch_impl<T, 1, true, false>(pos, crd, vals, B, C, rows, cols, K, rg, nullptr, "spmm_csr");
   }
-  if (vec_ok) return spmm_launch_impl<T, V, false>(pos, crd, vals, B, C, rows, K, rg);
-  return spmm_launch_impl<T, 1, false>(pos, crd, vals, B, C, rows, K, rg);
+  if (vec_ok) return spmm_launch_impl<T, V, false, false>(pos, crd, vals, B, C, rows, cols, K, rg, nullptr, "spmm_csr");
+  return spmm_launch_impl<T, 1, false, false>(pos, crd, vals, B, C, rows, cols, K, rg, nullptr, "spmm_csr");
 }
 
 int csr_nnz(const CsrView& A, int32_t vals_size_hint, int32_t* nnz);   // spmv.cu
@@ -681,7 +646,7 @@ static int spmm_compute_pipelined(const CsrView& Av, const DenseView& Bv, const 
     }
     TB_CUDA(cudaEventRecord(e_up, up));
     TB_CUDA(cudaStreamWaitEvent(main, e_up, 0));
-    rc = spmm_launch<T>((const int*)dpos, (const int*)dcrd, (const T*)dvals, (const T*)dB, (T*)dC, rows, K,
+    rc = spmm_launch<T>((const int*)dpos, (const int*)dcrd, (const T*)dvals, (const T*)dB, (T*)dC, rows, Av.cols, K,
                         SpmmRange{r0, r1, p0, p1}, false);
     TB_CUDA(cudaEventRecord(e_done, main));
     TB_CUDA(cudaStreamWaitEvent(down, e_done, 0));
@@ -743,10 +708,10 @@ int taco_b200_spmm_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t* B)
     const SpmmRange all{0, Av.rows, 0, nnz};
     if (Av.dt == DType::F32)
       TB_TRY(spmm_launch<float>(pos.as<int>(), crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(),
-                                Av.rows, K, all, cm));
+                                Av.rows, Av.cols, K, all, cm));
     else
       TB_TRY(spmm_launch<double>(pos.as<int>(), crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(),
-                                 Av.rows, K, all, cm));
+                                 Av.rows, Av.cols, K, all, cm));
   }
   TB_TRY(cout.commit());
   return finish_call();
@@ -801,9 +766,9 @@ int taco_b200_spmm_dcsr_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_
     const SpmmRange all{0, Av.rows, 0, nnz};
     int rc;
     if (Av.dt == DType::F32)
-      rc = spmm_launch<float>((const int*)pos_full, crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(), Av.rows, K, all, cm);
+      rc = spmm_launch<float>((const int*)pos_full, crd.as<int>(), vals.as<float>(), bin.as<float>(), cout.as<float>(), Av.rows, Av.cols, K, all, cm);
     else
-      rc = spmm_launch<double>((const int*)pos_full, crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(), Av.rows, K, all, cm);
+      rc = spmm_launch<double>((const int*)pos_full, crd.as<int>(), vals.as<double>(), bin.as<double>(), cout.as<double>(), Av.rows, Av.cols, K, all, cm);
     scratch_free(pos_full);
     TB_TRY(rc);
   }

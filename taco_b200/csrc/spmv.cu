@@ -23,6 +23,8 @@
 //              within 1e-12 of the sequential sum.
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*(cols + rows).
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -48,17 +50,18 @@ template <> struct ValVec<float> {
   }
 };
 
+// `vec`: crd + q and vals + q are 16-byte aligned for every q this launch asks for (see `shift` in the kernel)
 template <typename T>
-__device__ __forceinline__ void spmv_load4(const int* __restrict__ crd, const T* __restrict__ vals, int q, int nnz, int4& c,
+__device__ __forceinline__ void spmv_load4(const int* __restrict__ crd, const T* __restrict__ vals, int q, int nnz, bool vec, int4& c,
                                            T (&v)[4]) {
-  if (q + SPMV_VEC <= nnz) {
+  if (vec && q >= 0 && q + SPMV_VEC <= nnz) {
     c = tbd::ldg_stream_i4(crd + q);
     ValVec<T>::load4(vals + q, v);
   } else {
     int cc[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const bool ok = q + e < nnz;
+      const bool ok = q + e >= 0 && q + e < nnz;
       cc[e] = ok ? __ldg(crd + q + e) : 0;
       v[e] = ok ? __ldg(vals + q + e) : T(0);
     }
@@ -103,7 +106,7 @@ template <typename T, int MINB, bool MAPPED, int GV = 0, int STEPS = SPMV_STEPS>
 __global__ void __launch_bounds__(SPMV_THREADS, MINB)
 spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ x, T* __restrict__ y, int rows, int nnz, T* __restrict__ partial,
-                int* __restrict__ flag, int epoch, const unsigned* __restrict__ ymap) {
+                int* __restrict__ flag, int epoch, const unsigned* __restrict__ ymap, int shift, bool vec) {
   constexpr int TILE = SPMV_THREADS * SPMV_VEC * STEPS;      // nonzeros per CTA (TACO_B200_SPMV_VARIANT=4..6 sweep it)
   __shared__ T prod[TILE + SPMV_OV];
   __shared__ T red[SPMV_THREADS / 32];
@@ -111,7 +114,9 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   __shared__ int s_long[4];                        // tail row, its start
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
-  const int lo = b * TILE;                    // window [lo, hi), staged [lo, hiov)
+  // Tiles start `shift` (0..3) nonzeros before the arrays do, so that every 128-bit load of crd / vals is aligned even when the
+  // caller hands over a slice that starts at an arbitrary element (a row shard of a larger matrix): tile 0 is short.
+  const int lo = b * TILE - shift;            // window [lo, hi), staged [lo, hiov); positions < 0 do not exist
   const int hi = min(lo + TILE, nnz);
   const int hiov = min(lo + TILE + SPMV_OV, nnz);
   const bool last_tile = (b == (int)gridDim.x - 1);
@@ -120,7 +125,7 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   int4 c[STEPS];
   T v[STEPS][4];
 #pragma unroll
-  for (int s = 0; s < STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, c[s], v[s]);
+  for (int s = 0; s < STEPS; s++) spmv_load4<T>(crd, vals, lo + (s * SPMV_THREADS + tid) * SPMV_VEC, nnz, vec, c[s], v[s]);
   if (tid == 0) s_long[0] = -1;
 
   // ---- (1) owned rows [r_lo, r_hi): first row with pos[r] >= lo / >= hi.  Warp 0 alone runs two 16-ary searches
@@ -163,7 +168,7 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   // the overlap into the next window: 16 threads of warp 1
   if (tid >= 32 && tid < 32 + SPMV_OV / SPMV_VEC && lo + TILE + (tid - 32) * SPMV_VEC < hiov) {
     const int q = TILE + (tid - 32) * SPMV_VEC;
-    spmv_load4<T>(crd, vals, lo + q, nnz, c[0], v[0]);
+    spmv_load4<T>(crd, vals, lo + q, nnz, vec, c[0], v[0]);
     const T x0 = spmv_ld_x<T, GV>(x + c[0].x, keep), x1 = spmv_ld_x<T, GV>(x + c[0].y, keep), x2 = spmv_ld_x<T, GV>(x + c[0].z, keep),
             x3 = spmv_ld_x<T, GV>(x + c[0].w, keep);
     T* d = prod + q;
@@ -195,8 +200,8 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     const int e_head = __ldg(pos + r_lo);          // uniform over the CTA
     if (e_head > lo) {
       const int s_head = __ldg(pos + r_lo - 1);
-      const int b0 = s_head / TILE;           // owner tile
-      if (e_head > min((b0 + 1) * TILE + SPMV_OV, nnz)) {     // the owner handed this row over
+      const int b0 = (s_head + shift) / TILE; // owner tile
+      if (e_head > min((b0 + 1) * TILE - shift + SPMV_OV, nnz)) {     // the owner handed this row over
         if (e_head > hi) {                         // this window lies wholly inside the row
           const T sum = spmv_block_sum(prod, 0, hi - lo, red);
           if (tid == 0) {
@@ -221,12 +226,32 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   }
 }
 
-// persistent hand-over scratch (one slot per tile); flags are compared against a per-launch epoch, so they are
-// never cleared between calls
-static void* g_spmv_partial = nullptr;
-static int* g_spmv_flag = nullptr;
-static int g_spmv_cap = 0;
-static int g_spmv_epoch = 0;
+// Hand-over scratch (one partial + one flag per tile).  Flags are compared against a per-launch epoch, so they are never
+// cleared between calls.  One scratch set per STREAM: launches on one stream are serialised by the stream, launches on
+// different streams (taco_b200_set_stream) or from different host threads never share slots; the table is mutex-guarded.
+struct SpmvScratch { void* partial = nullptr; int* flag = nullptr; int cap = 0; int epoch = 0; };
+static std::mutex g_spmv_mu;
+static std::unordered_map<cudaStream_t, SpmvScratch> g_spmv_scratch;
+
+static int spmv_scratch_for(cudaStream_t st, int ntiles, SpmvScratch* out) {
+  std::lock_guard<std::mutex> lk(g_spmv_mu);
+  SpmvScratch& sc = g_spmv_scratch[st];
+  if (ntiles > sc.cap) {
+    if (sc.partial) { cudaFreeAsync(sc.partial, st); cudaFreeAsync(sc.flag, st); }     // stream-ordered: earlier launches finish first
+    sc.cap = ntiles + ntiles / 2 + 1024;
+    sc.partial = nullptr; sc.flag = nullptr;
+    TB_CUDA(cudaMallocAsync(&sc.partial, sizeof(double) * (size_t)sc.cap, st));
+    TB_CUDA(cudaMallocAsync((void**)&sc.flag, sizeof(int) * (size_t)sc.cap, st));
+    TB_CUDA(cudaMemsetAsync(sc.flag, 0, sizeof(int) * (size_t)sc.cap, st));
+    sc.epoch = 0;
+  }
+  if (++sc.epoch == INT32_MAX) {
+    TB_CUDA(cudaMemsetAsync(sc.flag, 0, sizeof(int) * (size_t)sc.cap, st));
+    sc.epoch = 1;
+  }
+  *out = sc;
+  return TACO_B200_OK;
+}
 
 template <typename T>
 static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const T* x, T* y, int rows, int nnz, const unsigned* ymap,
@@ -234,24 +259,25 @@ static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const 
   static const int variant = getenv("TACO_B200_SPMV_VARIANT") ? atoi(getenv("TACO_B200_SPMV_VARIANT")) : 0;
   const int steps = (!ymap && (variant == 4 || variant == 6)) ? 1 : (!ymap && variant == 5) ? 4 : SPMV_STEPS;
   const int tile = SPMV_THREADS * SPMV_VEC * steps;
-  const int ntiles = nnz > 0 ? (nnz + tile - 1) / tile : 1;
-  if (ntiles > g_spmv_cap) {
-    if (g_spmv_partial) { cudaFree(g_spmv_partial); cudaFree(g_spmv_flag); }
-    g_spmv_cap = ntiles + ntiles / 2 + 1024;
-    TB_CUDA(cudaMalloc(&g_spmv_partial, sizeof(double) * (size_t)g_spmv_cap));
-    TB_CUDA(cudaMalloc((void**)&g_spmv_flag, sizeof(int) * (size_t)g_spmv_cap));
-    TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
-    g_spmv_epoch = 0;
+  // 128-bit loads need crd + q and vals + q 16-byte aligned at every vector start q = 4m - shift: possible when both arrays
+  // are element-aligned and misaligned by the same number of elements modulo 4 (always true for a slice [o, o + nnz) of
+  // aligned arrays, i.e. a row shard); anything else takes scalar loads
+  const uintptr_t ca = (uintptr_t)crd, va = (uintptr_t)vals;
+  int shift = 0;
+  bool vec = (ca % 4 == 0) && (va % sizeof(T) == 0);
+  if (vec) {
+    shift = (int)((ca / 4) % 4);
+    vec = ((va / sizeof(T)) - (uintptr_t)shift) % (16 / sizeof(T)) == 0;
+    if (!vec) shift = 0;
   }
-  if (++g_spmv_epoch == INT32_MAX) {
-    TB_CUDA(cudaMemsetAsync(g_spmv_flag, 0, sizeof(int) * (size_t)g_spmv_cap, stream()));
-    g_spmv_epoch = 1;
-  }
+  const int ntiles = nnz > 0 ? (int)(((long long)nnz + shift + tile - 1) / tile) : 1;
+  SpmvScratch sc;
+  TB_TRY(spmv_scratch_for(stream(), ntiles, &sc));
   {
     ProfScope ps(prof_name);
 #define TB_SPMV_GO(MINB, MAPPED, GV, ...)                                                                              \
   spmv_csr_kernel<T, MINB, MAPPED, GV, ##__VA_ARGS__><<<ntiles, SPMV_THREADS, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz, \
-                                                                              (T*)g_spmv_partial, g_spmv_flag, g_spmv_epoch, ymap)
+                                                                              (T*)sc.partial, sc.flag, sc.epoch, ymap, shift, vec)
     if (ymap && variant == 3) TB_SPMV_GO(6, true, 1);
     else if (ymap) TB_SPMV_GO(6, true, 0);
     else if (variant == 1) TB_SPMV_GO(8, false, 0);
@@ -328,8 +354,6 @@ int taco_b200_spmv_compute(taco_tensor_t* y, taco_tensor_t* A, taco_tensor_t* x)
   TB_TRY(vals.acquire(Av.vals ? Av.vals : (void*)Av.pos, es * (size_t)nnz));
   TB_TRY(xin.acquire(xv.vals, es * (size_t)Av.cols));
   TB_TRY(yout.acquire(yv.vals, es * (size_t)Av.rows));
-  if (((uintptr_t)crd.dptr | (uintptr_t)vals.dptr) & 15)
-    return fail(TACO_B200_ERR_ARG, "spmv: device crd/vals arrays must be 16-byte aligned");
   if (Av.rows > 0) {
     if (Av.dt == DType::F64) TB_TRY(spmv_launch<double>(Av, pos, crd, vals, xin, yout, nnz));
     else TB_TRY(spmv_launch<float>(Av, pos, crd, vals, xin, yout, nnz));

@@ -47,8 +47,13 @@ def shard_csr(pos, crd, vals, n_rows, rank, world, bounds=None):
     return dict(pos=lp, crd=crd[lo:hi], vals=vals[lo:hi], row_begin=r0, row_end=r1)
 
 
-def shard_csf3(t, rank, world):
-    """Mode-0 slice shard of a CSF tensor (dict B1_pos.. as produced by formats.coo_to_csf3 / synth.csf3_uniform)."""
+def shard_csf3(t, rank, world, rebase_rows=False, dim0=None):
+    """Mode-0 slice shard of a CSF tensor (dict B1_pos.. as produced by formats.coo_to_csf3 / synth.csf3_uniform).
+
+    rebase_rows=True makes the shard a self-contained sub-problem over ITS OWN rows of the dense result (what a rank
+    of a multi-GPU MTTKRP runs): the shard owns the result rows [row_begin, row_end) -- from its first slice's row id
+    (0 for rank 0) up to the next shard's first row id (`dim0` for the last rank) -- and B1_crd is rebased to that
+    range, so the kernel writes a (row_end - row_begin) x R block that concatenates with the other ranks' blocks."""
     ns = int(t["B1_crd"].shape[0])
     # leaf offset at the start of every slice: B3_pos[B2_pos[s]]
     idx = t["B2_pos"].long() if _is_torch(t["B2_pos"]) else t["B2_pos"].astype(np.int64)
@@ -64,9 +69,18 @@ def shard_csf3(t, rank, world):
     b1 = np.array([0, s1 - s0], dtype=np.int32)
     if _is_torch(t["B2_pos"]):
         b1 = torch.as_tensor(b1, device=t["B2_pos"].device)
-    return dict(B1_pos=b1, B1_crd=mk(t["B1_crd"][s0:s1]), B2_pos=mk(_rebase(p2)), B2_crd=mk(t["B2_crd"][f0:f1]),
-                B3_pos=mk(_rebase(p3)), B3_crd=mk(t["B3_crd"][l0:l1]), B_vals=mk(t["B_vals"][l0:l1]),
-                slice_begin=s0, slice_end=s1)
+    c1 = t["B1_crd"][s0:s1]
+    out = dict(B1_pos=b1, B2_pos=mk(_rebase(p2)), B2_crd=mk(t["B2_crd"][f0:f1]),
+               B3_pos=mk(_rebase(p3)), B3_crd=mk(t["B3_crd"][l0:l1]), B_vals=mk(t["B_vals"][l0:l1]),
+               slice_begin=s0, slice_end=s1)
+    if rebase_rows:
+        assert dim0 is not None, "rebase_rows needs the mode-0 dimension"
+        row_begin = 0 if rank == 0 else (int(t["B1_crd"][s0]) if s0 < ns else int(dim0))
+        row_end = int(t["B1_crd"][s1]) if s1 < ns else int(dim0)
+        c1 = c1 - row_begin
+        out.update(row_begin=row_begin, row_end=row_end)
+    out["B1_crd"] = mk(c1)
+    return out
 
 
 def allgather_rows(local_rows, bounds, row_len=1, group=None):

@@ -22,7 +22,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from taco_b200 import formats, tbin  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import tbin  # noqa: E402  (oracle/tbin.py)
+from taco_b200 import formats  # noqa: E402
 
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "taco_ref_harness")
 OUT = os.path.dirname(os.path.abspath(__file__))

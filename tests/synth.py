@@ -261,17 +261,9 @@ def csr_rmat(xp, scale, edge_factor, seed, dtype, abcd=(0.57, 0.19, 0.19, 0.05))
     return xp.i32(pos), xp.i32(crd), values(xp, xp.arange(int(key.shape[0])), seed + 1, dtype)
 
 
-def csf3_uniform(xp, I, K, L, nnz, seed, dtype):
-    """order-3 CSF {Compressed x3} (mode order 0,1,2) with ~nnz uniform coordinates (duplicates removed).
-    Sorted lexicographically with two stable sorts (by l, then by i*K+k): the full key would not fit 63 bits at
-    10M x 1M x 1M."""
-    e = xp.arange(nnz)
-    i = uniform_int(xp, e, seed, I)
-    k = uniform_int(xp, e, seed + 1, K)
-    l = uniform_int(xp, e, seed + 2, L)
-    assert I * K < (1 << 62)
-    ik = i * K + k
-    del i, k, e
+def _csf3_from_coords(xp, ik, l, K, nnz, seed, dtype):
+    """sort (ik = i*K+k, l) lexicographically with two stable sorts (the full key would not fit 63 bits at
+    10M x 1M x 1M), drop duplicates, build the three CSF levels"""
     o = xp.argsort(l)
     l, ik = l[o], ik[o]
     o = xp.argsort(ik)
@@ -301,6 +293,33 @@ def csf3_uniform(xp, I, K, L, nnz, seed, dtype):
     )
 
 
+def csf3_uniform(xp, I, K, L, nnz, seed, dtype):
+    """order-3 CSF {Compressed x3} (mode order 0,1,2) with ~nnz uniform coordinates (duplicates removed)."""
+    e = xp.arange(nnz)
+    i = uniform_int(xp, e, seed, I)
+    k = uniform_int(xp, e, seed + 1, K)
+    l = uniform_int(xp, e, seed + 2, L)
+    assert I * K < (1 << 62)
+    ik = i * K + k
+    del i, k, e
+    return _csf3_from_coords(xp, ik, l, K, nnz, seed, dtype)
+
+
+def csf3_fibers(xp, I, K, L, nnz, nfib, seed, dtype):
+    """order-3 CSF whose (i,k) fibers hold about nnz / nfib leaves each (real tensors have fibers longer than one
+    leaf; csf3_uniform at the C4 shape has nfib ~ nnz): every nonzero draws one of `nfib` fibers, the fiber's (i,k) cell
+    is a hash of the fiber id, l is uniform."""
+    e = xp.arange(nnz)
+    f = uniform_int(xp, e, seed, nfib)
+    i = uniform_int(xp, f, seed + 1, I)
+    k = uniform_int(xp, f, seed + 4, K)
+    l = uniform_int(xp, e, seed + 2, L)
+    assert I * K < (1 << 62)
+    ik = i * K + k
+    del i, k, e, f
+    return _csf3_from_coords(xp, ik, l, K, nnz, seed, dtype)
+
+
 # ---- the named BASELINE workloads ---------------------------------------------------------------------------
 SEED0 = 0x7AC00000
 
@@ -309,6 +328,9 @@ FULL = {
     "spmm": dict(scale=22, edge_factor=16, K=128, dtype="float32"),
     "sddmm": dict(n=2_000_000, deg=20, K=64, dtype="float32"),
     "mttkrp": dict(I=10_000_000, K=1_000_000, L=1_000_000, nnz=200_000_000, R=32, dtype="float64"),
+    # a second MTTKRP tensor with realistic fiber lengths (about 12 leaves per (i,k) fiber, 4 fibers per slice): the C4 tensor
+    # above has one leaf per fiber, which hides what a per-fiber workspace saves
+    "mttkrp_fibers": dict(I=2_000_000, K=1_000_000, L=1_000_000, nnz=100_000_000, nfib=8_000_000, R=32, dtype="float64"),
     "spadd": dict(n=1_000_000, deg=10, dtype="float64"),
     "spgemm": dict(n=1_000_000, deg=10, dtype="float64"),
     # TTV / TTM: dense results, so the (i,j) plane is kept small enough to hold A in HBM
@@ -344,6 +366,11 @@ def make(workload, device=None, **over):
         t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 9, dt)
         t.update(dims=(p["I"], p["K"], p["L"], p["R"]), C=dense(xp, p["K"], p["R"], SEED0 + 14, dt),
                  D=dense(xp, p["L"], p["R"], SEED0 + 15, dt))
+        return t
+    if workload == "mttkrp_fibers":
+        t = csf3_fibers(xp, p["I"], p["K"], p["L"], p["nnz"], p["nfib"], SEED0 + 50, dt)
+        t.update(dims=(p["I"], p["K"], p["L"], p["R"]), C=dense(xp, p["K"], p["R"], SEED0 + 54, dt),
+                 D=dense(xp, p["L"], p["R"], SEED0 + 55, dt))
         return t
     if workload == "ttv":
         t = csf3_uniform(xp, p["I"], p["K"], p["L"], p["nnz"], SEED0 + 24, dt)

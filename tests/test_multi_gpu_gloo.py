@@ -23,7 +23,8 @@ def _worker(rank, world, port, results):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
-    from taco_b200 import partition, synth
+    import synth
+    from taco_b200 import partition
     try:
         # ---- CSR row sharding: iterative SpMV  x <- A x  (allgather of y between iterations) ---------------------
         w = synth.make("spmm", None, scale=12, K=8, dtype="float64")       # power-law rows: shards differ in row count
@@ -80,7 +81,8 @@ def test_partitioner_world2_gloo():
 
 
 def test_shard_rebase_is_consistent():
-    from taco_b200 import partition, synth
+    import synth
+    from taco_b200 import partition
     w = synth.make("spmv", None, n=1000, deg=7)
     for world in (1, 3, 8):
         b = partition.row_bounds(w["A_pos"], 1000, world)

@@ -6,7 +6,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
 import torch
 import gpu_util as G
 import taco_b200 as tb
-from taco_b200 import synth
+import synth
 
 def t(fn, n=5):
     fn(); torch.cuda.synchronize()

@@ -18,13 +18,24 @@ ncuq() {  # workload, kernel regex, env...
   wl=$1; k=$2; shift; shift
   echo "== ncu $wl $k $*"
   env "$@" timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct \
-     --clock-control none -k regex:$k --launch-skip 3 -c 1 python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu 2>&1 \
+     --clock-control none -k regex:$k --launch-skip ${SKIP:-3} -c ${CNT:-1} python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu 2>&1 \
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "bspmv" 2>&1 | tail -2
-run bspmv X=0
-run bspmv TACO_B200_BSPMV_VARIANT=1
-ncuq bspmv bspmv_warp X=0
-} > gpurun_out/exp_15.txt 2>&1
-cat gpurun_out/exp_15.txt
+echo skip-tests
+run spmm X=0
+run spmm TACO_B200_SPMM_OVERLAP=0
+run spmm TACO_B200_SPMM_LONGVAR=1
+run spmm TACO_B200_SPMM_LONGVAR=2
+run spmm TACO_B200_SPMM_LONGVAR=3
+run spmm TACO_B200_SPMM_LONGVAR=4
+run spmm TACO_B200_SPMM_LONG=128
+run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_LONGVAR=3
+run spmm TACO_B200_SPMM_LONG=64
+run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_VARIANT=4
+run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_VARIANT=1
+run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_OVERLAP=0
+SKIP=21 CNT=7 ncuq spmm "spmm_" TACO_B200_SPMM_LONG=128
+run spmv X=0
+} > gpurun_out/exp_r2_2.txt 2>&1
+cat gpurun_out/exp_r2_2.txt

@@ -3,7 +3,10 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from taco_b200 import synth, tbin
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import synth
+import tbin
 out = sys.argv[1] if len(sys.argv) > 1 else "/dev/shm"
 for wl in (() if len(sys.argv) > 2 else ("spmv", "spmm")):
     w = synth.make(wl, "cuda")
