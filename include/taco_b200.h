@@ -197,6 +197,10 @@ int _shim_taco_b200_pack(void** p);
  * pattern -- there is no CPU fallback. */
 typedef struct taco_b200_module taco_b200_module_t;
 taco_b200_module_t* taco_b200_module_open(const char* expr, const char* formats, const char* dtype);
+/* Same, with the order in which the caller will pack the tensors given explicitly (comma separated names; NULL = results
+ * first, then operands by first appearance in `expr` -- taco's own order, src/tensor.cpp:778-806).  The operands of a product
+ * or a sum commute: `y(i) = x(j) * A(i,j)` opens the spmv family and call_packed / the stub source reorder the pack. */
+taco_b200_module_t* taco_b200_module_open_args(const char* expr, const char* formats, const char* dtype, const char* args);
 const char* taco_b200_module_family(const taco_b200_module_t* m);   /* "spmv", "spmm", ... */
 int   taco_b200_module_num_args(const taco_b200_module_t* m);
 /* name in {"assemble","compute","evaluate"}; args = packed taco_tensor_t* exactly as Module::callFuncPacked */

@@ -67,6 +67,8 @@ lib.taco_b200_make_resident.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_invalidate.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_open.restype = ctypes.c_void_p
 lib.taco_b200_module_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+lib.taco_b200_module_open_args.restype = ctypes.c_void_p
+lib.taco_b200_module_open_args.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
 lib.taco_b200_module_family.restype = ctypes.c_char_p
 lib.taco_b200_module_family.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_num_args.argtypes = [ctypes.c_void_p]

@@ -8,6 +8,7 @@
 // the hand-written sm_100a kernel families, which are already resident in this library.  taco_b200_module_open() is
 // the cache lookup (keyed on the canonical statement string), taco_b200_module_call_packed() is callFuncPacked().
 // A statement that is not on the hot path is refused (TACO_B200_ERR_UNSUPPORTED) -- never run on the CPU.
+#include <algorithm>
 #include <cctype>
 #include <cstring>
 #include <map>
@@ -53,10 +54,11 @@ static const Family kFamilies[] = {
     {"bspmm",  "T0(a,b,c)=T1(a,d,b,e)*T2(d,e,c)",     {"ddd", "dsdd", "ddd", ""}, 3, TB_FAM3(bspmm)},
 };
 
-// "y(i) = A(i,j) * x(j)"  ->  canonical "T0(a)=T1(a,b)*T2(b)" + tensor names in order of first appearance
-static bool canonicalise(const std::string& expr, std::string* canon, std::vector<std::string>* tensors) {
-  std::map<std::string, int> tid, vid;
-  std::string out;
+// "y(i) = x(j) * A(i,j)"  ->  result access, operand accesses, operator
+struct Acc { std::string name; std::vector<std::string> vars; };
+struct Parsed { Acc lhs; std::vector<Acc> terms; char op = 0; };
+
+static bool parse_expr(const std::string& expr, Parsed* out) {
   size_t p = 0;
   auto skip = [&]() { while (p < expr.size() && isspace((unsigned char)expr[p])) p++; };
   auto ident = [&](std::string* s) {
@@ -68,39 +70,64 @@ static bool canonicalise(const std::string& expr, std::string* canon, std::vecto
   };
   bool first = true;
   while (true) {
-    std::string name;
-    if (!ident(&name)) return false;
-    if (!tid.count(name)) { int id = (int)tid.size(); tid[name] = id; tensors->push_back(name); }
-    out += "T" + std::to_string(tid[name]);
+    Acc a;
+    if (!ident(&a.name)) return false;
     skip();
     if (p < expr.size() && expr[p] == '(') {
       p++;
-      out += "(";
-      bool firstv = true;
       while (true) {
         std::string v;
         if (!ident(&v)) return false;
-        if (!vid.count(v)) { int id = (int)vid.size(); vid[v] = id; }
-        if (!firstv) out += ",";
-        out += (char)('a' + vid[v]);
-        firstv = false;
+        a.vars.push_back(v);
         skip();
         if (p < expr.size() && expr[p] == ',') { p++; continue; }
         if (p < expr.size() && expr[p] == ')') { p++; break; }
         return false;
       }
-      out += ")";
     }
+    if (first) out->lhs = a; else out->terms.push_back(a);
     skip();
     if (p >= expr.size()) break;
-    char c = expr[p];
-    if (first && c == '=') { out += "="; p++; first = false; continue; }
-    if (first && c == '+' && p + 1 < expr.size() && expr[p + 1] == '=') { out += "="; p += 2; first = false; continue; }
-    if (!first && (c == '*' || c == '+')) { out += c; p++; continue; }
+    const char c = expr[p];
+    if (first && c == '=') { p++; first = false; continue; }
+    if (first && c == '+' && p + 1 < expr.size() && expr[p + 1] == '=') { p += 2; first = false; continue; }
+    if (!first && (c == '*' || c == '+')) {
+      if (out->op && out->op != c) return false;          // products or sums, not mixtures
+      out->op = c;
+      p++;
+      continue;
+    }
     return false;
   }
-  *canon = out;
-  return !first;
+  return !first && !out->terms.empty();
+}
+
+// canonical text of the statement with its operands taken in the order `order`: tensors T0.. (T0 = result) and index
+// variables a,b,c.. are numbered by first appearance; `names` receives the tensor names in that numbering
+static std::string canonical(const Parsed& ps, const std::vector<int>& order, std::vector<std::string>* names) {
+  std::map<std::string, int> tid, vid;
+  names->clear();
+  std::string out;
+  auto emit = [&](const Acc& a) {
+    if (!tid.count(a.name)) { const int id = (int)tid.size(); tid[a.name] = id; names->push_back(a.name); }
+    out += "T" + std::to_string(tid[a.name]);
+    if (!a.vars.empty()) {
+      out += "(";
+      for (size_t v = 0; v < a.vars.size(); v++) {
+        if (!vid.count(a.vars[v])) { const int id = (int)vid.size(); vid[a.vars[v]] = id; }
+        out += (v ? "," : "");
+        out += (char)('a' + vid[a.vars[v]]);
+      }
+      out += ")";
+    }
+  };
+  emit(ps.lhs);
+  out += "=";
+  for (size_t t = 0; t < order.size(); t++) {
+    if (t) out += ps.op ? ps.op : '*';
+    emit(ps.terms[order[t]]);
+  }
+  return out;
 }
 
 // "A:ds,x:d,C:dd:1,0" -> per tensor (levels, ordering string)
@@ -133,6 +160,8 @@ static void parse_formats(const char* formats, std::map<std::string, std::pair<s
 struct taco_b200_module {
   const tb::Family* fam;
   std::string key;
+  int perm[4];           // family argument a is the caller's argument perm[a]
+  bool identity;
   std::string stub;      // lazily built C source for TensorBase::compileSource()
 };
 
@@ -143,62 +172,106 @@ static std::map<std::string, taco_b200_module*> g_mod_cache;   // canonical stat
 
 extern "C" {
 
-taco_b200_module_t* taco_b200_module_open(const char* expr, const char* formats, const char* dtype) {
+// The operands of a product (or sum) commute: `y(i) = x(j) * A(i,j)` is SpMV with its arguments in another order.  Every
+// order of the operands is tried against the family table; the module remembers how the caller's argument pack -- results
+// first, then operands by first appearance, as taco packs them (src/tensor.cpp:778-806), or the explicit `args` list -- maps
+// onto the family's signature.  (Reordering a product changes the association of floating-point products: permuted SDDMM /
+// MTTKRP statements are within the tolerance of the reference's order, not bit-identical to it.)
+taco_b200_module_t* taco_b200_module_open_args(const char* expr, const char* formats, const char* dtype, const char* args) {
   if (!expr) { fail(TACO_B200_ERR_ARG, "module_open: NULL expression"); return nullptr; }
   std::string dt = dtype ? dtype : "f64";
-  if (dt != "f32" && dt != "f64" && dt != "float" && dt != "double") {
+  if (dt == "float") dt = "f32";
+  if (dt == "double") dt = "f64";
+  if (dt != "f32" && dt != "f64") {
     fail(TACO_B200_ERR_UNSUPPORTED, "component type '%s' is not on the GPU hot path (f32 / f64 only)", dt.c_str());
     return nullptr;
   }
-  std::string canon;
-  std::vector<std::string> tensors;
-  if (!canonicalise(expr, &canon, &tensors)) {
+  Parsed ps;
+  if (!parse_expr(expr, &ps) || ps.terms.size() > 3) {
     fail(TACO_B200_ERR_UNSUPPORTED, "cannot parse '%s' as  result(vars) = access {*|+} access ...", expr);
     return nullptr;
   }
+  std::vector<int> order(ps.terms.size());
+  for (size_t t = 0; t < order.size(); t++) order[t] = (int)t;
+  std::vector<std::string> given;                       // the caller's argument order
+  const std::string canon_given = canonical(ps, order, &given);
+  if (args && *args) {
+    given.clear();
+    std::string a(args), cur;
+    for (size_t q = 0; q <= a.size(); q++) {
+      if (q == a.size() || a[q] == ',') {
+        while (!cur.empty() && isspace((unsigned char)cur.back())) cur.pop_back();
+        while (!cur.empty() && isspace((unsigned char)cur[0])) cur.erase(0, 1);
+        if (!cur.empty()) given.push_back(cur);
+        cur.clear();
+      } else cur += a[q];
+    }
+  }
   std::map<std::string, std::pair<std::string, std::string>> fm;
   parse_formats(formats, &fm);
-  std::string key = canon + "|" + (formats ? formats : "") + "|" + dt;
+  std::string key = canon_given + "|" + (formats ? formats : "") + "|" + dt + "|";
+  for (const std::string& g : given) key += g + ",";
   {
     std::lock_guard<std::mutex> lk(g_mod_mu);
     auto it = g_mod_cache.find(key);
     if (it != g_mod_cache.end()) return it->second;
   }
-  for (const Family& f : kFamilies) {
-    if (canon != f.canon || (int)tensors.size() != f.nargs) continue;
-    bool ok = true;
-    for (int a = 0; a < f.nargs && ok; a++) {
-      auto it = fm.find(tensors[a]);
-      std::string lv = it == fm.end() ? std::string(strlen(f.formats[a]), 'd') : it->second.first;
-      if (it == fm.end() && lv != f.formats[a]) ok = false;        // unlisted tensors are dense
-      else if (lv != f.formats[a]) ok = false;
-      if (ok && a == 1 && f.arg1_ordering) {       // this family needs the sparse operand in a specific (non-identity) ordering
-        if (it == fm.end() || it->second.second != f.arg1_ordering) ok = false;
-        continue;
+  std::string tried;
+  do {
+    std::vector<std::string> tensors;
+    const std::string canon = canonical(ps, order, &tensors);
+    if (tried.find(canon) == std::string::npos) tried += (tried.empty() ? "" : " | ") + canon;
+    for (const Family& f : kFamilies) {
+      if (canon != f.canon || (int)tensors.size() != f.nargs) continue;
+      bool ok = true;
+      for (int a = 0; a < f.nargs && ok; a++) {
+        auto it = fm.find(tensors[a]);
+        std::string lv = it == fm.end() ? std::string(strlen(f.formats[a]), 'd') : it->second.first;   // unlisted tensors are dense
+        if (lv != f.formats[a]) ok = false;
+        if (ok && a == 1 && f.arg1_ordering) {       // this family needs the sparse operand in a specific (non-identity) ordering
+          if (it == fm.end() || it->second.second != f.arg1_ordering) ok = false;
+          continue;
+        }
+        if (ok && it != fm.end() && !it->second.second.empty()) {
+          // only the spmm result may carry a non-identity mode ordering (the reference GPU test's column-major C)
+          std::string ident;
+          for (size_t l = 0; l < lv.size(); l++) ident += (l ? "," : "") + std::to_string(l);
+          if (it->second.second != ident && !((std::string(f.name) == "spmm" || std::string(f.name) == "spmm_dcsr") && a == 0 && it->second.second == "1,0")) ok = false;
+        }
       }
-      if (ok && it != fm.end() && !it->second.second.empty()) {
-        // only the spmm result may carry a non-identity mode ordering (the reference GPU test's column-major C)
-        std::string ident;
-        for (size_t l = 0; l < lv.size(); l++) ident += (l ? "," : "") + std::to_string(l);
-        if (it->second.second != ident && !((std::string(f.name) == "spmm" || std::string(f.name) == "spmm_dcsr") && a == 0 && it->second.second == "1,0")) ok = false;
+      if (!ok) continue;
+      taco_b200_module* m = new taco_b200_module{&f, key, {0, 1, 2, 3}, true, ""};
+      bool mapped = (int)given.size() == f.nargs;
+      for (int a = 0; a < f.nargs && mapped; a++) {
+        int at = -1;
+        for (int g = 0; g < f.nargs; g++) if (given[g] == tensors[a]) at = g;
+        if (at < 0) mapped = false;
+        else { m->perm[a] = at; m->identity &= (at == a); }
       }
+      if (!mapped) {
+        delete m;
+        fail(TACO_B200_ERR_ARG, "module_open: the argument list '%s' does not name the %d tensors of '%s'", args ? args : "", f.nargs, expr);
+        return nullptr;
+      }
+      std::lock_guard<std::mutex> lk(g_mod_mu);
+      g_mod_cache[key] = m;
+      return m;
     }
-    if (!ok) continue;
-    taco_b200_module* m = new taco_b200_module{&f, key};
-    std::lock_guard<std::mutex> lk(g_mod_mu);
-    g_mod_cache[key] = m;
-    return m;
-  }
+  } while (std::next_permutation(order.begin(), order.end()));
   fail(TACO_B200_ERR_UNSUPPORTED,
-       "statement '%s' with formats '%s' is not a GPU hot-path pattern (canonical form %s); no CPU fallback exists",
-       expr, formats ? formats : "", canon.c_str());
+       "statement '%s' with formats '%s' is not a GPU hot-path pattern (canonical forms tried: %s); no CPU fallback exists",
+       expr, formats ? formats : "", tried.c_str());
   return nullptr;
+}
+
+taco_b200_module_t* taco_b200_module_open(const char* expr, const char* formats, const char* dtype) {
+  return taco_b200_module_open_args(expr, formats, dtype, nullptr);
 }
 
 const char* taco_b200_module_family(const taco_b200_module_t* m) { return m ? m->fam->name : nullptr; }
 int taco_b200_module_num_args(const taco_b200_module_t* m) { return m ? m->fam->nargs : 0; }
 
-void* taco_b200_module_get_func_ptr(taco_b200_module_t* m, const char* name) {
+static void* module_func(taco_b200_module_t* m, const char* name) {
   if (!m || !name) return nullptr;
   if (!strcmp(name, "assemble")) return m->fam->assemble;
   if (!strcmp(name, "compute")) return m->fam->compute;
@@ -206,14 +279,23 @@ void* taco_b200_module_get_func_ptr(taco_b200_module_t* m, const char* name) {
   return nullptr;
 }
 
+void* taco_b200_module_get_func_ptr(taco_b200_module_t* m, const char* name) {
+  if (m && !m->identity) {        // a raw entry point cannot reorder its arguments: use call_packed or the stub source
+    fail(TACO_B200_ERR_UNSUPPORTED, "module_get_func_ptr: the statement's operands are permuted with respect to the %s kernel", m->fam->name);
+    return nullptr;
+  }
+  return module_func(m, name);
+}
+
 int taco_b200_module_call_packed(taco_b200_module_t* m, const char* name, void** args) {
   if (!m) return fail(TACO_B200_ERR_ARG, "module_call_packed: NULL module");
-  void* f = taco_b200_module_get_func_ptr(m, name);
+  void* f = module_func(m, name);
   if (!f) return fail(TACO_B200_ERR_ARG, "module has no function '%s'", name ? name : "(null)");
   if (!args) return fail(TACO_B200_ERR_ARG, "module_call_packed: NULL argument pack");
+  const int* p = m->perm;
   if (m->fam->nargs == 3)
-    return ((fn3_t)f)((taco_tensor_t*)args[0], (taco_tensor_t*)args[1], (taco_tensor_t*)args[2]);
-  return ((fn4_t)f)((taco_tensor_t*)args[0], (taco_tensor_t*)args[1], (taco_tensor_t*)args[2], (taco_tensor_t*)args[3]);
+    return ((fn3_t)f)((taco_tensor_t*)args[p[0]], (taco_tensor_t*)args[p[1]], (taco_tensor_t*)args[p[2]]);
+  return ((fn4_t)f)((taco_tensor_t*)args[p[0]], (taco_tensor_t*)args[p[1]], (taco_tensor_t*)args[p[2]], (taco_tensor_t*)args[p[3]]);
 }
 
 void taco_b200_module_close(taco_b200_module_t*) { /* modules are cached for the process lifetime */ }
@@ -232,7 +314,7 @@ const char* taco_b200_module_stub_source(taco_b200_module_t* m) {
   std::string params, args, types;
   for (int a = 0; a < n; a++) {
     params += std::string(a ? ", " : "") + "taco_tensor_t* t" + std::to_string(a);
-    args += std::string(a ? ", " : "") + "t" + std::to_string(a);
+    args += std::string(a ? ", " : "") + "t" + std::to_string(m->perm[a]);      // the caller's order -> the kernel's order
     types += std::string(a ? ", " : "") + "taco_tensor_t*";
   }
   std::string src =

@@ -33,7 +33,30 @@ def test_bench_line_contract(wl):
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
 
 
+def test_bench_default_line_carries_the_three_headline_workloads():
+    j = _line([])
+    assert j["metric"] == "spmm_gflops" and j["scaling"] == "strong"
+    assert set(j["workloads"]) == {"spmv", "mttkrp"}
+    for rec in j["workloads"].values():
+        assert rec["value"] > 0 and rec["gpu_launches"] > 0 and rec["e2e"]["h2d_bytes_per_step"] > 0
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rec["roofline"])
+        assert rec["cpu_baseline"]["kind"] in ("reference", "port")
+
+
 def test_bench_reference_arm_contract():
     j = _line(["--impl", "reference"])
     assert j["impl"] == "reference" and j["value"] > 0 and j["e2e"]["h2d_bytes_per_step"] == 0
     assert j["cpu_baseline"]["value"] == j["value"] and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["sample"] == "the full configuration"
+    assert set(j["workloads"]) == {"spmv", "mttkrp"}
+    ours = _line(["--workload", "spmm", "--no-e2e", "--no-cpu"])
+    assert ours["config"] == j["config"], "both arms must describe the same configuration"
+
+
+def test_reference_arm_does_not_load_the_product_library():
+    code = ("import sys, runpy\n"
+            "sys.argv=['bench.py','--impl','reference','--small','--steps','1','--warmup','0','--workload','spmv']\n"
+            "try:\n    runpy.run_path(%r, run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "print('MAPPED', 'libtaco_b200' in open('/proc/self/maps').read(), 'taco_b200' in sys.modules)\n") % os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "MAPPED False False" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]

@@ -22,20 +22,10 @@ ncuq() {  # workload, kernel regex, env...
      | grep -E "dram__|gpu__time|hit_rate|void " 
 }
 {
-echo skip-tests
+timeout 1500 python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu_gpu.py tests/test_bench_contract_gpu.py -m gpu -q -x 2>&1 | tail -8
 run spmm X=0
-run spmm TACO_B200_SPMM_OVERLAP=0
-run spmm TACO_B200_SPMM_LONGVAR=1
-run spmm TACO_B200_SPMM_LONGVAR=2
-run spmm TACO_B200_SPMM_LONGVAR=3
-run spmm TACO_B200_SPMM_LONGVAR=4
-run spmm TACO_B200_SPMM_LONG=128
-run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_LONGVAR=3
-run spmm TACO_B200_SPMM_LONG=64
-run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_VARIANT=4
-run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_VARIANT=1
-run spmm TACO_B200_SPMM_LONG=128 TACO_B200_SPMM_OVERLAP=0
-SKIP=21 CNT=7 ncuq spmm "spmm_" TACO_B200_SPMM_LONG=128
-run spmv X=0
-} > gpurun_out/exp_r2_2.txt 2>&1
-cat gpurun_out/exp_r2_2.txt
+SKIP=24 CNT=8 ncuq spmm "spmm_" X=0
+timeout 900 python bench.py --steps 10 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.err
+timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.err
+} > gpurun_out/exp_r2_3.txt 2>&1
+cat gpurun_out/exp_r2_3.txt
