@@ -51,7 +51,7 @@ static int view_bcsr(const taco_tensor_t* t, const char* name, BcsrView* v) {
 // number of stored blocks: pos[Mb] (device-resident tensors carry it in vals_size = blocks * br * bc)
 static int bcsr_nnzb(const BcsrView& A, int32_t vals_size_hint, int32_t* nnzb) {
   if (!A.pos) return fail(TACO_B200_ERR_ARG, "blocked CSR operand has no pos array");
-  if (classify(A.pos) == Mem::Device && vals_size_hint > 0) { *nnzb = vals_size_hint / (A.br * A.bc); return TACO_B200_OK; }
+  if (vals_size_hint > 0 && trusts_vals_size(A.pos)) { *nnzb = vals_size_hint / (A.br * A.bc); return TACO_B200_OK; }
   return read_i32(A.pos + A.Mb, nnzb);
 }
 

@@ -38,6 +38,10 @@ int result_space();
 
 enum class Mem { Host, Pinned, Device };
 Mem classify(const void* p);
+// true only for plain device memory (cudaMalloc / pool): the one case where the vals_size convention of taco_b200.h applies.
+// Managed memory classifies as Device (the kernels can dereference it) but is what the REFERENCE allocates with unified
+// memory on, and the reference never initialises vals_size (src/taco_tensor_t.cpp:32-67): sizes are read from pos[] there.
+bool trusts_vals_size(const void* p);
 
 // A read-only operand array made visible to the device for the duration of one call.
 // dev() is usable on stream() after acquire(); release happens in the destructor (stream-ordered free).
@@ -74,6 +78,26 @@ struct ProfScope {
 // stream-ordered scratch
 int scratch_alloc(void** p, size_t bytes);
 void scratch_free(void* p);
+// owns the scratch buffers and events of a multi-stream pipeline: released on every exit path (early error returns included)
+struct PipelineGuard {
+  void* bufs[16];
+  cudaEvent_t evs[4];
+  int nbufs = 0, nevs = 0;
+  ~PipelineGuard() {
+    for (int i = 0; i < nbufs; i++) scratch_free(bufs[i]);
+    for (int i = 0; i < nevs; i++) cudaEventDestroy(evs[i]);
+  }
+  int alloc(void** p, size_t bytes) {
+    const int rc = scratch_alloc(p, bytes);
+    if (rc == TACO_B200_OK && nbufs < 16) bufs[nbufs++] = *p;
+    return rc;
+  }
+  int event(cudaEvent_t* e) {
+    if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail(TACO_B200_ERR_CUDA, "cudaEventCreate failed");
+    if (nevs < 4) evs[nevs++] = *e;
+    return TACO_B200_OK;
+  }
+};
 
 // result allocation in the configured result space (HOST: malloc, DEVICE: cudaMalloc)
 void* result_alloc(size_t bytes);

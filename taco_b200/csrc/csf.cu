@@ -127,11 +127,15 @@ csf3_ttv_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, 
 // The leaf level is cut into slots of MK_W leaves; slot w (one warp) OWNS the mode-0 slices whose first leaf lies in
 // [w*W,(w+1)*W) and computes their rows of A completely in registers (lane <-> rank column), storing each row once:
 // no atomics, no zero-fill pass, summation in leaf order with the reference association (B*C)*D => bit-identical to
-// the reference's C kernel.  Only slices longer than MK_LONG leaves are split across the slots they span (partials
-// combined with red.global.add into a row the pre-pass zeroed).  Per 32 leaves: one coalesced load of B3_crd / B_vals,
-// the fiber of each leaf from a guessed position (exact when fibers are singletons) or a binary search in the slice's
-// B3_pos window, (k, l, val) staged in shared memory and read back as one 16-byte broadcast per leaf, U leaves = 2U
-// independent factor-row gathers in flight per warp.
+// the reference's C kernel.  Only slices longer than MK_LONG leaves are split across the slots they span; their pieces are
+// added into the row IN SLOT ORDER (the owner stores its piece, every later piece waits for its predecessor's flag, adds,
+// and raises its own), so the result does not depend on scheduling: run-to-run deterministic, no atomics on values.
+// Slot numbers are handed out by a ticket per CTA, so a piece's predecessor has always started -- the chain cannot deadlock
+// whatever order the hardware dispatches CTAs in.  Per 32 leaves: one coalesced load of B3_crd / B_vals, the fiber of each
+// leaf from a guessed position (exact when fibers are singletons) or a binary search in the slice's B3_pos window,
+// (k, l, val) staged in shared memory and read back as one 16-byte broadcast per leaf.  The row C(k,:) is gathered once
+// per FIBER, not per leaf (the reference's `w` workspace of scheduleMTTKRPCPU): consecutive leaves
+// of a fiber share k, so only D(l,:) is gathered for them.
 constexpr int MK_W = 64;
 constexpr int MK_LONG = 512;
 
@@ -153,11 +157,8 @@ __device__ __forceinline__ void st_stream(T* p, T v, uint64_t strm) {
 }
 
 // slot_slices[w] = first slice s (0..nslices) whose first leaf B3_pos[B2_pos[s]] is >= w*W; slot_slices[nslots] = nslices.
-// Also zeroes the A row of every hub slice (by the slot in which the slice's first slot boundary falls).
-template <typename T>
-__global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd,
-                                          const int* __restrict__ B2_pos, const int* __restrict__ B3_pos, int nnz, int nslots,
-                                          int R, int* __restrict__ slot_slices, T* __restrict__ A) {
+__global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B2_pos,
+                                          const int* __restrict__ B3_pos, int nslots, int* __restrict__ slot_slices) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w > nslots) return;
   const int s_base = __ldg(B1_pos), nslices = __ldg(B1_pos + 1) - s_base;
@@ -169,15 +170,6 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
     if (__ldg(B3_pos + __ldg(B2_pos + s_base + mid)) >= target) end = mid; else lo = mid + 1;
   }
   slot_slices[w] = lo;
-  if (target < nnz && lo > 0) {
-    // slice lo-1 starts before `target`; if it is a hub slice and this is its first slot boundary, zero its row
-    const int s = s_base + lo - 1;
-    const int l0 = __ldg(B3_pos + __ldg(B2_pos + s)), l1 = __ldg(B3_pos + __ldg(B2_pos + s + 1));
-    if (l1 > target && l1 - l0 > MK_LONG && target - l0 <= MK_W) {
-      T* row = A + (size_t)__ldg(B1_crd + s) * R;
-      for (int j = 0; j < R; j++) row[j] = T(0);
-    }
-  }
 }
 
 struct MkSlice { int f0, f1, l0, l1, row, zlo; };   // fibers, leaves, row of A, first row to zero before `row`
@@ -187,11 +179,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
-                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices) {
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain) {
   __shared__ MkLeaf<T> stage_all[WARPS][32];
   __shared__ MkSlice meta_all[WARPS][32];
+  __shared__ int s_ticket;
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  // chain[0] = CTA ticket, chain[1 + w] = "the pieces of a hub slice up to slot w are in the row" flag (zeroed per launch)
+  if (threadIdx.x == 0) s_ticket = atomicAdd(chain, 1);
+  __syncthreads();
+  const int w = s_ticket * WARPS + (threadIdx.x >> 5);
+  int* const flags = chain + 1;
   if (w >= nslots) return;
   MkLeaf<T>* stage = stage_all[threadIdx.x >> 5];
   MkSlice* meta = meta_all[threadIdx.x >> 5];
@@ -201,13 +198,15 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
   const int s_base = __ldg(B1_pos), nslices = __ldg(B1_pos + 1) - s_base;
   const int S0 = __ldg(slot_slices + w), S1 = __ldg(slot_slices + w + 1);
 
-  // group -1 (optional): the piece [lo, min(hi, end)) of a hub slice that started in an earlier slot (added atomically);
+  // group -1 (optional): the piece [lo, min(hi, end)) of a hub slice that started in an earlier slot (added in slot order);
   // groups 0..: the slices this slot owns, 32 at a time (metadata parked in shared memory, one broadcast read per slice)
   bool tail = false;
+  int tail_end = 0;                        // where that hub slice really ends
   if (S0 > 0 && lo < nnz) {
     const int f0 = __ldg(B2_pos + s_base + S0 - 1), f1 = __ldg(B2_pos + s_base + S0);
     const int l0 = __ldg(B3_pos + f0), l1 = __ldg(B3_pos + f1);
     tail = l1 > lo && l1 - l0 > MK_LONG;
+    tail_end = l1;
     if (tail && lane == 0) meta[0] = MkSlice{f0, f1, lo, min(hi, l1), __ldg(B1_crd + s_base + S0 - 1), -1};
   }
   for (int sb = tail ? S0 - 32 : S0; sb < S1; sb += 32) {
@@ -244,6 +243,8 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
         const T* Cj = C + (active ? j0 + lane : 0);
         const T* Dj = D + (active ? j0 + lane : 0);
         T acc = T(0);
+        int ck = -1;                       // the fiber row of C held in `cfib` (consecutive leaves of a fiber share k)
+        T cfib = T(0);
         for (int pb = m.l0; pb < l1; pb += 32) {
           const int cnt = min(32, l1 - pb);
           if (lane < cnt) {
@@ -264,7 +265,8 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
             for (int u = 0; u < U; u++) {
               const MkLeaf<T> e = stage[q + u];
               vv[u] = e.v;
-              cv[u] = __ldg(Cj + (size_t)e.k * R);
+              if (e.k != ck) { ck = e.k; cfib = __ldg(Cj + (size_t)e.k * R); }       // warp-uniform: a new fiber
+              cv[u] = cfib;
               dv[u] = __ldg(Dj + (size_t)e.l * R);
             }
 #pragma unroll
@@ -272,15 +274,26 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
           }
           for (; q < cnt; q++) {
             const MkLeaf<T> e = stage[q];
-            acc = acc + (e.v * __ldg(Cj + (size_t)e.k * R)) * __ldg(Dj + (size_t)e.l * R);
+            if (e.k != ck) { ck = e.k; cfib = __ldg(Cj + (size_t)e.k * R); }
+            acc = acc + (e.v * cfib) * __ldg(Dj + (size_t)e.l * R);
           }
           __syncwarp();
         }
+        if (is_tail && j0 == 0) {                          // a later piece of a hub slice: wait for the pieces before it
+          if (lane == 0) while (atomicAdd(flags + w - 1, 0) == 0) __nanosleep(64);
+          __syncwarp();
+          __threadfence();
+        }
         if (active) {
           T* dst = A + (size_t)m.row * R + j0 + lane;
-          if (hub) atomicAdd(dst, acc);
-          else *dst = acc;
+          if (is_tail) *dst = __ldcg(dst) + acc;           // pieces are added in slot order: deterministic
+          else *dst = acc;                                 // whole slices, and the owner's (first) piece of a hub slice
         }
+      }
+      if (hub && (is_tail ? tail_end > hi : true)) {       // more pieces follow in the next slot: publish this one
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(flags + w, 1);
       }
     }
   }
@@ -304,7 +317,7 @@ static int csf_prepare(taco_tensor_t* Bt, CsfCall* cc) {
   TB_TRY(read_i32(cc->B.pos[0] + 1, &cc->nslices));
   cc->nslices -= p10;
   TB_TRY(read_i32(cc->B.pos[1] + cc->nslices, &cc->nfib));
-  if (classify(cc->B.pos[2]) == Mem::Device && Bt->vals_size > 0) cc->nnz = Bt->vals_size;
+  if (Bt->vals_size > 0 && trusts_vals_size(cc->B.pos[2])) cc->nnz = Bt->vals_size;
   else TB_TRY(read_i32(cc->B.pos[2] + cc->nfib, &cc->nnz));
   if (cc->nslices < 0 || cc->nfib < 0 || cc->nnz < 0) return fail(TACO_B200_ERR_ARG, "csf: corrupt pos arrays");
   cc->host_described = true;
@@ -343,7 +356,7 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
 }
 
 template <typename T, int U, int WARPS, int MINB>
-static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices) {
+static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain) {
   const dim3 grid((nslots + WARPS - 1) / WARPS);
   // The single-pass specialisation (R <= 32) spills less but measures SLOWER at C4 (23.1 vs 16.7 ms, same box, A/B):
   // ptxas unrolls the leaf loop of the general version four deep, which is what keeps HBM at 98 % of its peak.
@@ -351,11 +364,11 @@ static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslo
   if (R <= 32 && single)
     mttkrp_csf_kernel<T, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain);
   else
     mttkrp_csf_kernel<T, U, WARPS, MINB, false><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain);
 }
 
 template <typename T>
@@ -370,22 +383,29 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
   const int nslots = (cc.nnz + MK_W - 1) / MK_W;
   void* slot_slices = nullptr;
   TB_TRY(scratch_alloc(&slot_slices, sizeof(int) * (size_t)(nslots + 1)));
-  mttkrp_slot_slices_kernel<T><<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(
-      cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.p3.as<int>(), cc.nnz, nslots, R, (int*)slot_slices, A);
+  mttkrp_slot_slices_kernel<<<(nslots + 1 + 255) / 256, 256, 0, stream()>>>(cc.p1.as<int>(), cc.p2.as<int>(), cc.p3.as<int>(), nslots,
+                                                                           (int*)slot_slices);
+  void* chain = nullptr;                      // CTA ticket + one flag per slot (only hub slices ever touch the flags)
+  if (scratch_alloc(&chain, sizeof(int) * ((size_t)nslots + 1)) != TACO_B200_OK) { scratch_free(slot_slices); return TACO_B200_ERR_ALLOC; }
+  if (cudaMemsetAsync(chain, 0, sizeof(int) * ((size_t)nslots + 1), stream()) != cudaSuccess) {
+    scratch_free(chain); scratch_free(slot_slices);
+    return fail(TACO_B200_ERR_CUDA, "mttkrp: memset failed");
+  }
   static const int variant = getenv("TACO_B200_MTTKRP_VARIANT") ? atoi(getenv("TACO_B200_MTTKRP_VARIANT")) : 0;
   {
     ProfScope ps("mttkrp_csf");
     const int* ss = (const int*)slot_slices;
     switch (variant) {
-      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss); break;
-      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss); break;
-      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss); break;
-      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss); break;
-      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss); break;
-      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss); break;
+      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
     }
   }
   count_launch(2);
+  scratch_free(chain);
   scratch_free(slot_slices);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
@@ -420,17 +440,20 @@ static int mttkrp_compute_pipelined(CsfCall& cc, const T* C, const T* D, T* host
   cudaStream_t main = stream(), up = aux_stream(0), down = aux_stream(1);
   const int nchunks = 16;
   void *d_p1 = nullptr, *d_c1 = nullptr, *d_p2 = nullptr, *d_c2 = nullptr, *d_p3 = nullptr, *d_c3 = nullptr, *d_vals = nullptr, *dA = nullptr;
-  TB_TRY(scratch_alloc(&d_p1, sizeof(int) * 2 * nchunks));
-  TB_TRY(scratch_alloc(&d_c1, sizeof(int) * (size_t)ns));
-  TB_TRY(scratch_alloc(&d_p2, sizeof(int) * ((size_t)ns + nchunks)));       // chunk c lives at offset s0 + c (own closing entry)
-  TB_TRY(scratch_alloc(&d_c2, sizeof(int) * (size_t)nf));
-  TB_TRY(scratch_alloc(&d_p3, sizeof(int) * ((size_t)nf + nchunks)));
-  TB_TRY(scratch_alloc(&d_c3, sizeof(int) * (size_t)nz));
-  TB_TRY(scratch_alloc(&d_vals, es * (size_t)nz));
-  TB_TRY(scratch_alloc(&dA, es * (size_t)I * R));
-  cudaEvent_t ready, done_all;
-  TB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  TB_CUDA(cudaEventCreateWithFlags(&done_all, cudaEventDisableTiming));
+  PipelineGuard guard;                              // scratch and events are released on every exit path
+  TB_TRY(guard.alloc(&d_p1, sizeof(int) * 2 * nchunks));
+  TB_TRY(guard.alloc(&d_c1, sizeof(int) * (size_t)ns));
+  TB_TRY(guard.alloc(&d_p2, sizeof(int) * ((size_t)ns + nchunks)));       // chunk c lives at offset s0 + c (own closing entry)
+  TB_TRY(guard.alloc(&d_c2, sizeof(int) * (size_t)nf));
+  TB_TRY(guard.alloc(&d_p3, sizeof(int) * ((size_t)nf + nchunks)));
+  TB_TRY(guard.alloc(&d_c3, sizeof(int) * (size_t)nz));
+  TB_TRY(guard.alloc(&d_vals, es * (size_t)nz));
+  TB_TRY(guard.alloc(&dA, es * (size_t)I * R));
+  cudaEvent_t ready, done_all, e_up, e_done;        // e_up / e_done are re-recorded per chunk
+  TB_TRY(guard.event(&ready));
+  TB_TRY(guard.event(&done_all));
+  TB_TRY(guard.event(&e_up));
+  TB_TRY(guard.event(&e_done));
   TB_CUDA(cudaEventRecord(ready, main));            // pool allocations and the C / D uploads are ordered on the compute stream
   TB_CUDA(cudaStreamWaitEvent(up, ready, 0));
   TB_CUDA(cudaStreamWaitEvent(down, ready, 0));
@@ -464,9 +487,6 @@ static int mttkrp_compute_pipelined(CsfCall& cc, const T* C, const T* D, T* host
     const int f0 = h_p2[s_base + s0], f1 = h_p2[s_base + s1], l0 = h_p3[f0], l1 = h_p3[f1];
     int* c1 = (int*)d_c1 + s0; int* p2 = (int*)d_p2 + s0 + c; int* c2 = (int*)d_c2 + f0; int* p3 = (int*)d_p3 + f0 + c;
     int* c3 = (int*)d_c3 + l0; T* vv = (T*)d_vals + l0;
-    cudaEvent_t e_up, e_done;
-    TB_CUDA(cudaEventCreateWithFlags(&e_up, cudaEventDisableTiming));
-    TB_CUDA(cudaEventCreateWithFlags(&e_done, cudaEventDisableTiming));
     if (s1 > s0) {
       TB_CUDA(cudaMemcpyAsync(c1, h_c1 + s_base + s0, sizeof(int) * (size_t)(s1 - s0), cudaMemcpyHostToDevice, up));
       TB_CUDA(cudaMemcpyAsync(p2, h_p2 + s_base + s0, sizeof(int) * (size_t)(s1 - s0 + 1), cudaMemcpyHostToDevice, up));
@@ -496,15 +516,9 @@ static int mttkrp_compute_pipelined(CsfCall& cc, const T* C, const T* D, T* host
     TB_CUDA(cudaStreamWaitEvent(down, e_done, 0));
     if (row1 > row0)
       TB_CUDA(cudaMemcpyAsync(hostA + (size_t)row0 * R, Achunk, es * (size_t)(row1 - row0) * R, cudaMemcpyDeviceToHost, down));
-    cudaEventDestroy(e_up);
-    cudaEventDestroy(e_done);
   }
   TB_CUDA(cudaEventRecord(done_all, down));
-  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));
-  cudaEventDestroy(ready);
-  cudaEventDestroy(done_all);
-  scratch_free(d_p1); scratch_free(d_c1); scratch_free(d_p2); scratch_free(d_c2); scratch_free(d_p3); scratch_free(d_c3);
-  scratch_free(d_vals); scratch_free(dA);
+  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));    // the guard's frees are ordered after the downloads
   TB_TRY(rc);
   TB_CUDA(cudaStreamSynchronize(main));
   return TACO_B200_OK;

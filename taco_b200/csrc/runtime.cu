@@ -145,6 +145,15 @@ Mem classify(const void* p) {
   }
 }
 
+bool trusts_vals_size(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice;
+}
+
 ProfScope::ProfScope(const char* kernel_name) {
   if (!g.profile) return;
   std::lock_guard<std::mutex> lk(g.mu);
@@ -194,6 +203,9 @@ int In::acquire(const void* p, size_t bytes) {
   dptr = owned;
   if (bytes >= (8u << 20) && m == Mem::Host) return h2d_pageable(owned, p, bytes);     // pageable operand (taco's malloc'ed arrays)
   if (bytes) TB_CUDA(cudaMemcpyAsync(owned, p, bytes, cudaMemcpyHostToDevice, g.cur_stream));
+  // a copy out of PINNED memory is truly asynchronous: the call must not return before the DMA has read the operand, or a
+  // caller that updates x / B for its next step would race with it (pageable sources are staged before the call returns)
+  if (bytes && m == Mem::Pinned) g_need_sync = true;
   return TACO_B200_OK;
 }
 

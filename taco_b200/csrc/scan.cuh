@@ -65,6 +65,45 @@ scan_add_kernel(int* __restrict__ out, const int* __restrict__ offsets, long lon
     if (base + k < n) out[base + k] += off;
 }
 
+// 64-bit total of n int32 counts (one atomic per CTA): the size of a sparse result BEFORE its int32 prefix sum, so that a
+// result with more than 2^31-1 entries is refused instead of wrapping negative and under-allocating crd / vals.
+static __global__ void __launch_bounds__(256)
+total_i64_kernel(const int* __restrict__ in, long long n, unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long warp_sums[8];
+  unsigned long long s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += (unsigned)in[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; w++) t += warp_sums[w];
+    if (t) atomicAdd(total, t);
+  }
+}
+
+// reads the total back (one synchronisation -- the caller needs the size on the host anyway) and refuses sizes beyond int32
+static int checked_total_i32(const int* counts, long long n, const char* what, int32_t* total_out) {
+  void* d = nullptr;
+  TB_TRY(scratch_alloc(&d, sizeof(unsigned long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), stream());
+  if (e != cudaSuccess) { scratch_free(d); return fail(TACO_B200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); }
+  if (n > 0) {
+    const long long ctas = (n + 2047) / 2048;
+    total_i64_kernel<<<(unsigned)(ctas < 1184 ? ctas : 1184), 256, 0, stream()>>>(counts, n, (unsigned long long*)d);
+    count_launch(1);
+  }
+  unsigned long long h = 0;
+  const int rc = read_back(&h, d, sizeof(h));
+  scratch_free(d);
+  TB_TRY(rc);
+  if (h > (unsigned long long)INT32_MAX)
+    return fail(TACO_B200_ERR_ARG, "%s: the result has %llu stored entries, more than int32 positions can address", what, h);
+  *total_out = (int32_t)h;
+  return TACO_B200_OK;
+}
+
 // exclusive scan of n int32 on the current stream; in and out may be the same buffer
 static int exclusive_scan_i32(const int* in, int* out, long long n) {
   if (n <= 0) return TACO_B200_OK;

@@ -925,11 +925,12 @@ static int publish_structure(taco_tensor_t* C, int n, int* dpos, int* dcrd, int3
     int32_t* hpos = (int32_t*)malloc(sizeof(int32_t) * ((size_t)n + 1));
     int32_t* hcrd = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnzC > 0 ? nnzC : 1));
     void* vals = malloc(esize * (size_t)(nnzC > 0 ? nnzC : 1));
-    if (!hpos || !hcrd || !vals) return fail(TACO_B200_ERR_ALLOC, "cannot allocate host result arrays");
-    TB_TRY(d2h_fresh(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1)));
-    if (nnzC) TB_TRY(d2h_fresh(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC));
-    if (nnzC && dvals) TB_TRY(d2h_fresh(vals, dvals, esize * (size_t)nnzC));
-    TB_CUDA(cudaStreamSynchronize(stream()));
+    int rc = (!hpos || !hcrd || !vals) ? fail(TACO_B200_ERR_ALLOC, "cannot allocate host result arrays") : TACO_B200_OK;
+    if (rc == TACO_B200_OK) rc = d2h_fresh(hpos, dpos, sizeof(int32_t) * ((size_t)n + 1));
+    if (rc == TACO_B200_OK && nnzC) rc = d2h_fresh(hcrd, dcrd, sizeof(int32_t) * (size_t)nnzC);
+    if (rc == TACO_B200_OK && nnzC && dvals) rc = d2h_fresh(vals, dvals, esize * (size_t)nnzC);
+    if (rc == TACO_B200_OK && cudaStreamSynchronize(stream()) != cudaSuccess) rc = fail(TACO_B200_ERR_CUDA, "stream synchronisation failed");
+    if (rc != TACO_B200_OK) { free(hpos); free(hcrd); free(vals); return rc; }
     device_result_free(dpos);
     device_result_free(dcrd);
     device_result_free(dvals);
@@ -956,7 +957,7 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* 
                                  !(getenv("TACO_B200_SPADD_VARIANT") && atoi(getenv("TACO_B200_SPADD_VARIANT")) >= 1 &&
                                    atoi(getenv("TACO_B200_SPADD_VARIANT")) <= 5);
   const size_t bound = (size_t)s.nnzA + (size_t)s.nnzB;
-  if (with_vals && onepass_on && n > 0 && bound > 0 && bound * (4 + sizeof(T)) <= ((size_t)8 << 30)) {
+  if (with_vals && onepass_on && n > 0 && bound > 0 && bound <= (size_t)INT32_MAX && bound * (4 + sizeof(T)) <= ((size_t)8 << 30)) {
     int* dcrd = nullptr;
     void* dvals = nullptr;
     TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * bound));
@@ -977,9 +978,9 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* 
   } else {
     TB_CUDA(cudaMemsetAsync(dpos, 0, sizeof(int), stream()));
   }
+  int32_t nnzC = 0;             // 64-bit total of the row counts first: refuses results beyond int32 instead of wrapping
+  if (checked_total_i32(dpos, n, "spadd", &nnzC) != TACO_B200_OK) { device_result_free(dpos); return TACO_B200_ERR_ARG; }
   TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
-  int32_t nnzC = 0;
-  TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
   int* dcrd = nullptr;
   TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
   void* dvals = nullptr;
@@ -1110,9 +1111,9 @@ static int spgemm_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T*
     }
   }
   TB_CUDA(cudaGetLastError());
+  int32_t nnzC = 0;             // 64-bit total of the row counts first: refuses results beyond int32 instead of wrapping
+  if (checked_total_i32(dpos, n, "spgemm", &nnzC) != TACO_B200_OK) { device_result_free(dpos); return TACO_B200_ERR_ARG; }
   TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
-  int32_t nnzC = 0;
-  TB_TRY(read_back(&nnzC, dpos + n, sizeof(int32_t)));
   int* dcrd = nullptr;
   TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
   void* dvals = nullptr;

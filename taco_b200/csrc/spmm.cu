@@ -606,15 +606,18 @@ static int spmm_compute_pipelined(const CsrView& Av, const DenseView& Bv, const 
   In bin;                                           // device-resident / registered B is used in place
   const bool b_host = classify(Bv.vals) != Mem::Device && !is_resident(Bv.vals, es * (size_t)Av.cols * K);
   void* dB = nullptr;
-  TB_TRY(scratch_alloc(&dpos, sizeof(int) * ((size_t)rows + 1)));
-  TB_TRY(scratch_alloc(&dcrd, sizeof(int) * (size_t)nnz));
-  TB_TRY(scratch_alloc(&dvals, es * (size_t)nnz));
-  TB_TRY(scratch_alloc(&dC, es * (size_t)rows * K));
-  if (b_host) TB_TRY(scratch_alloc(&dB, es * (size_t)Av.cols * K));
+  PipelineGuard guard;                              // scratch and events are released on every exit path
+  TB_TRY(guard.alloc(&dpos, sizeof(int) * ((size_t)rows + 1)));
+  TB_TRY(guard.alloc(&dcrd, sizeof(int) * (size_t)nnz));
+  TB_TRY(guard.alloc(&dvals, es * (size_t)nnz));
+  TB_TRY(guard.alloc(&dC, es * (size_t)rows * K));
+  if (b_host) TB_TRY(guard.alloc(&dB, es * (size_t)Av.cols * K));
   else { TB_TRY(bin.acquire(Bv.vals, es * (size_t)Av.cols * K)); dB = (void*)bin.dptr; }
-  cudaEvent_t ready, done_all;
-  TB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  TB_CUDA(cudaEventCreateWithFlags(&done_all, cudaEventDisableTiming));
+  cudaEvent_t ready, done_all, e_up, e_done;        // e_up / e_done are re-recorded per chunk (a wait captures the state at its call)
+  TB_TRY(guard.event(&ready));
+  TB_TRY(guard.event(&done_all));
+  TB_TRY(guard.event(&e_up));
+  TB_TRY(guard.event(&e_done));
   TB_CUDA(cudaEventRecord(ready, main));            // the pool allocations above are ordered on the compute stream
   TB_CUDA(cudaStreamWaitEvent(up, ready, 0));
   TB_CUDA(cudaStreamWaitEvent(down, ready, 0));
@@ -637,9 +640,6 @@ static int spmm_compute_pipelined(const CsrView& Av, const DenseView& Bv, const 
       r1 = lo;
     }
     const int p0 = Av.pos[r0], p1 = Av.pos[r1];
-    cudaEvent_t e_up, e_done;
-    TB_CUDA(cudaEventCreateWithFlags(&e_up, cudaEventDisableTiming));
-    TB_CUDA(cudaEventCreateWithFlags(&e_done, cudaEventDisableTiming));
     if (p1 > p0) {
       TB_CUDA(cudaMemcpyAsync((int*)dcrd + p0, Av.crd + p0, sizeof(int) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, up));
       TB_CUDA(cudaMemcpyAsync((T*)dvals + p0, (const T*)Av.vals + p0, es * (size_t)(p1 - p0), cudaMemcpyHostToDevice, up));
@@ -652,16 +652,10 @@ static int spmm_compute_pipelined(const CsrView& Av, const DenseView& Bv, const 
     TB_CUDA(cudaStreamWaitEvent(down, e_done, 0));
     TB_CUDA(cudaMemcpyAsync((T*)Cv.vals + (size_t)r0 * K, (const T*)dC + (size_t)r0 * K, es * (size_t)(r1 - r0) * K,
                             cudaMemcpyDeviceToHost, down));
-    cudaEventDestroy(e_up);
-    cudaEventDestroy(e_done);
     r0 = r1;
   }
   TB_CUDA(cudaEventRecord(done_all, down));
-  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));  // frees below (and the caller's sync) are ordered after the downloads
-  cudaEventDestroy(ready);
-  cudaEventDestroy(done_all);
-  scratch_free(dpos); scratch_free(dcrd); scratch_free(dvals); scratch_free(dC);
-  if (b_host) scratch_free(dB);
+  TB_CUDA(cudaStreamWaitEvent(main, done_all, 0));  // the guard's frees (and the caller's sync) are ordered after the downloads
   TB_TRY(rc);
   TB_CUDA(cudaStreamSynchronize(main));
   return TACO_B200_OK;
@@ -739,7 +733,7 @@ int taco_b200_spmm_dcsr_compute(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_
   TB_TRY(read_i32(Av.pos0, &first));
   TB_TRY(read_i32(Av.pos0 + 1, &stored));
   if (first != 0 || stored < 0 || stored > Av.rows) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: bad level-0 pos {%d, %d}", first, stored);
-  if (classify(Av.pos1) == Mem::Device && A->vals_size > 0) nnz = A->vals_size;
+  if (A->vals_size > 0 && trusts_vals_size(Av.pos1)) nnz = A->vals_size;
   else TB_TRY(read_i32(Av.pos1 + stored, &nnz));
   if (nnz < 0 || nnz > INT32_MAX - 65536) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: bad nnz %d", nnz);
   if (stored > 0 && !Av.crd0) return fail(TACO_B200_ERR_ARG, "spmm_dcsr: level 0 has no crd array");

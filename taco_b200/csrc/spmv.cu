@@ -308,7 +308,7 @@ int spmv_mapped(DType dt, const int* pos, const int* crd, const void* vals, cons
 
 int csr_nnz(const CsrView& A, int32_t vals_size_hint, int32_t* nnz) {
   if (!A.pos) return fail(TACO_B200_ERR_ARG, "CSR operand has no pos array");
-  if (classify(A.pos) == Mem::Device && vals_size_hint > 0) { *nnz = vals_size_hint; return TACO_B200_OK; }
+  if (vals_size_hint > 0 && trusts_vals_size(A.pos)) { *nnz = vals_size_hint; return TACO_B200_OK; }
   return read_i32(A.pos + A.rows, nnz);
 }
 

@@ -309,6 +309,23 @@ def test_oracle_mttkrp_long_fibers_and_gaps():
     assert np.array_equal(A.reshape(5000, 32), want)
 
 
+@pytest.mark.parametrize("dtype,R", [("float64", 32), ("float32", 40)])
+def test_mttkrp_hub_slices_deterministic(dtype, R):
+    # slices of thousands of leaves are split across 64-leaf slots; the pieces are added into the row in slot order
+    # (owner stores, every later piece waits for its predecessor): no atomics on values, so repeated runs agree bit for
+    # bit; whole slices keep the reference's order exactly.  Long fibers: C(k,:) is gathered once per fiber.
+    I, K, L = 9, 7, 5000
+    w = synth.make("mttkrp", None, I=I, K=K, L=L, nnz=150_000, R=R, dtype=dtype)
+    t = {k: v for k, v in w.items() if k.startswith("B")}
+    assert np.diff(t["B3_pos"][t["B2_pos"]]).max() > 2000 and np.diff(t["B3_pos"]).mean() > 100
+    wd = G.to_device(dict(dims=w["dims"], C=w["C"], D=w["D"], **t))
+    first = G.run("mttkrp", wd)
+    for _ in range(4):
+        assert np.array_equal(G.run("mttkrp", wd), first)
+    want = oracle.mttkrp(t, w["C"].reshape(K, R), w["D"].reshape(L, R), I)
+    H.assert_close(first, want.reshape(-1), np.dtype(dtype))
+
+
 @pytest.mark.parametrize("dtype,R", [("float64", 32), ("float32", 16), ("float64", 5)])
 def test_oracle_mttkrp_host_pipeline(dtype, R, monkeypatch):
     # host operands through the slice-chunked upload / rebase / kernel / download pipeline (forced for this small case):
