@@ -638,8 +638,10 @@ def ours_record(wl, args, D, sampler):
         h, frac = cpu_sample
         tsec, kind = run_reference_cpu(wl, h, stats["esize"], 3, threads)
         sec = min(tsec)
+        what = (f"first {int(h['vals'].shape[0])} coordinates" if fam == "pack" else
+                f"first {int(h['B1_crd'].shape[0])} slices" if fam in ("mttkrp", "ttv", "ttm") else f"first {int(h['dims'][0])} rows")
         cpu = {"value": FLOPS[wl](full) * frac / sec / 1e9, "unit": metric_of(wl)[1], "cores": threads, "kind": kind,
-               "sample": (f"first {int(h['vals'].shape[0])} coordinates" if fam == "pack" else f"first {int(h['dims'][0])} rows") +
+               "sample": what +
                          f" ({frac * 100:.1f}% of the nonzeros), best of {len(tsec)}"}
     m, u = metric_of(wl)
     rec = {"metric": m, "value": value, "unit": u, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -658,13 +660,15 @@ def ours_record(wl, args, D, sampler):
     return rec
 
 
-def iteration_mode(wl, fam, ws, row_len, args, D, flops_job, tdt, nch=4):
+def iteration_mode(wl, fam, ws, row_len, args, D, flops_job, tdt):
     """step = kernels on `nch` row chunks of the shard; chunk c's all-gather (NCCL over NVLink) runs on a side stream while
-    chunk c+1 computes.  Uneven chunks are padded to the largest rank's chunk for the collective."""
+    chunk c+1 computes.  Uneven chunks are padded to the largest rank's chunk for the collective.  Results too small for
+    chunking to pay (under 32 MB per rank: the collective is latency-bound) are gathered in one piece."""
     import torch
     import torch.distributed as dist
     import gpu_util as G
     world = D.world
+    nch = 4 if int(ws["dims"][0]) * row_len * (4 if tdt == torch.float32 else 8) >= (32 << 20) else 1
     chunks = [shard_workload(wl, ws, c, nch)[:2] for c in range(nch)]
     rows_t = torch.tensor([r for _, r in chunks], dtype=torch.int64, device="cuda")
     allrows = [torch.zeros_like(rows_t) for _ in range(world)]

@@ -188,6 +188,15 @@ int taco_b200_spgemm_evaluate(taco_tensor_t* C, taco_tensor_t* A, taco_tensor_t*
 int taco_b200_pack(taco_tensor_t* A, taco_tensor_t* coo);
 int _shim_taco_b200_pack(void** p);
 
+/* File -> packed tensor, parsed on the device: the replacement for taco::read(filename, format) on the two text formats the
+ * reference's tests and CLI use -- Matrix Market coordinate files (.mtx / .ttx, `real`, `general` | `symmetric`;
+ * src/storage/file_io_mtx.cpp:39-150) and FROSTT files (.tns; src/storage/file_io_tns.cpp:39-96).  The bytes are uploaded once,
+ * split into lines and parsed by one thread per entry (values bit-identical to strtod), then packed by taco_b200_pack.
+ * `A` gives the target format and component type as for taco_b200_pack; A->dimensions[m] <= 0 means "take it from the file"
+ * (the size line of a .mtx, the largest coordinate of a .tns -- as the reference infers it) and is filled in. */
+int taco_b200_read(const char* path, taco_tensor_t* A);
+int _shim_taco_b200_read(void** p);       /* p[0] = const char* path, p[1] = taco_tensor_t* */
+
 /* ---- module object: the replacement for ir::Module on the GPU path ------------------------------------ */
 /* expr    : index notation as the CLI / Tensor API prints it, e.g. "y(i) = A(i,j) * x(j)"
  * formats : comma separated per-tensor level formats in CLI syntax (tools/taco.cpp -f=), e.g. "A:ds,x:d,y:d";

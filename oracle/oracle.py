@@ -268,3 +268,55 @@ def pack(kind, dims, coords, vals):
         res[f"A{l + 1}_crd"] = uc[l][head].astype(np.int32)
         parent_ids, nparents = node, nnodes
     return res
+
+
+# ---- file readers restated (test infrastructure): /root/reference/src/storage/file_io_mtx.cpp:39-150, file_io_tns.cpp:39-96 ----
+def read_mtx(path):
+    """Matrix Market coordinate file -> (dims, [coords per mode], vals) in insertion order (0-based), as readMTX + readSparse
+    insert them: header, '%' comments, size line `d1 d2 [..] nnz`, then nnz entries with 1-based indices and a strtod value;
+    symmetric files insert the transposed entry right after every off-diagonal one."""
+    with open(path, "rb") as fh:
+        lines = fh.read().decode("ascii", "replace").split("\n")
+    head = lines[0].split()
+    assert head[0] == "%%MatrixMarket" and head[1] in ("matrix", "tensor") and head[2] == "coordinate" and head[3] == "real"
+    symm = head[4] == "symmetric"
+    q = 1
+    while lines[q].split() and lines[q].split()[0].startswith("%"):
+        q += 1
+    size = [int(t) for t in lines[q].split()]
+    dims, nnz = size[:-1], size[-1]
+    coords = [[] for _ in dims]
+    vals = []
+    taken = 0
+    for line in lines[q + 1:]:
+        t = line.split()
+        if not t or taken >= nnz:
+            continue
+        c = [int(x) - 1 for x in t[:len(dims)]]
+        v = float(t[len(dims)])               # Python's float() is correctly rounded, like strtod
+        for m, x in enumerate(c):
+            coords[m].append(x)
+        vals.append(v)
+        taken += 1
+        if symm and c[0] != c[-1]:
+            for m, x in enumerate(reversed(c)):
+                coords[m].append(x)
+            vals.append(v)
+    return dims, [np.array(c, np.int64) for c in coords], np.array(vals, np.float64)
+
+
+def read_tns(path):
+    """FROSTT file -> (dims, coords, vals): order from the first line, dimensions = largest coordinate per mode (readTNS)"""
+    coords, vals = None, []
+    with open(path, "rb") as fh:
+        for line in fh.read().decode("ascii", "replace").split("\n"):
+            t = line.split()
+            if not t:
+                continue
+            if coords is None:
+                coords = [[] for _ in t[:-1]]
+            for m in range(len(coords)):
+                coords[m].append(int(t[m]) - 1)
+            vals.append(float(t[len(coords)]))
+    dims = [int(max(c)) + 1 for c in coords]
+    return dims, [np.array(c, np.int64) for c in coords], np.array(vals, np.float64)

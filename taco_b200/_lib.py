@@ -77,6 +77,8 @@ lib.taco_b200_module_get_func_ptr.restype = ctypes.c_void_p
 lib.taco_b200_module_get_func_ptr.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
 lib.taco_b200_pack.argtypes = [_TP, _TP]
 lib._shim_taco_b200_pack.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+lib.taco_b200_read.argtypes = [ctypes.c_char_p, _TP]
+lib._shim_taco_b200_read.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
 lib.taco_b200_partition_pos.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
 for _f in FAMILIES:
     for _p in PHASES:

@@ -80,7 +80,7 @@ int scratch_alloc(void** p, size_t bytes);
 void scratch_free(void* p);
 // owns the scratch buffers and events of a multi-stream pipeline: released on every exit path (early error returns included)
 struct PipelineGuard {
-  void* bufs[16];
+  void* bufs[32];
   cudaEvent_t evs[4];
   int nbufs = 0, nevs = 0;
   ~PipelineGuard() {
@@ -89,7 +89,7 @@ struct PipelineGuard {
   }
   int alloc(void** p, size_t bytes) {
     const int rc = scratch_alloc(p, bytes);
-    if (rc == TACO_B200_OK && nbufs < 16) bufs[nbufs++] = *p;
+    if (rc == TACO_B200_OK && nbufs < 32) bufs[nbufs++] = *p;
     return rc;
   }
   int event(cudaEvent_t* e) {

@@ -293,6 +293,19 @@ def pack(name, dims, fmt, coords, vals):
     return t
 
 
+def read(path, fmt, dtype=np.float64, dims=None, name="A"):
+    """taco::read(filename, format) for .mtx / .ttx (Matrix Market coordinate) and .tns (FROSTT) files
+    (/root/reference/src/tensor.cpp read(), src/storage/file_io_mtx.cpp, file_io_tns.cpp): the file is parsed and packed on
+    the device (taco_b200_read).  `dims` = None takes the dimensions from the file, as the reference does."""
+    fmt = fmt if isinstance(fmt, Format) else Format(fmt)
+    order = len(fmt.levels)
+    t = Tensor(name, list(dims) if dims is not None else [0] * order, fmt, dtype)
+    check(lib.taco_b200_read(str(path).encode(), t.ptr))
+    t.dims = [int(t._dims[m]) for m in range(order)]
+    t.adopt_results()
+    return t
+
+
 def makeBCSR(name, dims, pos, crd, vals):
     """dims = [Mb, Nb, br, bc]; pos/crd over the block columns, vals = [stored blocks * br * bc] (zero-copy attach)."""
     dt = np.float32 if (_is_torch(vals) and vals.dtype == torch.float32) or (not _is_torch(vals) and vals.dtype == np.float32) else np.float64
