@@ -133,9 +133,10 @@ csf3_ttv_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, 
 // Slot numbers are handed out by a ticket per CTA, so a piece's predecessor has always started -- the chain cannot deadlock
 // whatever order the hardware dispatches CTAs in.  Per 32 leaves: one coalesced load of B3_crd / B_vals, the fiber of each
 // leaf from a guessed position (exact when fibers are singletons) or a binary search in the slice's B3_pos window,
-// (k, l, val) staged in shared memory and read back as one 16-byte broadcast per leaf.  The row C(k,:) is gathered once
-// per FIBER, not per leaf (the reference's `w` workspace of scheduleMTTKRPCPU): consecutive leaves
-// of a fiber share k, so only D(l,:) is gathered for them.
+// (k, l, val) staged in shared memory and read back as one 16-byte broadcast per leaf.  C(k,:) is requested per leaf, but
+// consecutive leaves of a fiber share k and the repeats are L1 hits: holding the row in a register across a fiber (the
+// reference's `w` workspace idea) was measured and is SLOWER -- 6.70 ms against 6.17 ms on the 12.5-leaves-per-fiber tensor
+// of bench.py (mttkrp_fibers), no change at C4 -- because the conditional load stops ptxas from batching the gathers.
 constexpr int MK_W = 64;
 constexpr int MK_LONG = 512;
 
@@ -179,15 +180,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
-                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain) {
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed) {
   __shared__ MkLeaf<T> stage_all[WARPS][32];
   __shared__ MkSlice meta_all[WARPS][32];
   __shared__ int s_ticket;
   const int lane = threadIdx.x & 31;
   // chain[0] = CTA ticket, chain[1 + w] = "the pieces of a hub slice up to slot w are in the row" flag (zeroed per launch)
-  if (threadIdx.x == 0) s_ticket = atomicAdd(chain, 1);
-  __syncthreads();
-  const int w = s_ticket * WARPS + (threadIdx.x >> 5);
+  if (ticketed) {
+    if (threadIdx.x == 0) s_ticket = atomicAdd(chain, 1);
+    __syncthreads();
+  }
+  const int w = (ticketed ? s_ticket : (int)blockIdx.x) * WARPS + (threadIdx.x >> 5);
   int* const flags = chain + 1;
   if (w >= nslots) return;
   MkLeaf<T>* stage = stage_all[threadIdx.x >> 5];
@@ -243,8 +246,6 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
         const T* Cj = C + (active ? j0 + lane : 0);
         const T* Dj = D + (active ? j0 + lane : 0);
         T acc = T(0);
-        int ck = -1;                       // the fiber row of C held in `cfib` (consecutive leaves of a fiber share k)
-        T cfib = T(0);
         for (int pb = m.l0; pb < l1; pb += 32) {
           const int cnt = min(32, l1 - pb);
           if (lane < cnt) {
@@ -265,8 +266,7 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
             for (int u = 0; u < U; u++) {
               const MkLeaf<T> e = stage[q + u];
               vv[u] = e.v;
-              if (e.k != ck) { ck = e.k; cfib = __ldg(Cj + (size_t)e.k * R); }       // warp-uniform: a new fiber
-              cv[u] = cfib;
+              cv[u] = __ldg(Cj + (size_t)e.k * R);       // consecutive leaves of a fiber share k: L1 serves the repeats
               dv[u] = __ldg(Dj + (size_t)e.l * R);
             }
 #pragma unroll
@@ -274,8 +274,7 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
           }
           for (; q < cnt; q++) {
             const MkLeaf<T> e = stage[q];
-            if (e.k != ck) { ck = e.k; cfib = __ldg(Cj + (size_t)e.k * R); }
-            acc = acc + (e.v * cfib) * __ldg(Dj + (size_t)e.l * R);
+            acc = acc + (e.v * __ldg(Cj + (size_t)e.k * R)) * __ldg(Dj + (size_t)e.l * R);
           }
           __syncwarp();
         }
@@ -358,17 +357,20 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
 template <typename T, int U, int WARPS, int MINB>
 static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain) {
   const dim3 grid((nslots + WARPS - 1) / WARPS);
+  // TACO_B200_MTTKRP_NOTICKET=1: slot numbers from blockIdx instead of the ticket (A/B measurements only: the ordered
+  // hand-over of hub slices then relies on in-order CTA dispatch)
+  static const bool ticketed = getenv("TACO_B200_MTTKRP_NOTICKET") == nullptr;
   // The single-pass specialisation (R <= 32) spills less but measures SLOWER at C4 (23.1 vs 16.7 ms, same box, A/B):
   // ptxas unrolls the leaf loop of the general version four deep, which is what keeps HBM at 98 % of its peak.
   static const bool single = getenv("TACO_B200_MTTKRP_SINGLE") != nullptr;
   if (R <= 32 && single)
     mttkrp_csf_kernel<T, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed);
   else
     mttkrp_csf_kernel<T, U, WARPS, MINB, false><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed);
 }
 
 template <typename T>

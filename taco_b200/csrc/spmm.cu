@@ -15,7 +15,8 @@
 //       C kernel's order (Appendix A.1) -- so these rows are bit-identical to it.
 //   (2) long rows (> LONG nonzeros; 45 % of the nonzeros of the power-law config C2) -- COLUMN-PANEL schedule.  The
 //       columns are cut into P panels; a long row's nonzeros inside one panel form work items of at most CAP
-//       nonzeros.  Items are laid out panel-major and handed out in that order by a ticket, so at any moment the
+//       nonzeros (fused multiply-add: these rows are reassociated by the partial sums anyway).  Items are laid out
+//       panel-major and handed out in that order by a ticket, so at any moment the
 //       whole chip gathers rows of B from ONE panel (B panel = cols/P rows, L2-resident): every B row a long row needs
 //       is fetched from HBM about once instead of once per reference.  Each item stores its partial row sum; a combine
 //       kernel adds the partials of a row in ascending column (= position) order.  The plan (long-row list, panel cuts by
@@ -85,52 +86,54 @@ __global__ void spmm_slot_rows_kernel(const int* __restrict__ pos, SpmmRange rg,
   slot_rows[w] = (w == nslots) ? rg.r1 : tbd::search_first_ge(pos, rg.r0, rg.r1, rg.p0 + w * SPMM_W);
 }
 
-// acc += sum over nonzeros p in [a,b) of vals[p] * B[crd[p], col..col+VEC), in ascending p with separate multiply and
-// add (the reference C kernel's order, Appendix A.1).  32 nonzeros are fetched with one coalesced load per array and
-// broadcast by shuffle; U independent B-row gathers are in flight per warp.
-template <typename T, int VEC, int U>
+// One staged nonzero: column and value side by side, so that a warp reads both with ONE broadcast shared-memory load.
+template <typename T> struct __align__(8) SpmmNz { int c; T v; };
+
+// acc += sum over nonzeros p in [a,b) of vals[p] * B[crd[p], col..col+VEC), in ascending p.  32 nonzeros are fetched with one
+// coalesced load per array and parked in the warp's shared-memory stage; per nonzero the warp then issues one broadcast LDS
+// (column + value), one 64-bit multiply-add for the row address (unsigned column x row stride in bytes) and one 16-byte
+// gather, U gathers in flight.  FMA = false keeps multiply and add separate -- the reference C kernel's arithmetic
+// (Appendix A.1), bit-identical to it; FMA = true (long rows, whose partial sums are reassociated anyway) contracts them.
+template <typename T, int VEC, int U, bool FMA>
 __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __restrict__ crd, const T* __restrict__ vals,
-                                                const T* __restrict__ Bcol, int K, int a, int b, int lane) {
+                                                const char* __restrict__ Bbytes, unsigned stride, int a, int b, int lane,
+                                                SpmmNz<T>* __restrict__ stage) {
   for (int pb = a; pb < b; pb += 32) {
     const int cnt = min(32, b - pb);
-    int my_c = 0;
-    T my_v = T(0);
+    __syncwarp();                       // the previous chunk has been consumed
     if (lane < cnt) {
-      my_c = tbd::ldg_stream_i32(crd + pb + lane);
-      my_v = __ldg(vals + pb + lane);
+      SpmmNz<T> e;
+      e.c = tbd::ldg_stream_i32(crd + pb + lane);
+      e.v = __ldg(vals + pb + lane);
+      stage[lane] = e;
     }
+    __syncwarp();
     int j = 0;
     for (; j + U <= cnt; j += U) {
       Frag<T, VEC> bv[U];
+      T v[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int c = __shfl_sync(0xffffffffu, my_c, j + u);
-        bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
+        const SpmmNz<T> e = stage[j + u];
+        v[u] = e.v;
+        bv[u] = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)(unsigned)e.c * stride));
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const T v = __shfl_sync(0xffffffffu, my_v, j + u);
 #pragma unroll
-        for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];   // mul then add: never fused
+        for (int x = 0; x < VEC; x++) {
+          if constexpr (FMA) acc.v[x] = sizeof(T) == 4 ? (T)__fmaf_rn((float)v[u], (float)bv[u].v[x], (float)acc.v[x]) : (T)__fma_rn((double)v[u], (double)bv[u].v[x], (double)acc.v[x]);
+          else acc.v[x] = acc.v[x] + v[u] * bv[u].v[x];                       // mul then add: never fused (-fmad=false)
+        }
       }
     }
-    if (j < cnt) {                      // 1 .. U-1 left: same two phases, warp-uniform predicates
-      const int rem = cnt - j;
-      Frag<T, VEC> bv[U > 1 ? U - 1 : 1];
+    for (; j < cnt; j++) {              // 1 .. U-1 left
+      const SpmmNz<T> e = stage[j];
+      const Frag<T, VEC> b1 = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)(unsigned)e.c * stride));
 #pragma unroll
-      for (int u = 0; u < U - 1; u++) {
-        if (u < rem) {
-          const int c = __shfl_sync(0xffffffffu, my_c, j + u);
-          bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U - 1; u++) {
-        if (u < rem) {
-          const T v = __shfl_sync(0xffffffffu, my_v, j + u);
-#pragma unroll
-          for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];
-        }
+      for (int x = 0; x < VEC; x++) {
+        if constexpr (FMA) acc.v[x] = sizeof(T) == 4 ? (T)__fmaf_rn((float)e.v, (float)b1.v[x], (float)acc.v[x]) : (T)__fma_rn((double)e.v, (double)b1.v[x], (double)acc.v[x]);
+        else acc.v[x] = acc.v[x] + e.v * b1.v[x];
       }
     }
   }
@@ -143,18 +146,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
                 const int* __restrict__ slot_rows, int long_thresh, const unsigned* __restrict__ rowmap = nullptr) {
+  __shared__ SpmmNz<T> stage_all[WARPS][32];
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
   const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
   if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
+  SpmmNz<T>* stage = stage_all[threadIdx.x >> 5];
   const int lo = rg.p0 + w * SPMM_W;
   // the slot's own window of crd / vals is needed two dependent loads from now: pull it into L2 meanwhile
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
   else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
   const int col = (blockIdx.y * 32 + lane) * VEC;
   const bool active = col < K;
-  const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
+  const char* Bbytes = (const char*)(B + (active ? col : 0));        // inactive lanes (ragged K) gather column 0 and never store
+  const unsigned stride = (unsigned)K * (unsigned)sizeof(T);            // bytes between rows of B
   for (int rb = R0; rb < R1; rb += 32) {
     const int r = rb + lane;
     const bool valid = r < R1;
@@ -177,10 +183,15 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
       const int he = __shfl_sync(0xffffffffu, e, h);
 #pragma unroll
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      spmm_accumulate<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane);
+      spmm_accumulate<T, VEC, U, false>(acc, crd, vals, Bbytes, stride, hs, he, lane, stage);
       if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc);
     }
   }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -266,6 +277,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_long_kernel(const int* __restrict__ crd, const T* __restrict__ vals, const T* __restrict__ B, int K,
                  const int2* __restrict__ items, const int* __restrict__ pair_off, long long total_pairs, int* __restrict__ counters,
                  T* __restrict__ partials) {
+  __shared__ SpmmNz<T> stage_all[WARPS][32];
+  SpmmNz<T>* stage = stage_all[threadIdx.x >> 5];
+  const unsigned stride = (unsigned)K * (unsigned)sizeof(T);
   const int lane = threadIdx.x & 31;
   const int nitems = __ldg(pair_off + total_pairs);
   for (;;) {
@@ -282,7 +296,7 @@ spmm_long_kernel(const int* __restrict__ crd, const T* __restrict__ vals, const 
         Frag<T, VEC> acc;
 #pragma unroll
         for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-        spmm_accumulate<T, VEC, U>(acc, crd, vals, B + (active ? col : 0), K, m.x, m.y, lane);
+        spmm_accumulate<T, VEC, U, true>(acc, crd, vals, (const char*)(B + (active ? col : 0)), stride, m.x, m.y, lane, stage);
         if (active) {
           T* dst = partials + (size_t)it * K + col;
 #pragma unroll
@@ -335,10 +349,6 @@ spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restric
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 // TACO_B200_SPMM_LONG / _PANELS / _CAP override the defaults (tuning runs); the partial-sum scratch is kept under 4 GiB by
 // halving the panel count, then doubling the threshold.
@@ -368,7 +378,11 @@ template <typename T, int VEC, int U, int MINB>
 static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const int2* items, const int* pair_off, long long pairs,
                          int* counters, T* partials, cudaStream_t st) {
   constexpr int WARPS = 8;
-  spmm_long_kernel<T, VEC, U, WARPS, MINB><<<num_sms() * MINB, WARPS * 32, 0, st>>>(crd, vals, B, K, items, pair_off, pairs, counters, partials);
+  // persistent grid: MINB CTAs per SM by default; TACO_B200_SPMM_LONGCTAS caps it so that the slot kernel (side by side on the
+  // other stream) keeps part of every SM
+  static const int cap = env_int("TACO_B200_SPMM_LONGCTAS", 0);
+  const int per_sm = cap > 0 && cap < MINB ? cap : MINB;
+  spmm_long_kernel<T, VEC, U, WARPS, MINB><<<num_sms() * per_sm, WARPS * 32, 0, st>>>(crd, vals, B, K, items, pair_off, pairs, counters, partials);
 }
 
 // Builds the plan on the compute stream, then runs the item kernel and the combine kernel on `run_st` (the compute stream
@@ -443,7 +457,7 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
   ProfScope ps(prof_name);
   const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
-  static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 1);
+  static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 0);
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
   if (!ev_fork) {
     TB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
