@@ -22,6 +22,7 @@
 //              most two tiles (<= 2048 nonzeros always do) therefore stay bit-exact; longer rows are deterministic and
 //              within 1e-12 of the sequential sum.
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*(cols + rows).
+#include <climits>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -226,12 +227,201 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   }
 }
 
+// =========================================================================================================
+// Barrier-free variant (TTV's default; SpMV keeps the CTA-tile kernel above, see spmv_launch_raw): one WARP owns a chunk of SW_CHUNK consecutive nonzeros and walks it in windows of
+// SW_WIN = 128 (4 per lane, one 128-bit load of crd and two of vals per lane).  Per window: products into the warp's own
+// 1 KB shared-memory slice (__syncwarp only -- no CTA barrier anywhere), then
+//   * the row left open by the previous window is continued in order (its running sum lives in a register),
+//   * every row that STARTS in the window is found through a row cursor (32 pos entries per step, ballot), and one lane
+//     sums it in ascending position order -- the reference C kernel's order, bit-identical to it; the row that runs past
+//     the window becomes the open row.
+// A row still open at the end of the chunk is finished by the same warp (it reads on past its chunk; the next chunk's
+// warp starts at the first row that starts in ITS chunk and skips what lies before it).  Rows longer than SW_LONG are not
+// summed here at all: their start lane appends them to a list and a second, tiny kernel sums each with a fixed-shape
+// strided + tree reduction (deterministic, within 1e-12 of the sequential order).  Windows that lie wholly inside such a
+// row are skipped without loading anything.  No flags, no epochs, no dependence on CTA dispatch order; 64 independent
+// warps per SM keep the L1 gather pipe busy where the CTA-wide phases of the tile kernel left it idle a third of the time.
+// =========================================================================================================
+constexpr int SW_WIN = 128;
+constexpr int SW_LONG = 1024;
+constexpr int SW_WARPS = 8;
+
+// first i in [0, n) with a[i] >= target (a non-decreasing), n if none: 32-ary search by one warp, 4-5 dependent rounds
+__device__ __forceinline__ int warp_first_ge(const int* __restrict__ a, int n, int target, int lane) {
+  int base = 0, len = n;
+  while (len > 0) {
+    const int stride = (len + 31) >> 5;
+    const int idx = base + lane * stride;
+    const bool below = idx < base + len && __ldg(a + idx) < target;
+    const int f = __popc(__ballot_sync(0xffffffffu, below));
+    if (f == 0) return base;
+    const int nb = base + (f - 1) * stride + 1;
+    const int ne = min(base + f * stride, base + len);
+    base = nb;
+    len = ne - nb;
+  }
+  return base;
+}
+
+template <typename T, bool MAPPED, int MINB, int WINS>
+__global__ void __launch_bounds__(SW_WARPS * 32, MINB)
+spmv_warp_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals, const T* __restrict__ x,
+                 T* __restrict__ y, int rows, int nnz, const unsigned* __restrict__ ymap, int shift, bool vec, int nchunks,
+                 int* __restrict__ long_rows, int* __restrict__ counters, int long_cap) {
+  __shared__ T prod_all[SW_WARPS][SW_WIN];
+  const int lane = threadIdx.x & 31;
+  T* prod = prod_all[threadIdx.x >> 5];
+  const int w = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+  if (w >= nchunks) return;
+  constexpr int SW_CHUNK = SW_WIN * WINS;          // nonzeros per warp
+  const int lo = w * SW_CHUNK - shift;             // chunks start `shift` nonzeros early so that 128-bit loads stay aligned
+  const int hi = min(lo + SW_CHUNK, nnz);
+  const uint64_t keep = tbd::policy_evict_last();
+  // row cursor: the first row that starts in this chunk
+  int r = warp_first_ge(pos, rows + 1, max(lo, 0), lane);
+  int next_start = r < rows ? __ldg(pos + r) : INT_MAX;
+  bool open = false;
+  int open_row = 0, open_end = 0;
+  T acc = T(0);
+  for (int p0 = lo;; p0 += SW_WIN) {
+    const bool in_chunk = p0 < hi;
+    if (!in_chunk && !open) break;
+    const int p1 = min(p0 + SW_WIN, in_chunk ? hi : open_end);
+    if (!open && next_start >= p1) continue;       // nothing starts or continues here (inside a long / foreign row)
+    // ---- products of the window into the warp's slice ----------------------------------------------------------
+    {
+      const int q = p0 + lane * SPMV_VEC;
+      if (q < p1) {
+        int4 c;
+        T v[4];
+        spmv_load4<T>(crd, vals, q, nnz, vec, c, v);
+        const T x0 = spmv_ld_x<T, 0>(x + c.x, keep), x1 = spmv_ld_x<T, 0>(x + c.y, keep), x2 = spmv_ld_x<T, 0>(x + c.z, keep),
+                x3 = spmv_ld_x<T, 0>(x + c.w, keep);
+        T* d = prod + lane * SPMV_VEC;
+        d[0] = v[0] * x0; d[1] = v[1] * x1; d[2] = v[2] * x2; d[3] = v[3] * x3;
+      }
+    }
+    __syncwarp();
+    // ---- the row left open by an earlier window: continue in position order ---------------------------------------
+    if (open) {
+      const int e = min(open_end, p1);
+      for (int i = max(p0, 0); i < e; i++) acc += prod[i - p0];
+      if (open_end <= p1) {
+        if (lane == 0) {
+          if constexpr (MAPPED) y[__ldg(ymap + open_row)] = acc;
+          else y[open_row] = acc;
+        }
+        open = false;
+      }
+    }
+    // ---- rows that start in this window ---------------------------------------------------------------------------
+    if (in_chunk) {
+      while (next_start < p1) {
+        const int ri = r + lane;
+        int s = INT_MAX, e = INT_MAX;
+        if (ri < rows) { s = __ldg(pos + ri); e = __ldg(pos + ri + 1); }
+        const bool valid = ri < rows && s < p1;
+        const int nv = __popc(__ballot_sync(0xffffffffu, valid));      // a prefix of the lanes
+        const int deg = valid ? e - s : 0;
+        if (valid) {
+          if (deg > SW_LONG) {
+            const int at = atomicAdd(counters, 1);
+            if (at < long_cap) long_rows[at] = ri;
+          } else if (e <= p1) {                      // complete inside the window (empty rows included)
+            T a = T(0);
+            for (int i = s; i < e; i++) a += prod[i - p0];
+            if constexpr (MAPPED) y[__ldg(ymap + ri)] = a;
+            else y[ri] = a;
+          }
+        }
+        const unsigned em = __ballot_sync(0xffffffffu, valid && deg <= SW_LONG && e > p1);
+        if (em) {                                    // at most one row runs past the window: it becomes the open row
+          const int src = __ffs(em) - 1;
+          T a = T(0);
+          if (lane == src)
+            for (int i = s; i < p1; i++) a += prod[i - p0];
+          acc = __shfl_sync(0xffffffffu, a, src);
+          open_row = __shfl_sync(0xffffffffu, ri, src);
+          open_end = __shfl_sync(0xffffffffu, e, src);
+          open = true;
+        }
+        const int s_next = __shfl_sync(0xffffffffu, nv == 32 ? e : s, nv == 32 ? 31 : nv);
+        r += nv;
+        next_start = r < rows ? s_next : INT_MAX;
+        if (nv == 0) break;
+      }
+    }
+    __syncwarp();                                    // the slice is rewritten by the next window
+  }
+  // trailing rows that start at nnz (all empty) belong to the last chunk
+  if (w == nchunks - 1)
+    for (int rr = r + lane; rr < rows; rr += 32) {
+      if constexpr (MAPPED) y[__ldg(ymap + rr)] = T(0);
+      else y[rr] = T(0);
+    }
+}
+
+// rows longer than SW_LONG: one CTA per row, fixed strided partial sums + fixed tree -> deterministic.  The last CTA to
+// finish resets the list counters for the next launch on this stream.
+template <typename T, bool MAPPED>
+__global__ void __launch_bounds__(256)
+spmv_long_rows_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals, const T* __restrict__ x,
+                      T* __restrict__ y, const unsigned* __restrict__ ymap, const int* __restrict__ long_rows, int* __restrict__ counters,
+                      int long_cap) {
+  __shared__ T red[256];
+  const int tid = threadIdx.x;
+  const int count = min(*(volatile int*)counters, long_cap);
+  const uint64_t keep = tbd::policy_evict_last();
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int r = long_rows[i];
+    const int s = __ldg(pos + r), e = __ldg(pos + r + 1);
+    T a = T(0);
+    for (int p = s + tid; p < e; p += 256) a += __ldg(vals + p) * spmv_ld_x<T, 0>(x + __ldg(crd + p), keep);
+    red[tid] = a;
+    __syncthreads();
+#pragma unroll
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if constexpr (MAPPED) y[__ldg(ymap + r)] = red[0];
+      else y[r] = red[0];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(counters + 1, 1) == (int)gridDim.x - 1) { counters[0] = 0; counters[1] = 0; __threadfence(); }
+  }
+}
+
 // Hand-over scratch (one partial + one flag per tile).  Flags are compared against a per-launch epoch, so they are never
 // cleared between calls.  One scratch set per STREAM: launches on one stream are serialised by the stream, launches on
 // different streams (taco_b200_set_stream) or from different host threads never share slots; the table is mutex-guarded.
-struct SpmvScratch { void* partial = nullptr; int* flag = nullptr; int cap = 0; int epoch = 0; };
+struct SpmvScratch {
+  void* partial = nullptr; int* flag = nullptr; int cap = 0; int epoch = 0;      // tile kernel: hand-over slots
+  int* long_rows = nullptr; int* counters = nullptr; int long_cap = 0;            // warp kernel: long-row list + {count, done}
+};
 static std::mutex g_spmv_mu;
 static std::unordered_map<cudaStream_t, SpmvScratch> g_spmv_scratch;
+
+static int spmv_long_scratch_for(cudaStream_t st, int cap, SpmvScratch* out) {
+  std::lock_guard<std::mutex> lk(g_spmv_mu);
+  SpmvScratch& sc = g_spmv_scratch[st];
+  if (!sc.counters) {
+    TB_CUDA(cudaMallocAsync((void**)&sc.counters, sizeof(int) * 4, st));
+    TB_CUDA(cudaMemsetAsync(sc.counters, 0, sizeof(int) * 4, st));     // the long-row kernel leaves them zeroed again
+  }
+  if (cap > sc.long_cap) {
+    if (sc.long_rows) cudaFreeAsync(sc.long_rows, st);
+    sc.long_cap = cap + cap / 2 + 1024;
+    sc.long_rows = nullptr;
+    TB_CUDA(cudaMallocAsync((void**)&sc.long_rows, sizeof(int) * (size_t)sc.long_cap, st));
+  }
+  *out = sc;
+  return TACO_B200_OK;
+}
 
 static int spmv_scratch_for(cudaStream_t st, int ntiles, SpmvScratch* out) {
   std::lock_guard<std::mutex> lk(g_spmv_mu);
@@ -269,6 +459,40 @@ static int spmv_launch_raw(const int* pos, const int* crd, const T* vals, const 
     shift = (int)((ca / 4) % 4);
     vec = ((va / sizeof(T)) - (uintptr_t)shift) % (16 / sizeof(T)) == 0;
     if (!vec) shift = 0;
+  }
+  // Which kernel: measured on the B200 (profiles/r02_variants.md) -- the CTA-tile kernel wins on CSR SpMV with rows of ~10
+  // nonzeros (C1: 64.6 us against 80-89 us), the barrier-free warp-chunk kernel on TTV, whose "rows" (fibers) average 1.5 leaves
+  // (0.710 ms against 0.738 ms).  TACO_B200_SPMV_KERNEL = 0 / 1..4 forces one or the other.
+  static const int forced = getenv("TACO_B200_SPMV_KERNEL") ? atoi(getenv("TACO_B200_SPMV_KERNEL")) : -1;
+  const int kernel_sel = forced >= 0 ? forced : (ymap ? 1 : 0);
+  if (kernel_sel != 0) {
+    // nonzeros per warp: 8 windows of 128 by default (TACO_B200_SPMV_KERNEL = 2: 16 windows, 3: 8 windows / 6 CTAs per SM,
+    // 4: 4 windows)
+    const int wins = kernel_sel == 2 ? 16 : kernel_sel == 4 ? 4 : 8;
+    const int chunk = SW_WIN * wins;
+    const int nchunks = nnz > 0 ? (int)(((long long)nnz + shift + chunk - 1) / chunk) : 1;
+    const int lcap = nnz / (SW_LONG + 1) + 1;
+    SpmvScratch sc;
+    TB_TRY(spmv_long_scratch_for(stream(), lcap, &sc));
+    const int grid = (nchunks + SW_WARPS - 1) / SW_WARPS;
+    {
+      ProfScope ps(prof_name);
+#define TB_SW_GO(MAPPED, MINB, WINS)                                                                                                    \
+  spmv_warp_kernel<T, MAPPED, MINB, WINS><<<grid, SW_WARPS * 32, 0, stream()>>>(pos, crd, vals, x, y, rows, nnz, ymap, shift, vec, nchunks, \
+                                                                                sc.long_rows, sc.counters, lcap)
+      if (ymap) {
+        if (kernel_sel == 2) TB_SW_GO(true, 8, 16); else if (kernel_sel == 3) TB_SW_GO(true, 6, 8); else if (kernel_sel == 4) TB_SW_GO(true, 8, 4); else TB_SW_GO(true, 8, 8);
+      } else {
+        if (kernel_sel == 2) TB_SW_GO(false, 8, 16); else if (kernel_sel == 3) TB_SW_GO(false, 6, 8); else if (kernel_sel == 4) TB_SW_GO(false, 8, 4); else TB_SW_GO(false, 8, 8);
+      }
+#undef TB_SW_GO
+      const int lgrid = lcap < num_sms() * 2 ? lcap : num_sms() * 2;
+      if (ymap) spmv_long_rows_kernel<T, true><<<lgrid, 256, 0, stream()>>>(pos, crd, vals, x, y, ymap, sc.long_rows, sc.counters, lcap);
+      else spmv_long_rows_kernel<T, false><<<lgrid, 256, 0, stream()>>>(pos, crd, vals, x, y, ymap, sc.long_rows, sc.counters, lcap);
+    }
+    count_launch(2);
+    TB_CUDA(cudaGetLastError());
+    return TACO_B200_OK;
   }
   const int ntiles = nnz > 0 ? (int)(((long long)nnz + shift + tile - 1) / tile) : 1;
   SpmvScratch sc;

@@ -13,20 +13,17 @@ run() {  # workload, env assignments...
   env "$@" timeout 600 python bench.py --workload $wl --no-e2e --no-cpu --steps 10 2>&1 | tail -1 | python -c "$summ"
 }
 {
-timeout 2400 python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu_gpu.py -m gpu -q -x -k "spmm or mttkrp or ttm or dcsr or csf or shards" 2>&1 | tail -4
-run spmm X=0
-run spmm TACO_B200_SPMM_LONGCTAS=3
-run spmm TACO_B200_SPMM_LONGCTAS=4
-run spmm TACO_B200_SPMM_LONGVAR=1
-run spmm TACO_B200_SPMM_LONGVAR=3
-run spmm TACO_B200_SPMM_LONG=64
-run spmm TACO_B200_SPMM_LONG=256
-run spmm TACO_B200_SPMM_OVERLAP=0
+timeout 2400 python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu_gpu.py tests/test_pytaco_gpu.py tests/test_fullsize_gpu.py -m gpu -q -x -k "spmv or ttv or shards or pytaco or c1 or c2 or mttkrp or nccl or csf" 2>&1 | tail -6
+run spmv X=0
+run spmv TACO_B200_SPMV_KERNEL=0
+run spmv TACO_B200_SPMV_KERNEL=2
+run spmv TACO_B200_SPMV_KERNEL=3
+run spmv TACO_B200_SPMV_KERNEL=4
+run ttv X=0
+run ttv TACO_B200_SPMV_KERNEL=0
 run mttkrp X=0
-run mttkrp TACO_B200_MTTKRP_NOHOIST=1
-run mttkrp TACO_B200_MTTKRP_VARIANT=3
+run mttkrp TACO_B200_MTTKRP_NOTICKET=1
 run mttkrp_fibers X=0
-run mttkrp_fibers TACO_B200_MTTKRP_NOHOIST=1
-run mttkrp_fibers TACO_B200_MTTKRP_VARIANT=3
-} > gpurun_out/exp_r2_6.txt 2>&1
-cat gpurun_out/exp_r2_6.txt
+run spmm X=0
+} > gpurun_out/exp_r2_7.txt 2>&1
+cat gpurun_out/exp_r2_7.txt
