@@ -780,6 +780,7 @@ def e2e_mode(wl, fam, ws, stats, args, D, flops_job, sparse_out, sharded):
         hstep()             # returns after the D2H of the result has completed (host-visible result => sync)
     torch.cuda.synchronize()
     e2e_s = D.max((time.perf_counter() - t0) / e2e_steps)
+    pcie = pcie_probe(D, torch, tb) if world > 1 else None
     tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1 and sharded:
         dist.all_reduce(tot)
@@ -789,10 +790,36 @@ def e2e_mode(wl, fam, ws, stats, args, D, flops_job, sparse_out, sharded):
     for v in list(hw.values()) + pinned_slices:
         if isinstance(v, np.ndarray):
             tb.pinned_free(v)
-    return {"value": flops_job / e2e_s / 1e9, "unit": metric_of(wl)[1], "h2d_bytes_per_step": int(tot[0].item()),
+    out = {} if pcie is None else {"pcie_probe": pcie}
+    return {**out, "value": flops_job / e2e_s / 1e9, "unit": metric_of(wl)[1], "h2d_bytes_per_step": int(tot[0].item()),
             "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
             "path": "taco_b200_<family>_compute(taco_tensor_t*) with pinned host arrays" +
                     ("" if not repl else f"; replicated dense operand(s) {repl}: 1/{world} uploaded per rank + NCCL all-gather; bytes summed over ranks")}
+
+
+def pcie_probe(D, torch, tb, mb=256):
+    """what the box's host<->device path gives when every rank copies at once (256 MB up and 256 MB down per rank, pinned):
+    the e2e number of a PCIe-bound step cannot scale past this aggregate, whatever the kernels do"""
+    n = mb << 20
+    h_up, h_dn = tb.pinned_empty((n,), np.uint8), tb.pinned_empty((n,), np.uint8)
+    d_up, d_dn = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")
+    t_up, t_dn = torch.from_numpy(h_up), torch.from_numpy(h_dn)
+    side = torch.cuda.Stream()
+    best = None
+    for _ in range(3):
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_up.copy_(t_up, non_blocking=True)
+        with torch.cuda.stream(side):
+            t_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize()
+        t = D.max(time.perf_counter() - t0)
+        best = t if best is None else min(best, t)
+    tb.pinned_free(h_up)
+    tb.pinned_free(h_dn)
+    return {"aggregate_GBps": 2 * n * D.world / best / 1e9, "per_rank_GBps": 2 * n / best / 1e9,
+            "what": f"{D.world} ranks copying {mb} MB up and {mb} MB down at once (pinned), max over ranks"}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -1,13 +1,12 @@
 #!/bin/bash
-# multi-GPU bench exactly as the driver launches it: tools/gpu_scale.sh N
-N=${1:-2}
+# strong-scaling bench at N GPUs of one box (usage: tools/gpu_scale.sh N [steps]); output gpurun_out/bench_n<N>.json
+N=${1:-8}; STEPS=${2:-10}
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 \
-   > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 2 --warmup 1 \
-   > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err
-for wl in ${EXTRA_WL:-spmv mttkrp}; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --no-cpu \
-   > gpurun_out/bench_${wl}_n$N.json 2> gpurun_out/bench_${wl}_n$N.err
-done
-tail -2 gpurun_out/bench_n$N.err; cat gpurun_out/bench_*_n$N.json gpurun_out/bench_n$N.json
+{
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -$N
+nvidia-smi topo -m 2>/dev/null | head -14
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $STEPS --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+echo "rc=$?"
+grep -v "^\*\|OMP_NUM" gpurun_out/bench_n$N.err | tail -20
+} > gpurun_out/exp_n$N.txt 2>&1
+cat gpurun_out/exp_n$N.txt
