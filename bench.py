@@ -550,7 +550,8 @@ def ours_record(wl, args, D, sampler):
     if sharded:
         w = broadcast_workload(w, D)
     full = sizes_of(wl, w)
-    ws, out_rows, row_len, _ = shard_workload(wl, w, D.rank, world)
+    ws, out_rows, row_len, row0 = shard_workload(wl, w, D.rank, world)
+    total_rows = int(w["dims"][0])
     cpu_sample = None
     if D.rank == 0 and world == 1 and not args.no_cpu:
         cpu_sample = reference_sample(wl, w, SAMPLE_ROWS[wl] if not args.small else None)
@@ -626,6 +627,7 @@ def ours_record(wl, args, D, sampler):
     iteration = None
     if sharded and not sparse_out:
         iteration = iteration_mode(wl, fam, ws, row_len, args, D, flops_job, tdt)
+        iteration["fused"] = fused_iteration(wl, fam, ws, row_len, row0, out_rows, total_rows, args, D, flops_job, tdt)
 
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region --------------------------------
     e2e = None
@@ -722,6 +724,62 @@ def iteration_mode(wl, fam, ws, row_len, args, D, flops_job, tdt):
                           "chunk c gathered on a side stream while chunk c+1 computes",
             "allgather_alone_ms": ag_ms, "allgather_bytes_per_rank": nbytes,
             "allgather_recv_GBps_per_rank": nbytes * (world - 1) / (ag_ms * 1e-3) / 1e9}
+
+
+def fused_iteration(wl, fam, ws, row_len, row0, out_rows, total_rows, args, D, flops_job, tdt):
+    """the same iteration with the all-gather INSIDE the kernel: the dense result lives in a symmetric allocation
+    (torch.distributed._symmetric_memory), the library stores every result row through its NVLink multicast mapping
+    (taco_b200_set_result_multicast), so the NVSwitch delivers it to all ranks while the kernel is still computing; the step
+    ends with a device-side cross-rank barrier.  No NCCL collective, no second pass over the result."""
+    import torch
+    import torch.distributed as dist
+    import gpu_util as G
+    import taco_b200 as tb
+    if fam not in ("spmm", "mttkrp"):
+        return {"unavailable": "in-kernel multicast stores are implemented for the SpMM and MTTKRP results"}
+    try:
+        import torch.distributed._symmetric_memory as symm
+        buf = symm.empty(total_rows * row_len, dtype=tdt, device="cuda")
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        mc = int(hdl.multicast_ptr)
+        if not mc:
+            return {"unavailable": "no NVLink multicast mapping for the symmetric allocation on this box"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"symmetric memory: {type(e).__name__}: {str(e)[:160]}"}
+    nbytes = buf.numel() * buf.element_size()
+    tb.set_result_multicast(buf.data_ptr(), mc, nbytes)
+    try:
+        k, ts = G.build(fam, ws)
+        ts[0].set_vals(buf[row0 * row_len: (row0 + out_rows) * row_len])
+
+        def fstep():
+            if out_rows > 0:
+                k.compute(*ts)
+            hdl.barrier()           # every rank's rows have landed everywhere
+
+        for _ in range(max(args.warmup, 3)):
+            fstep()
+        torch.cuda.synchronize()
+        D.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            fstep()
+        b.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = D.max(a.elapsed_time(b)) / args.steps
+        # every rank must now hold the whole result: compare checksums of the gathered buffer across ranks
+        chk = buf.double().sum().reshape(1)
+        lo, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        same = bool(lo.item() == hi_.item())
+        return {"value": flops_job / (ms * 1e-3) / 1e9, "unit": metric_of(wl)[1], "ms_per_step": ms, "all_ranks_hold_identical_result": same,
+                "collective": "none: result rows stored through the NVLink multicast mapping inside the kernel (multimem.st), "
+                              "then a device-side cross-rank barrier", "bytes_multicast_per_rank": out_rows * row_len * buf.element_size()}
+    finally:
+        tb.set_result_multicast(None, None, 0)
 
 
 def e2e_mode(wl, fam, ws, stats, args, D, flops_job, sparse_out, sharded):

@@ -97,6 +97,13 @@ void  taco_b200_host_free(void* p);
 void* taco_b200_device_alloc(size_t bytes);
 void  taco_b200_free(void* p);                    /* frees device OR pinned-host memory from this library */
 
+/* Fused compute + all-gather over NVLink (multi-GPU).  Register a window of THIS GPU's memory together with
+ * the NVLink multicast mapping of the same symmetric allocation (e.g. torch.distributed._symmetric_memory: buffer_ptrs[rank] and
+ * multicast_ptr).  A dense result (SpMM C, MTTKRP A) that lies inside the window is then stored through the multicast address:
+ * every row a kernel produces is delivered by the NVSwitch to all GPUs of the group in the same store, so after the step (and
+ * a cross-rank barrier) every rank holds the whole gathered result -- no separate all-gather.  NULL, NULL, 0 clears. */
+int  taco_b200_set_result_multicast(const void* local_base, void* multicast_base, size_t bytes);
+
 /* Residency cache: keep a device mirror of an immutable host array across calls (pinned upload once). */
 int  taco_b200_make_resident(const void* host_ptr, size_t bytes);
 int  taco_b200_invalidate(const void* host_ptr);  /* host array changed or is about to be freed */

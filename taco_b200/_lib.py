@@ -63,6 +63,7 @@ lib.taco_b200_host_free.argtypes = [ctypes.c_void_p]
 lib.taco_b200_device_alloc.restype = ctypes.c_void_p
 lib.taco_b200_device_alloc.argtypes = [ctypes.c_size_t]
 lib.taco_b200_free.argtypes = [ctypes.c_void_p]
+lib.taco_b200_set_result_multicast.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_make_resident.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_invalidate.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_open.restype = ctypes.c_void_p

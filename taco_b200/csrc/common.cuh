@@ -75,6 +75,12 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// Result multicast window (taco_b200_set_result_multicast): when the dense result [p, p + bytes) lies inside the registered
+// local window, returns the byte distance to the same location of the NVLink multicast mapping (0 otherwise).  Kernels that get
+// a non-zero distance store their result rows through the multicast address: one store, delivered by the NVSwitch to every
+// GPU of the group (the local one included) -- the all-gather of the result happens inside the kernel.
+long long multicast_delta(const void* p, size_t bytes);
+
 // stream-ordered scratch
 int scratch_alloc(void** p, size_t bytes);
 void scratch_free(void* p);

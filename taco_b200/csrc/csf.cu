@@ -173,14 +173,22 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
   slot_slices[w] = lo;
 }
 
-struct MkSlice { int f0, f1, l0, l1, row, zlo; };   // fibers, leaves, row of A, first row to zero before `row`
+struct MkSlice { int f0, f1, l0, l1, row, zlo; };
+
+// result store: plain, or through the NVLink multicast mapping `mcd` bytes away (fused all-gather of A's rows, common.cuh)
+template <typename T>
+__device__ __forceinline__ void mk_store(T* dst, T v, long long mcd) {
+  if (mcd == 0) *dst = v;
+  else if constexpr (sizeof(T) == 4) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"((char*)dst + mcd), "f"(v) : "memory");
+  else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"((char*)dst + mcd), "d"(v) : "memory");
+}   // fibers, leaves, row of A, first row to zero before `row`
 
 template <typename T, int U, int WARPS, int MINB, bool SINGLE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
-                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed) {
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed, long long mcd) {
   __shared__ MkLeaf<T> stage_all[WARPS][32];
   __shared__ MkSlice meta_all[WARPS][32];
   __shared__ int s_ticket;
@@ -236,10 +244,10 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
       const int l1 = hub ? min(hi, m.l1) : m.l1;
       if (!is_tail) {
         for (int r = m.zlo; r < m.row; r++)
-          for (int j = lane; j < R; j += 32) A[(size_t)r * R + j] = T(0);
+          for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), mcd);
         if (sb + h == nslices - 1)                       // the last slice also owns the rows after it
           for (int r = m.row + 1; r < Idim; r++)
-            for (int j = lane; j < R; j += 32) A[(size_t)r * R + j] = T(0);
+            for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), mcd);
       }
       for (int j0 = 0; j0 < (SINGLE ? 1 : R); j0 += 32) {      // SINGLE: R <= 32, one pass over the slice's leaves
         const bool active = j0 + lane < R;
@@ -285,8 +293,13 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
         }
         if (active) {
           T* dst = A + (size_t)m.row * R + j0 + lane;
-          if (is_tail) *dst = __ldcg(dst) + acc;           // pieces are added in slot order: deterministic
-          else *dst = acc;                                 // whole slices, and the owner's (first) piece of a hub slice
+          // pieces of a hub slice are added in slot order (deterministic) in LOCAL memory; only the piece that completes
+          // the row -- and every whole slice -- goes out through the multicast mapping, if there is one
+          if (is_tail) {
+            const T sum = __ldcg(dst) + acc;
+            if (tail_end <= hi) mk_store<T>(dst, sum, mcd); else *dst = sum;
+          } else if (hub) *dst = acc;
+          else mk_store<T>(dst, acc, mcd);
         }
       }
       if (hub && (is_tail ? tail_end > hi : true)) {       // more pieces follow in the next slot: publish this one
@@ -355,7 +368,7 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
 }
 
 template <typename T, int U, int WARPS, int MINB>
-static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain) {
+static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain, long long mcd) {
   const dim3 grid((nslots + WARPS - 1) / WARPS);
   // TACO_B200_MTTKRP_NOTICKET=1: slot numbers from blockIdx instead of the ticket (A/B measurements only: the ordered
   // hand-over of hub slices then relies on in-order CTA dispatch)
@@ -366,11 +379,11 @@ static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslo
   if (R <= 32 && single)
     mttkrp_csf_kernel<T, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd);
   else
     mttkrp_csf_kernel<T, U, WARPS, MINB, false><<<grid, WARPS * 32, 0, stream()>>>(
         cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed);
+        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd);
 }
 
 template <typename T>
@@ -394,16 +407,17 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
     return fail(TACO_B200_ERR_CUDA, "mttkrp: memset failed");
   }
   static const int variant = getenv("TACO_B200_MTTKRP_VARIANT") ? atoi(getenv("TACO_B200_MTTKRP_VARIANT")) : 0;
+  const long long mcd = multicast_delta(A, a_count * sizeof(T));     // result inside the registered multicast window?
   {
     ProfScope ps("mttkrp_csf");
     const int* ss = (const int*)slot_slices;
     switch (variant) {
-      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
-      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
-      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
-      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
-      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
-      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain); break;
+      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
     }
   }
   count_launch(2);

@@ -58,6 +58,9 @@ struct Context {
   std::unordered_set<const void*> pooled;   // device result arrays handed to the caller that came from the pool
   bool profile = false;
   std::vector<ProfEntry> prof;
+  const char* mc_local = nullptr;            // result multicast window: local base, multicast base, size
+  char* mc_base = nullptr;
+  size_t mc_bytes = 0;
 };
 static Context g;
 
@@ -143,6 +146,13 @@ Mem classify(const void* p) {
     case cudaMemoryTypeHost: return Mem::Pinned;
     default: return Mem::Host;
   }
+}
+
+long long multicast_delta(const void* p, size_t bytes) {
+  if (!g.mc_base || !p) return 0;
+  const char* c = (const char*)p;
+  if (c < g.mc_local || c + bytes > g.mc_local + g.mc_bytes) return 0;
+  return (long long)(g.mc_base - g.mc_local);
 }
 
 bool trusts_vals_size(const void* p) {
@@ -479,6 +489,18 @@ void taco_b200_free(void* p) {
   if (m == Mem::Device) cudaFree(p);
   else if (m == Mem::Pinned) cudaFreeHost(p);
   else free(p);
+}
+
+int taco_b200_set_result_multicast(const void* local_base, void* multicast_base, size_t bytes) {
+  TB_TRY(ensure_init());
+  if ((local_base == nullptr) != (multicast_base == nullptr)) return fail(TACO_B200_ERR_ARG, "set_result_multicast: both bases or neither");
+  if (local_base && (((uintptr_t)local_base | (uintptr_t)multicast_base) & 15))
+    return fail(TACO_B200_ERR_ARG, "set_result_multicast: bases must be 16-byte aligned");
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.mc_local = (const char*)local_base;
+  g.mc_base = (char*)multicast_base;
+  g.mc_bytes = local_base ? bytes : 0;
+  return TACO_B200_OK;
 }
 
 int taco_b200_make_resident(const void* host_ptr, size_t bytes) {

@@ -20,7 +20,7 @@
 //       whole chip gathers rows of B from ONE panel (B panel = cols/P rows, L2-resident): every B row a long row needs
 //       is fetched from HBM about once instead of once per reference.  Each item stores its partial row sum; a combine
 //       kernel adds the partials of a row in ascending column (= position) order.  The plan (long-row list, panel cuts by
-//       binary search, item offsets by prefix sum) is rebuilt on the device every call: no cached inspector state, no
+//       binary search, item slots by one warp-aggregated atomic per panel) is rebuilt on the device every call: no cached inspector state, no
 //       host read-back, results independent of scheduling (run-to-run deterministic, within 1e-5 / 1e-12 of the
 //       sequential order).
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*K*(cols + rows).
@@ -54,8 +54,33 @@ __device__ __forceinline__ Frag<T, VEC> load_row(const T* __restrict__ p) {
   return f;
 }
 
+// one component through the NVLink multicast mapping of the result (delivered to every GPU of the group)
+template <typename T>
+__device__ __forceinline__ void st_multicast(T* p, T v) {
+  if constexpr (sizeof(T) == 4) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// `mcd` != 0: the row goes out through the multicast mapping, `mcd` bytes away from the local address (common.cuh)
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f) {
+__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f,
+                                          long long mcd) {
+  if (mcd != 0) {
+    if constexpr (COLMAJOR) {
+#pragma unroll
+      for (int e = 0; e < VEC; e++) st_multicast<T>((T*)((char*)(C + (size_t)(col + e) * rows + row) + mcd), f.v[e]);
+    } else {
+      T* p = (T*)((char*)(C + row * K + col) + mcd);
+      if constexpr (VEC == 4 && sizeof(T) == 4) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
+                     "f"(f.v[3]) : "memory");
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) st_multicast<T>(p + e, f.v[e]);
+      }
+    }
+    return;
+  }
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) C[(size_t)(col + e) * rows + row] = f.v[e];
@@ -139,20 +164,59 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
   }
 }
 
+// The same sum with the (column, value) pairs broadcast by shuffle instead of staged in shared memory: one dependent step
+// fewer between the crd load and the first gather.  The short-row kernel is latency-bound (rows average 10 nonzeros: one
+// chunk, one chain crd -> gather -> store per row), so it takes this form (measured: 1.24 ms against 1.40 ms staged); the
+// long-row kernel, issue- and L1-bound over runs of up to 256 nonzeros, takes the staged form (1.29 ms against 1.58 ms).
+// Always separate multiply and add: the reference's arithmetic.
+template <typename T, int VEC, int U>
+__device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const int* __restrict__ crd, const T* __restrict__ vals,
+                                                     const char* __restrict__ Bbytes, unsigned stride, int a, int b, int lane) {
+  for (int pb = a; pb < b; pb += 32) {
+    const int cnt = min(32, b - pb);
+    int my_c = 0;
+    T my_v = T(0);
+    if (lane < cnt) {
+      my_c = tbd::ldg_stream_i32(crd + pb + lane);
+      my_v = __ldg(vals + pb + lane);
+    }
+    int j = 0;
+    for (; j + U <= cnt; j += U) {
+      Frag<T, VEC> bv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned c = (unsigned)__shfl_sync(0xffffffffu, my_c, j + u);
+        bv[u] = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)c * stride));
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const T v = __shfl_sync(0xffffffffu, my_v, j + u);
+#pragma unroll
+        for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];   // mul then add: never fused
+      }
+    }
+    for (; j < cnt; j++) {
+      const unsigned c = (unsigned)__shfl_sync(0xffffffffu, my_c, j);
+      const T v = __shfl_sync(0xffffffffu, my_v, j);
+      const Frag<T, VEC> b1 = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)c * stride));
+#pragma unroll
+      for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * b1.v[x];
+    }
+  }
+}
+
 // Schedule (1): the rows of at most `long_thresh` nonzeros.  RMAP: result row r is stored at row rowmap[r] of C (TTM: the
 // rows are the fibers of a CSF tensor, rowmap their cells in the dense (i,j) plane, csf.cu).
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                const int* __restrict__ slot_rows, int long_thresh, const unsigned* __restrict__ rowmap = nullptr) {
-  __shared__ SpmmNz<T> stage_all[WARPS][32];
+                const int* __restrict__ slot_rows, int long_thresh, long long mcd, const unsigned* __restrict__ rowmap = nullptr) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
   const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
   if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
-  SpmmNz<T>* stage = stage_all[threadIdx.x >> 5];
   const int lo = rg.p0 + w * SPMM_W;
   // the slot's own window of crd / vals is needed two dependent loads from now: pull it into L2 meanwhile
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
@@ -174,7 +238,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     while (empty) {
       const int h = __ffs(empty) - 1;
       empty &= empty - 1;
-      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, mcd);
     }
     while (full) {
       const int h = __ffs(full) - 1;
@@ -183,8 +247,8 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
       const int he = __shfl_sync(0xffffffffu, e, h);
 #pragma unroll
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      spmm_accumulate<T, VEC, U, false>(acc, crd, vals, Bbytes, stride, hs, he, lane, stage);
-      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc);
+      spmm_accumulate_shfl<T, VEC, U>(acc, crd, vals, Bbytes, stride, hs, he, lane);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, mcd);
     }
   }
 }
@@ -232,42 +296,85 @@ spmm_long_find_kernel(const int* __restrict__ pos, SpmmRange rg, SpmmLongCfg cfg
   }
 }
 
+// The three plan kernels below run a fixed grid with grid-stride loops over the ACTUAL number of long rows (read from
+// `counters[0]` on the device): their cost follows the work, not the capacity (nnz / (thresh+1) rows) the scratch is sized for.
+constexpr int SPMM_PLAN_CTAS = 592;        // 148 SMs x 4
+
 // cut[p][li] (p = 0..P) = first position of long row li whose column lies in panel p or later: one binary search per
-// (row, panel boundary).  Rows beyond the number of long rows found get 0 everywhere (empty pairs).
+// (row, panel boundary).
 __global__ void __launch_bounds__(256)
 spmm_long_cut_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const int* __restrict__ long_rows,
                      const int* __restrict__ counters, SpmmLongCfg cfg, int* __restrict__ cut) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)(cfg.panels + 1) * cfg.nlong_max) return;
-  const int p = (int)(idx / cfg.nlong_max), li = (int)(idx % cfg.nlong_max);
-  int q = 0;
-  if (li < min(__ldg(counters), cfg.nlong_max)) {
+  const int nlong = min(__ldg(counters), cfg.nlong_max);
+  const long long total = (long long)(cfg.panels + 1) * nlong;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t / nlong), li = (int)(t % nlong);
     const int r = __ldg(long_rows + li);
     const int s = __ldg(pos + r), e = __ldg(pos + r + 1);
-    q = (p == 0) ? s : (p == cfg.panels) ? e : tbd::search_first_ge(crd, s, e - 1, p * cfg.panel_w);
+    cut[(long long)p * cfg.nlong_max + li] = (p == 0) ? s : (p == cfg.panels) ? e : tbd::search_first_ge(crd, s, e - 1, p * cfg.panel_w);
   }
-  cut[idx] = q;
 }
 
 // pair (p, li) = the nonzeros [cut[p][li], cut[p+1][li]) of long row li whose columns lie in panel p, cut into
-// ceil((b-a)/cap) items.  Pairs are numbered panel-major (idx = p * nlong_max + li) so that the prefix sum of the item counts
-// lays the items out in panel order; element `total` closes the scan.
+// ceil((b-a)/cap) items.  Item slots are allocated PER PANEL: a warp (32 consecutive rows of one panel) adds up its counts
+// by shuffle and takes its range with one atomicAdd on the panel's cursor (counters[8 + p]) -- no prefix sum over the
+// capacity-sized pair array.  pair_loc[p][li] = first slot inside the panel, pair_cnt[p][li] = items.  The order of the
+// items inside a panel depends on scheduling; the RESULT does not (every row adds its own partials in position order).
 __global__ void __launch_bounds__(256)
-spmm_long_count_kernel(const int* __restrict__ cut, SpmmLongCfg cfg, int* __restrict__ pair_cnt) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)cfg.panels * cfg.nlong_max;
-  if (idx > total) return;
-  pair_cnt[idx] = idx == total ? 0 : (__ldg(cut + idx + cfg.nlong_max) - __ldg(cut + idx) + cfg.cap - 1) / cfg.cap;
+spmm_long_alloc_kernel(const int* __restrict__ cut, int* __restrict__ counters, SpmmLongCfg cfg, int* __restrict__ pair_loc,
+                       int* __restrict__ pair_cnt) {
+  const int nlong = min(__ldg(counters), cfg.nlong_max);
+  const int lane = threadIdx.x & 31;
+  const int per = (nlong + 31) & ~31;                        // rows of a panel padded to whole warps
+  const long long total = (long long)cfg.panels * per;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t / per), li = (int)(t % per);       // warp-uniform p
+    int c = 0;
+    if (li < nlong) {
+      const long long idx = (long long)p * cfg.nlong_max + li;
+      c = (__ldg(cut + idx + cfg.nlong_max) - __ldg(cut + idx) + cfg.cap - 1) / cfg.cap;
+    }
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && warp_total > 0) base = atomicAdd(counters + 8 + p, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (li < nlong) {
+      const long long idx = (long long)p * cfg.nlong_max + li;
+      pair_loc[idx] = base + incl - c;
+      pair_cnt[idx] = c;
+    }
+  }
+}
+
+// counters[8 + p] (items of panel p) -> counters[48 + p] = first item of panel p, counters[2] = number of items
+__global__ void spmm_long_bases_kernel(int* __restrict__ counters, int panels) {
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int p = 0; p < panels; p++) { counters[48 + p] = run; run += counters[8 + p]; }
+    counters[2] = run;
+  }
 }
 
 __global__ void __launch_bounds__(256)
-spmm_long_items_kernel(const int* __restrict__ cut, const int* __restrict__ pair_off, SpmmLongCfg cfg, int2* __restrict__ items) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)cfg.panels * cfg.nlong_max) return;
-  const int o = __ldg(pair_off + idx), c = __ldg(pair_off + idx + 1) - o;
-  if (c == 0) return;
-  const int a = __ldg(cut + idx), b = __ldg(cut + idx + cfg.nlong_max);
-  for (int j = 0; j < c; j++) items[o + j] = make_int2(a + j * cfg.cap, min(a + (j + 1) * cfg.cap, b));
+spmm_long_items_kernel(const int* __restrict__ cut, const int* __restrict__ pair_loc, const int* __restrict__ pair_cnt,
+                       const int* __restrict__ counters, SpmmLongCfg cfg, int2* __restrict__ items) {
+  const int nlong = min(__ldg(counters), cfg.nlong_max);
+  const long long total = (long long)cfg.panels * nlong;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t / nlong), li = (int)(t % nlong);
+    const long long idx = (long long)p * cfg.nlong_max + li;
+    const int c = __ldg(pair_cnt + idx);
+    if (c == 0) continue;
+    const int o = __ldg(counters + 48 + p) + __ldg(pair_loc + idx);
+    const int a = __ldg(cut + idx), b = __ldg(cut + idx + cfg.nlong_max);
+    for (int j = 0; j < c; j++) items[o + j] = make_int2(a + j * cfg.cap, min(a + (j + 1) * cfg.cap, b));
+  }
 }
 
 // Persistent warps take items in panel order (tickets of SPMM_LONG_CHUNK items) and store one partial row sum per item.
@@ -275,13 +382,12 @@ constexpr int SPMM_LONG_CHUNK = 4;
 template <typename T, int VEC, int U, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_long_kernel(const int* __restrict__ crd, const T* __restrict__ vals, const T* __restrict__ B, int K,
-                 const int2* __restrict__ items, const int* __restrict__ pair_off, long long total_pairs, int* __restrict__ counters,
-                 T* __restrict__ partials) {
+                 const int2* __restrict__ items, int* __restrict__ counters, T* __restrict__ partials) {
   __shared__ SpmmNz<T> stage_all[WARPS][32];
   SpmmNz<T>* stage = stage_all[threadIdx.x >> 5];
   const unsigned stride = (unsigned)K * (unsigned)sizeof(T);
   const int lane = threadIdx.x & 31;
-  const int nitems = __ldg(pair_off + total_pairs);
+  const int nitems = *(volatile int*)(counters + 2);
   for (;;) {
     int base = 0;
     if (lane == 0) base = atomicAdd(counters + 1, SPMM_LONG_CHUNK);
@@ -310,19 +416,21 @@ spmm_long_kernel(const int* __restrict__ crd, const T* __restrict__ vals, const 
 // One warp per long row: its partials added in ascending panel / item (= position) order, the row of C stored once.
 template <typename T, int VEC, bool COLMAJOR, bool RMAP>
 __global__ void __launch_bounds__(256)
-spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restrict__ counters, const int* __restrict__ pair_off,
+spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restrict__ counters, const int* __restrict__ pair_loc,
+                         const int* __restrict__ pair_cnt,
                          SpmmLongCfg cfg, const T* __restrict__ partials, T* __restrict__ C, int rows, int K,
-                         const unsigned* __restrict__ rowmap) {
+                         const unsigned* __restrict__ rowmap, long long mcd) {
   const int lane = threadIdx.x & 31;
-  const int li = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (li >= min(__ldg(counters), cfg.nlong_max)) return;
+  const int nlong = min(__ldg(counters), cfg.nlong_max);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int li = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); li < nlong; li += nwarps) {   // fixed grid, actual work
   const int r = __ldg(long_rows + li);
   const size_t orow = RMAP ? (size_t)__ldg(rowmap + r) : (size_t)r;
   int o = 0, c = 0;
   if (lane < cfg.panels) {
     const long long idx = (long long)lane * cfg.nlong_max + li;
-    o = __ldg(pair_off + idx);
-    c = __ldg(pair_off + idx + 1) - o;
+    c = __ldg(pair_cnt + idx);
+    o = __ldg(counters + 48 + lane) + __ldg(pair_loc + idx);
   }
   for (int c0 = 0; c0 < K; c0 += 32 * VEC) {
     const int col = c0 + lane * VEC;
@@ -345,7 +453,8 @@ spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restric
           }
       }
     }
-    if (active) store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc);
+    if (active) store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc, mcd);
+  }
   }
 }
 
@@ -375,14 +484,14 @@ static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es) {
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <typename T, int VEC, int U, int MINB>
-static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const int2* items, const int* pair_off, long long pairs,
-                         int* counters, T* partials, cudaStream_t st) {
+static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const int2* items, int* counters, T* partials,
+                         cudaStream_t st) {
   constexpr int WARPS = 8;
   // persistent grid: MINB CTAs per SM by default; TACO_B200_SPMM_LONGCTAS caps it so that the slot kernel (side by side on the
   // other stream) keeps part of every SM
   static const int cap = env_int("TACO_B200_SPMM_LONGCTAS", 0);
   const int per_sm = cap > 0 && cap < MINB ? cap : MINB;
-  spmm_long_kernel<T, VEC, U, WARPS, MINB><<<num_sms() * per_sm, WARPS * 32, 0, st>>>(crd, vals, B, K, items, pair_off, pairs, counters, partials);
+  spmm_long_kernel<T, VEC, U, WARPS, MINB><<<num_sms() * per_sm, WARPS * 32, 0, st>>>(crd, vals, B, K, items, counters, partials);
 }
 
 // Builds the plan on the compute stream, then runs the item kernel and the combine kernel on `run_st` (the compute stream
@@ -390,10 +499,13 @@ static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const
 // gathers by the L2 -> SM path, the short rows by HBM).  *scratch_out is released by the caller after the streams have joined.
 template <typename T, int VEC, bool COLMAJOR, bool RMAP>
 static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int cols, int K, SpmmRange rg,
-                          const SpmmLongCfg& cfg, const unsigned* rowmap, cudaStream_t run_st, cudaEvent_t fork, void** scratch_out) {
+                          const SpmmLongCfg& cfg, const unsigned* rowmap, cudaStream_t run_st, cudaEvent_t fork, void** scratch_out,
+                          long long mcd) {
   const long long pairs = (long long)cfg.panels * cfg.nlong_max;
-  const size_t o_cnt = 0, o_rows = align256(16), o_ab = o_rows + align256(sizeof(int) * (size_t)cfg.nlong_max),
-               o_off = o_ab + align256(sizeof(int) * (size_t)(pairs + cfg.nlong_max)), o_items = o_off + align256(sizeof(int) * (size_t)(pairs + 1)),
+  // counters: [0] long rows, [1] item ticket, [2] items, [8..8+P) items per panel, [48..48+P) first item of a panel
+  const size_t o_cnt = 0, o_rows = align256(sizeof(int) * 96), o_ab = o_rows + align256(sizeof(int) * (size_t)cfg.nlong_max),
+               o_off = o_ab + align256(sizeof(int) * (size_t)(pairs + cfg.nlong_max)), o_pc = o_off + align256(sizeof(int) * (size_t)pairs),
+               o_items = o_pc + align256(sizeof(int) * (size_t)pairs),
                o_part = o_items + align256(sizeof(int2) * (size_t)cfg.items_max),
                total = o_part + align256(sizeof(T) * (size_t)cfg.items_max * K);
   void* buf = nullptr;
@@ -403,18 +515,19 @@ static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T
   int* counters = (int*)(b + o_cnt);
   int* long_rows = (int*)(b + o_rows);
   int* cut = (int*)(b + o_ab);
-  int* pair_off = (int*)(b + o_off);
+  int* pair_loc = (int*)(b + o_off);
+  int* pair_cnt = (int*)(b + o_pc);
   int2* items = (int2*)(b + o_items);
   T* partials = (T*)(b + o_part);
   cudaStream_t st = stream();
-  cudaError_t e = cudaMemsetAsync(counters, 0, 16, st);
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int) * 96, st);
   if (e != cudaSuccess) return fail(TACO_B200_ERR_CUDA, "spmm: memset failed: %s", cudaGetErrorString(e));
   const int nrows = rg.r1 - rg.r0;
   spmm_long_find_kernel<<<(nrows + 256 * SPMM_FIND_ROWS - 1) / (256 * SPMM_FIND_ROWS), 256, 0, st>>>(pos, rg, cfg, long_rows, counters);
-  spmm_long_cut_kernel<<<(unsigned)((pairs + cfg.nlong_max + 255) / 256), 256, 0, st>>>(pos, crd, long_rows, counters, cfg, cut);
-  spmm_long_count_kernel<<<(unsigned)((pairs + 1 + 255) / 256), 256, 0, st>>>(cut, cfg, pair_off);
-  TB_TRY(exclusive_scan_i32(pair_off, pair_off, pairs + 1));
-  spmm_long_items_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(cut, pair_off, cfg, items);
+  spmm_long_cut_kernel<<<SPMM_PLAN_CTAS, 256, 0, st>>>(pos, crd, long_rows, counters, cfg, cut);
+  spmm_long_alloc_kernel<<<SPMM_PLAN_CTAS, 256, 0, st>>>(cut, counters, cfg, pair_loc, pair_cnt);
+  spmm_long_bases_kernel<<<1, 32, 0, st>>>(counters, cfg.panels);
+  spmm_long_items_kernel<<<SPMM_PLAN_CTAS, 256, 0, st>>>(cut, pair_loc, pair_cnt, counters, cfg, items);
   if (run_st != st) {
     TB_CUDA(cudaEventRecord(fork, st));
     TB_CUDA(cudaStreamWaitEvent(run_st, fork, 0));
@@ -423,14 +536,14 @@ static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T
   // parallelism pays more than occupancy here (TACO_B200_SPMM_LONGVAR sweeps it)
   static const int lvar = env_int("TACO_B200_SPMM_LONGVAR", 0);
   switch (lvar) {
-    case 1: spmm_long_go<T, VEC, 2, 8>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
-    case 2: spmm_long_go<T, VEC, 4, 4>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
-    case 3: spmm_long_go<T, VEC, 8, 4>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
-    case 4: spmm_long_go<T, VEC, 8, 3>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
-    default: spmm_long_go<T, VEC, 4, 6>(crd, vals, B, K, items, pair_off, pairs, counters, partials, run_st); break;
+    case 1: spmm_long_go<T, VEC, 2, 8>(crd, vals, B, K, items, counters, partials, run_st); break;
+    case 2: spmm_long_go<T, VEC, 4, 4>(crd, vals, B, K, items, counters, partials, run_st); break;
+    case 3: spmm_long_go<T, VEC, 8, 4>(crd, vals, B, K, items, counters, partials, run_st); break;
+    case 4: spmm_long_go<T, VEC, 8, 3>(crd, vals, B, K, items, counters, partials, run_st); break;
+    default: spmm_long_go<T, VEC, 4, 6>(crd, vals, B, K, items, counters, partials, run_st); break;
   }
-  spmm_long_combine_kernel<T, VEC, COLMAJOR, RMAP><<<(unsigned)(((long long)cfg.nlong_max * 32 + 255) / 256), 256, 0, run_st>>>(
-      long_rows, counters, pair_off, cfg, partials, C, rows, K, rowmap);
+  spmm_long_combine_kernel<T, VEC, COLMAJOR, RMAP><<<num_sms() * 8, 256, 0, run_st>>>(
+      long_rows, counters, pair_loc, pair_cnt, cfg, partials, C, rows, K, rowmap, mcd);
   count_launch(7);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
@@ -440,10 +553,10 @@ static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T
 // selects one for tuning runs; the default is the measured best at config C2 (profiles/).
 template <typename T, int VEC, bool COLMAJOR, bool RMAP, int U, int WARPS, int MINB>
 static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
-                    const int* slot_rows, int long_thresh, const unsigned* rowmap, cudaStream_t st) {
+                    const int* slot_rows, int long_thresh, const unsigned* rowmap, long long mcd, cudaStream_t st) {
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
   spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, RMAP><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                       slot_rows, long_thresh, rowmap);
+                                                                                       slot_rows, long_thresh, mcd, rowmap);
 }
 
 // The whole SpMM launch sequence over a row range: long-row plan + column-panel kernels, then the slot kernel.
@@ -456,6 +569,8 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   void* slot_rows = nullptr;
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
   ProfScope ps(prof_name);
+  // a result inside the registered multicast window is stored through the NVLink multicast mapping (fused all-gather)
+  const long long mcd = RMAP ? 0 : multicast_delta(C, sizeof(T) * (size_t)rows * K);
   const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
   static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 0);
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
@@ -467,7 +582,7 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   void* long_scratch = nullptr;
   int rc = TACO_B200_OK;
   if (cfg.nlong_max > 0)
-    rc = spmm_long_rows<T, VEC, COLMAJOR, RMAP>(pos, crd, vals, B, C, rows, cols, K, rg, cfg, rowmap, side, ev_fork, &long_scratch);
+    rc = spmm_long_rows<T, VEC, COLMAJOR, RMAP>(pos, crd, vals, B, C, rows, cols, K, rg, cfg, rowmap, side, ev_fork, &long_scratch, mcd);
   if (rc != TACO_B200_OK) {
     if (side != stream()) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(stream(), ev_join, 0); }
     scratch_free(long_scratch); scratch_free(slot_rows);
@@ -478,11 +593,11 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   const int* sr = (const int*)slot_rows;
   cudaStream_t st = stream();
   switch (variant) {
-    case 1: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
-    case 2: spmm_go<T, VEC, COLMAJOR, RMAP, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
-    case 3: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
-    case 4: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
-    default: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, st); break;
+    case 1: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
+    case 2: spmm_go<T, VEC, COLMAJOR, RMAP, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
+    case 3: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
+    case 4: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
+    default: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
   }
   count_launch(2);
   if (side != stream()) {                 // join: the scratch is released (stream-ordered) only after the side stream is done

@@ -396,6 +396,11 @@ def use_torch_stream():
     check(lib.taco_b200_set_stream(ctypes.c_void_p(h if h else 1)))
 
 
+def set_result_multicast(local_ptr, multicast_ptr, nbytes):
+    """dense results inside [local_ptr, local_ptr + nbytes) are stored through the NVLink multicast mapping (None clears)"""
+    check(lib.taco_b200_set_result_multicast(ctypes.c_void_p(local_ptr or 0), ctypes.c_void_p(multicast_ptr or 0), int(nbytes or 0)))
+
+
 def synchronize():
     check(lib.taco_b200_synchronize())
 
