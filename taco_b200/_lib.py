@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtaco_b200.so")
+# TACO_B200_LIB (the variable the compileSource stub and the patched taco use) may point at another build of the library
+LIB_PATH = os.environ.get("TACO_B200_LIB") or os.path.join(_HERE, "lib", "libtaco_b200.so")
 
 
 class TacoError(RuntimeError):
@@ -47,6 +48,16 @@ if not os.path.exists(LIB_PATH):
 
 lib = ctypes.CDLL(LIB_PATH)
 
+
+class _Optional:
+    """argtypes of entry points an older build of the library (A/B runs through TACO_B200_LIB) may not export yet"""
+    argtypes = restype = None
+
+
+def _sym(name):
+    return getattr(lib, name) if hasattr(lib, name) else _Optional()
+
+
 FAMILIES = ("spmv", "spmm", "spmm_dcsr", "sddmm", "sddmm_dense", "mttkrp", "ttv", "ttm", "spadd", "spgemm", "bspmv", "bspmm")
 NARGS = {"spmv": 3, "spmm": 3, "spmm_dcsr": 3, "sddmm": 4, "sddmm_dense": 4, "mttkrp": 4, "ttv": 3, "ttm": 3, "spadd": 3, "spgemm": 3, "bspmv": 3,
          "bspmm": 3}
@@ -63,13 +74,13 @@ lib.taco_b200_host_free.argtypes = [ctypes.c_void_p]
 lib.taco_b200_device_alloc.restype = ctypes.c_void_p
 lib.taco_b200_device_alloc.argtypes = [ctypes.c_size_t]
 lib.taco_b200_free.argtypes = [ctypes.c_void_p]
-lib.taco_b200_set_result_multicast.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+_sym("taco_b200_set_result_multicast").argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_make_resident.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_invalidate.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_open.restype = ctypes.c_void_p
 lib.taco_b200_module_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
-lib.taco_b200_module_open_args.restype = ctypes.c_void_p
-lib.taco_b200_module_open_args.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+_sym("taco_b200_module_open_args").restype = ctypes.c_void_p
+_sym("taco_b200_module_open_args").argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
 lib.taco_b200_module_family.restype = ctypes.c_char_p
 lib.taco_b200_module_family.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_num_args.argtypes = [ctypes.c_void_p]
@@ -78,8 +89,8 @@ lib.taco_b200_module_get_func_ptr.restype = ctypes.c_void_p
 lib.taco_b200_module_get_func_ptr.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
 lib.taco_b200_pack.argtypes = [_TP, _TP]
 lib._shim_taco_b200_pack.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
-lib.taco_b200_read.argtypes = [ctypes.c_char_p, _TP]
-lib._shim_taco_b200_read.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+_sym("taco_b200_read").argtypes = [ctypes.c_char_p, _TP]
+_sym("_shim_taco_b200_read").argtypes = [ctypes.POINTER(ctypes.c_void_p)]
 lib.taco_b200_partition_pos.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
 for _f in FAMILIES:
     for _p in PHASES:

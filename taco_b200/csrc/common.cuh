@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/taco_b200.h"
@@ -80,6 +81,13 @@ struct ProfScope {
 // a non-zero distance store their result rows through the multicast address: one store, delivered by the NVSwitch to every
 // GPU of the group (the local one included) -- the all-gather of the result happens inside the kernel.
 long long multicast_delta(const void* p, size_t bytes);
+
+// A persistent 256-byte device buffer for tiny synchronous reductions (counters read back right away).  Deliberately NOT a
+// pool allocation: a 16-byte cudaMallocAsync between the large result arrays of consecutive calls splits the pool's big free
+// blocks, and every other call then pays milliseconds for fresh physical memory (measured on SpAdd: 0.25 -> 0.6-6 ms).
+// The caller holds small_scratch_mutex() from the first use until its read-back has completed.
+void* small_scratch();
+std::mutex& small_scratch_mutex();
 
 // stream-ordered scratch
 int scratch_alloc(void** p, size_t bytes);

@@ -186,6 +186,17 @@ ProfScope::~ProfScope() {
   cudaEventRecord(g.prof[slot].pending.back().second, g.cur_stream);
 }
 
+void* small_scratch() {
+  static void* buf = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] { if (cudaMalloc(&buf, 256) != cudaSuccess) { buf = nullptr; cudaGetLastError(); } });
+  return buf;
+}
+std::mutex& small_scratch_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 int scratch_alloc(void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;

@@ -85,19 +85,18 @@ total_i64_kernel(const int* __restrict__ in, long long n, unsigned long long* __
 
 // reads the total back (one synchronisation -- the caller needs the size on the host anyway) and refuses sizes beyond int32
 static int checked_total_i32(const int* counts, long long n, const char* what, int32_t* total_out) {
-  void* d = nullptr;
-  TB_TRY(scratch_alloc(&d, sizeof(unsigned long long)));
+  std::lock_guard<std::mutex> lk(small_scratch_mutex());
+  void* d = small_scratch();
+  if (!d) return fail(TACO_B200_ERR_ALLOC, "no device scratch");
   cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), stream());
-  if (e != cudaSuccess) { scratch_free(d); return fail(TACO_B200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) return fail(TACO_B200_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
   if (n > 0) {
     const long long ctas = (n + 2047) / 2048;
     total_i64_kernel<<<(unsigned)(ctas < 1184 ? ctas : 1184), 256, 0, stream()>>>(counts, n, (unsigned long long*)d);
     count_launch(1);
   }
   unsigned long long h = 0;
-  const int rc = read_back(&h, d, sizeof(h));
-  scratch_free(d);
-  TB_TRY(rc);
+  TB_TRY(read_back(&h, d, sizeof(h)));
   if (h > (unsigned long long)INT32_MAX)
     return fail(TACO_B200_ERR_ARG, "%s: the result has %llu stored entries, more than int32 positions can address", what, h);
   *total_out = (int32_t)h;

@@ -207,20 +207,25 @@ __device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const in
 
 // Schedule (1): the rows of at most `long_thresh` nonzeros.  RMAP: result row r is stored at row rowmap[r] of C (TTM: the
 // rows are the fibers of a CSF tensor, rowmap their cells in the dense (i,j) plane, csf.cu).
-template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false>
+// MC: the result goes out through the multicast mapping (`mcd_arg` bytes away); a template flag so that the common
+// single-GPU instantiation does not carry the offset in registers (32-register budget, every spill is in the per-row path)
+template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false, bool MC = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                const int* __restrict__ slot_rows, int long_thresh, long long mcd, const unsigned* __restrict__ rowmap = nullptr) {
+                const int* __restrict__ slot_rows, int long_thresh, long long mcd_arg, const unsigned* __restrict__ rowmap = nullptr) {
+  const long long mcd = MC ? mcd_arg : 0;
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
-  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
-  if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
   const int lo = rg.p0 + w * SPMM_W;
-  // the slot's own window of crd / vals is needed two dependent loads from now: pull it into L2 meanwhile
+  // the slot's own window of crd / vals is needed three dependent loads from now (slot_rows -> pos -> crd): pull it into L2
+  // meanwhile.  Issued before anything is known about the slot -- slots inside a long row fetch 512 bytes for nothing (+0.4 GB
+  // at C2), but placing it after the slot_rows load cost the latency-bound short-row kernels 15 % (TTM 2.50 -> 2.93 ms)
   if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(crd + lo + lane * 32));
   else if (lane < 2 + (int)(2 * sizeof(T) / 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + lo + (lane - 2) * (128 / (int)sizeof(T))));
+  const int R0 = __ldg(slot_rows + w), R1 = __ldg(slot_rows + w + 1);
+  if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
   const int col = (blockIdx.y * 32 + lane) * VEC;
   const bool active = col < K;
   const char* Bbytes = (const char*)(B + (active ? col : 0));        // inactive lanes (ragged K) gather column 0 and never store
@@ -555,8 +560,12 @@ template <typename T, int VEC, bool COLMAJOR, bool RMAP, int U, int WARPS, int M
 static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
                     const int* slot_rows, int long_thresh, const unsigned* rowmap, long long mcd, cudaStream_t st) {
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, RMAP><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                       slot_rows, long_thresh, mcd, rowmap);
+  if (mcd != 0 && !RMAP)
+    spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, false, true><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
+                                                                                               slot_rows, long_thresh, mcd, rowmap);
+  else
+    spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, RMAP, false><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
+                                                                                                slot_rows, long_thresh, 0, rowmap);
 }
 
 // The whole SpMM launch sequence over a row range: long-row plan + column-panel kernels, then the slot kernel.
@@ -572,7 +581,7 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   // a result inside the registered multicast window is stored through the NVLink multicast mapping (fused all-gather)
   const long long mcd = RMAP ? 0 : multicast_delta(C, sizeof(T) * (size_t)rows * K);
   const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
-  static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 0);
+  static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 1);
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
   if (!ev_fork) {
     TB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));

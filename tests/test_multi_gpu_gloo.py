@@ -93,3 +93,23 @@ def test_shard_rebase_is_consistent():
             assert sh["pos"][0] == 0 and sh["pos"][-1] == sh["crd"].shape[0] == sh["vals"].shape[0]
             tot += int(sh["crd"].shape[0])
         assert tot == 7000
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_csf_shards_with_rebased_rows_are_self_contained(world):
+    """shard_csf3(rebase_rows=True): every shard is an MTTKRP over its OWN rows of the result (row ids rebased, contiguous row
+    ranges that tile [0, I)); the concatenated blocks equal the single-process oracle bit for bit"""
+    import oracle
+    import synth
+    from taco_b200 import partition
+    t = synth.make("mttkrp", None, I=3000, K=200, L=150, nnz=40_000, R=8, dtype="float64")
+    I, K, L, R = t["dims"]
+    full = oracle.mttkrp(t, t["C"].reshape(K, R), t["D"].reshape(L, R), I)
+    blocks, nxt = [], 0
+    for r in range(world):
+        st = partition.shard_csf3(t, r, world, rebase_rows=True, dim0=I)
+        assert st["row_begin"] == nxt and st["row_end"] >= st["row_begin"]
+        nxt = st["row_end"]
+        blocks.append(oracle.mttkrp(st, t["C"].reshape(K, R), t["D"].reshape(L, R), st["row_end"] - st["row_begin"]))
+    assert nxt == I
+    assert np.array_equal(np.concatenate(blocks), full)

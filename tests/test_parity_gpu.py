@@ -855,3 +855,42 @@ def test_pack_then_compute_and_edge_cases():
     assert G.to_host(E.level(0)[0]).tolist() == [0, 0]
     with pytest.raises(tb.TacoError):
         tb.pack("B", [6, 5], tb.Format([tb.dense, tb.dense]), [z, z], np.zeros(0))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the _shim_ entry points (void** parameterPack, codegen_cuda.cpp:1500-1540) are CALLED, not only exported
+# ---------------------------------------------------------------------------------------------------------
+def test_shims_are_called_through_the_packed_convention(tmp_path):
+    import ctypes
+    from taco_b200 import _lib
+    w = synth.make("spmv", None, n=20_011, deg=9)
+    y = tb.Tensor("y", [20_011], tb.Format([tb.dense]), np.float64)
+    A = tb.makeCSR("A", [20_011, 20_011], w["A_pos"], w["A_crd"], w["A_vals"])
+    x = tb.makeDense("x", [20_011], w["x"])
+    pack = (ctypes.c_void_p * 3)(*[ctypes.cast(t.ptr, ctypes.c_void_p) for t in (y, A, x)])
+    tb.set_result_space("host")
+    _lib.check(_lib.lib._shim_taco_b200_spmv_assemble(pack))
+    y.adopt_results()
+    _lib.check(_lib.lib._shim_taco_b200_spmv_compute(pack))
+    assert np.array_equal(y.vals(), oracle.spmv(w["A_pos"], w["A_crd"], w["A_vals"], w["x"]))
+    # sparse result through the shim of evaluate
+    s = synth.make("spadd", None, n=5_003, deg=7)
+    C = tb.Tensor("C", [5_003, 5_003], tb.CSR, np.float64)
+    Aa = tb.makeCSR("A", [5_003, 5_003], s["A_pos"], s["A_crd"], s["A_vals"])
+    Bb = tb.makeCSR("B", [5_003, 5_003], s["B_pos"], s["B_crd"], s["B_vals"])
+    pack = (ctypes.c_void_p * 3)(*[ctypes.cast(t.ptr, ctypes.c_void_p) for t in (C, Aa, Bb)])
+    _lib.check(_lib.lib._shim_taco_b200_spadd_evaluate(pack))
+    C.adopt_results()
+    cp, cc, cv = oracle.spadd(s["A_pos"], s["A_crd"], s["A_vals"], s["B_pos"], s["B_crd"], s["B_vals"])
+    assert np.array_equal(C.level(1)[0], cp) and np.array_equal(C.level(1)[1], cc) and np.array_equal(C.vals(), cv)
+    # _shim_taco_b200_read: (path, tensor)
+    path = tmp_path / "m.mtx"
+    path.write_text("%%MatrixMarket matrix coordinate real general\n3 4 3\n1 1 2.5\n3 4 -1e-3\n2 2 7\n")
+    T = tb.Tensor("T", [0, 0], tb.CSR, np.float64)
+    bpath = ctypes.create_string_buffer(str(path).encode())
+    pack2 = (ctypes.c_void_p * 2)(ctypes.cast(bpath, ctypes.c_void_p), ctypes.cast(T.ptr, ctypes.c_void_p))
+    _lib.check(_lib.lib._shim_taco_b200_read(pack2))
+    T.dims = [int(T._dims[0]), int(T._dims[1])]
+    T.adopt_results()
+    assert T.dims == [3, 4] and T.level(1)[0].tolist() == [0, 1, 2, 3] and T.level(1)[1].tolist() == [0, 1, 3]
+    assert T.vals().tolist() == [2.5, 7.0, -1e-3]

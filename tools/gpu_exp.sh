@@ -1,5 +1,4 @@
 #!/bin/bash
-# Experiment pass on one GPU box.  outputs: gpurun_out/exp_*.txt
 mkdir -p gpurun_out
 summ='import sys,json
 for l in sys.stdin:
@@ -13,32 +12,15 @@ run() {  # workload, env assignments...
   env "$@" timeout 600 python bench.py --workload $wl --no-e2e --no-cpu --steps 10 2>&1 | tail -1 | python -c "$summ"
 }
 {
-timeout 2400 python -m pytest tests/test_parity_gpu.py tests/test_multi_gpu_gpu.py tests/test_fullsize_gpu.py -m gpu -q -x -k "spmm or ttm or dcsr or shards or c2 or spadd or sparse" 2>&1 | tail -4
-run spmm X=0
-run spmm TACO_B200_SPMM_PANELS=16
-run spmm TACO_B200_SPMM_PANELS=24
-run spmm TACO_B200_SPMM_LONG=96
-run spmm TACO_B200_SPMM_LONG=192
-run spmm TACO_B200_SPMM_CAP=512
-run spmm TACO_B200_SPMM_OVERLAP=1
 run ttm X=0
-run spadd X=0
-run spadd X=0
-run spgemm X=0
-python - <<'PY'
-import sys, time
-sys.path[:0]=['.','tests','oracle']
-import torch, gpu_util as G, synth, taco_b200 as tb
-tb.use_torch_stream(); tb.set_result_space("device")
-w = synth.make("spadd", "cuda")
-k, ts = G.build("spadd", w)
-for _ in range(5): k(*ts)
-torch.cuda.synchronize()
-for rep in range(3):
-    t0=time.perf_counter()
-    for _ in range(20): k(*ts)
-    torch.cuda.synchronize()
-    print("spadd wall per call ms", (time.perf_counter()-t0)/20*1e3)
-PY
-} > gpurun_out/exp_r2_8.txt 2>&1
-cat gpurun_out/exp_r2_8.txt
+run ttm TACO_B200_LIB=$PWD/tools/ab/libtaco_b200_r1.so
+run spmm X=0
+run spmm TACO_B200_LIB=$PWD/tools/ab/libtaco_b200_r1.so
+run mttkrp X=0
+run mttkrp TACO_B200_LIB=$PWD/tools/ab/libtaco_b200_r1.so
+run sddmm X=0
+run sddmm TACO_B200_LIB=$PWD/tools/ab/libtaco_b200_r1.so
+run spmv X=0
+run spmv TACO_B200_LIB=$PWD/tools/ab/libtaco_b200_r1.so
+} > gpurun_out/exp_r2_11.txt 2>&1
+cat gpurun_out/exp_r2_11.txt
