@@ -183,12 +183,13 @@ __device__ __forceinline__ void mk_store(T* dst, T v, long long mcd) {
   else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"((char*)dst + mcd), "d"(v) : "memory");
 }   // fibers, leaves, row of A, first row to zero before `row`
 
-template <typename T, int U, int WARPS, int MINB, bool SINGLE>
+template <typename T, int U, int WARPS, int MINB, bool SINGLE, bool MC>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
-                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed, long long mcd) {
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed, long long mcd_arg) {
+  const long long mcd = MC ? mcd_arg : 0;         // a template flag: the single-GPU instantiation keeps the offset out of its registers
   __shared__ MkLeaf<T> stage_all[WARPS][32];
   __shared__ MkSlice meta_all[WARPS][32];
   __shared__ int s_ticket;
@@ -376,14 +377,13 @@ static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslo
   // The single-pass specialisation (R <= 32) spills less but measures SLOWER at C4 (23.1 vs 16.7 ms, same box, A/B):
   // ptxas unrolls the leaf loop of the general version four deep, which is what keeps HBM at 98 % of its peak.
   static const bool single = getenv("TACO_B200_MTTKRP_SINGLE") != nullptr;
-  if (R <= 32 && single)
-    mttkrp_csf_kernel<T, U, WARPS, MINB, true><<<grid, WARPS * 32, 0, stream()>>>(
-        cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd);
-  else
-    mttkrp_csf_kernel<T, U, WARPS, MINB, false><<<grid, WARPS * 32, 0, stream()>>>(
-        cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C,
-        D, A, R, cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd);
+#define TB_MK_GO(SINGLE, MC)                                                                                                   \
+  mttkrp_csf_kernel<T, U, WARPS, MINB, SINGLE, MC><<<grid, WARPS * 32, 0, stream()>>>(                                            \
+      cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D, A, R, \
+      cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd)
+  if (R <= 32 && single) { if (mcd) TB_MK_GO(true, true); else TB_MK_GO(true, false); }
+  else { if (mcd) TB_MK_GO(false, true); else TB_MK_GO(false, false); }
+#undef TB_MK_GO
 }
 
 template <typename T>

@@ -980,19 +980,13 @@ static int spadd_assemble_impl(taco_tensor_t* C, Csr3& s, const T* av, const T* 
   } else {
     TB_CUDA(cudaMemsetAsync(dpos, 0, sizeof(int), stream()));
   }
-  static const bool trace = getenv("TACO_B200_TRACE") != nullptr;
-  auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-  const double t0 = trace ? now_us() : 0;
   int32_t nnzC = 0;             // 64-bit total of the row counts first: refuses results beyond int32 instead of wrapping
   if (checked_total_i32(dpos, n, "spadd", &nnzC) != TACO_B200_OK) { device_result_free(dpos); return TACO_B200_ERR_ARG; }
-  const double t1 = trace ? now_us() : 0;
   TB_TRY(exclusive_scan_i32(dpos, dpos, (long long)n + 1));
-  const double t2 = trace ? now_us() : 0;
   int* dcrd = nullptr;
   TB_TRY(device_result_alloc((void**)&dcrd, sizeof(int) * (size_t)(nnzC > 0 ? nnzC : 1)));
   void* dvals = nullptr;
   if (with_vals) TB_TRY(device_result_alloc(&dvals, sizeof(T) * (size_t)(nnzC > 0 ? nnzC : 1)));
-  if (trace) fprintf(stderr, "spadd trace: total+sync %.0f us, scan launches %.0f us, allocs %.0f us\n", t1 - t0, t2 - t1, now_us() - t2);
   if (n > 0 && nnzC > 0) {
     if (with_vals) {
       ProfScope ps("spadd_numeric");

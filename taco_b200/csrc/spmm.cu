@@ -168,10 +168,12 @@ __device__ __forceinline__ void spmm_accumulate(Frag<T, VEC>& acc, const int* __
 // fewer between the crd load and the first gather.  The short-row kernel is latency-bound (rows average 10 nonzeros: one
 // chunk, one chain crd -> gather -> store per row), so it takes this form (measured: 1.24 ms against 1.40 ms staged); the
 // long-row kernel, issue- and L1-bound over runs of up to 256 nonzeros, takes the staged form (1.29 ms against 1.58 ms).
+// The row address is the plain element form Bcol + (size_t)c * K here: the byte form with IMAD.WIDE.U32 that pays in the
+// issue-bound long kernel measured SLOWER in this latency-bound one (same-box A/B: TTM 3.16 -> 2.47 ms, C2 2.85 -> 2.74 ms).
 // Always separate multiply and add: the reference's arithmetic.
 template <typename T, int VEC, int U>
 __device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const int* __restrict__ crd, const T* __restrict__ vals,
-                                                     const char* __restrict__ Bbytes, unsigned stride, int a, int b, int lane) {
+                                                     const T* __restrict__ Bcol, int K, int a, int b, int lane) {
   for (int pb = a; pb < b; pb += 32) {
     const int cnt = min(32, b - pb);
     int my_c = 0;
@@ -185,8 +187,8 @@ __device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const in
       Frag<T, VEC> bv[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const unsigned c = (unsigned)__shfl_sync(0xffffffffu, my_c, j + u);
-        bv[u] = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)c * stride));
+        const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+        bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -195,12 +197,24 @@ __device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const in
         for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];   // mul then add: never fused
       }
     }
-    for (; j < cnt; j++) {
-      const unsigned c = (unsigned)__shfl_sync(0xffffffffu, my_c, j);
-      const T v = __shfl_sync(0xffffffffu, my_v, j);
-      const Frag<T, VEC> b1 = load_row<T, VEC>((const T*)(Bbytes + (unsigned long long)c * stride));
+    if (j < cnt) {                      // 1 .. U-1 left: same two phases, warp-uniform predicates (no loop: at most U-1 gathers)
+      const int rem = cnt - j;
+      Frag<T, VEC> bv[U > 1 ? U - 1 : 1];
 #pragma unroll
-      for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * b1.v[x];
+      for (int u = 0; u < U - 1; u++) {
+        if (u < rem) {
+          const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+          bv[u] = load_row<T, VEC>(Bcol + (size_t)c * K);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U - 1; u++) {
+        if (u < rem) {
+          const T v = __shfl_sync(0xffffffffu, my_v, j + u);
+#pragma unroll
+          for (int x = 0; x < VEC; x++) acc.v[x] = acc.v[x] + v * bv[u].v[x];
+        }
+      }
     }
   }
 }
@@ -228,8 +242,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   if (R1 <= R0) return;                 // the slot lies inside one row that started earlier (typically a long row)
   const int col = (blockIdx.y * 32 + lane) * VEC;
   const bool active = col < K;
-  const char* Bbytes = (const char*)(B + (active ? col : 0));        // inactive lanes (ragged K) gather column 0 and never store
-  const unsigned stride = (unsigned)K * (unsigned)sizeof(T);            // bytes between rows of B
+  const T* Bcol = B + (active ? col : 0);        // inactive lanes (ragged K) gather column 0 and never store
   for (int rb = R0; rb < R1; rb += 32) {
     const int r = rb + lane;
     const bool valid = r < R1;
@@ -252,11 +265,12 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
       const int he = __shfl_sync(0xffffffffu, e, h);
 #pragma unroll
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
-      spmm_accumulate_shfl<T, VEC, U>(acc, crd, vals, Bbytes, stride, hs, he, lane);
+      spmm_accumulate_shfl<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane);
       if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, mcd);
     }
   }
 }
+
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
