@@ -728,35 +728,35 @@ def iteration_mode(wl, fam, ws, row_len, args, D, flops_job, tdt):
 
 def fused_iteration(wl, fam, ws, row_len, row0, out_rows, total_rows, args, D, flops_job, tdt):
     """the same iteration with the all-gather INSIDE the kernel: the dense result lives in a symmetric allocation
-    (torch.distributed._symmetric_memory), the library stores every result row through its NVLink multicast mapping
-    (taco_b200_set_result_multicast), so the NVSwitch delivers it to all ranks while the kernel is still computing; the step
-    ends with a device-side cross-rank barrier.  No NCCL collective, no second pass over the result."""
+    (torch.distributed._symmetric_memory) and the library stores every result row to all GPUs while the kernel is still
+    computing -- `peers`: a local store plus one peer-to-peer store per other GPU (taco_b200_set_result_peers); `multicast`: one
+    store through the NVLink multicast mapping, replicated by the NVSwitch (taco_b200_set_result_multicast).  The step ends with a
+    device-side cross-rank barrier.  No NCCL collective, no second pass over the result."""
     import torch
     import torch.distributed as dist
     import gpu_util as G
     import taco_b200 as tb
     if fam not in ("spmm", "mttkrp"):
-        return {"unavailable": "in-kernel multicast stores are implemented for the SpMM and MTTKRP results"}
+        return {"unavailable": "in-kernel result fan-out is implemented for the SpMM and MTTKRP results"}
     try:
         import torch.distributed._symmetric_memory as symm
         buf = symm.empty(total_rows * row_len, dtype=tdt, device="cuda")
         hdl = symm.rendezvous(buf, dist.group.WORLD)
-        mc = int(hdl.multicast_ptr)
-        if not mc:
-            return {"unavailable": "no NVLink multicast mapping for the symmetric allocation on this box"}
     except Exception as e:  # noqa: BLE001
         return {"unavailable": f"symmetric memory: {type(e).__name__}: {str(e)[:160]}"}
     nbytes = buf.numel() * buf.element_size()
-    tb.set_result_multicast(buf.data_ptr(), mc, nbytes)
-    try:
-        k, ts = G.build(fam, ws)
-        ts[0].set_vals(buf[row0 * row_len: (row0 + out_rows) * row_len])
+    k, ts = G.build(fam, ws)
+    ts[0].set_vals(buf[row0 * row_len: (row0 + out_rows) * row_len])
 
-        def fstep():
-            if out_rows > 0:
-                k.compute(*ts)
-            hdl.barrier()           # every rank's rows have landed everywhere
+    def fstep():
+        if out_rows > 0:
+            k.compute(*ts)
+        hdl.barrier()           # every rank's rows have landed everywhere
 
+    def measure(what):
+        buf.zero_()
+        torch.cuda.synchronize()
+        D.barrier()
         for _ in range(max(args.warmup, 3)):
             fstep()
         torch.cuda.synchronize()
@@ -774,12 +774,32 @@ def fused_iteration(wl, fam, ws, row_len, row0, out_rows, total_rows, args, D, f
         lo, hi_ = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
-        same = bool(lo.item() == hi_.item())
-        return {"value": flops_job / (ms * 1e-3) / 1e9, "unit": metric_of(wl)[1], "ms_per_step": ms, "all_ranks_hold_identical_result": same,
-                "collective": "none: result rows stored through the NVLink multicast mapping inside the kernel (multimem.st), "
-                              "then a device-side cross-rank barrier", "bytes_multicast_per_rank": out_rows * row_len * buf.element_size()}
+        return {"value": flops_job / (ms * 1e-3) / 1e9, "unit": metric_of(wl)[1], "ms_per_step": ms,
+                "all_ranks_hold_identical_result": bool(lo.item() == hi_.item() and chk.item() != 0.0), "collective": what,
+                "result_bytes_per_rank": out_rows * row_len * buf.element_size()}
+
+    out = {}
+    rank, world = D.rank, D.world
+    try:
+        peers = [int(p) for r, p in enumerate(hdl.buffer_ptrs) if r != rank]
+        if 1 <= len(peers) <= 7:
+            tb.set_result_peers(buf.data_ptr(), peers, nbytes)
+            out["peers"] = measure(f"none: every result row stored locally and into the {world - 1} peer GPU(s) from inside the kernel "
+                                   "(st.global over NVLink peer mappings), then a device-side cross-rank barrier")
+            tb.set_result_peers(None, None, 0)
+        mc = int(hdl.multicast_ptr)
+        if mc:
+            tb.set_result_multicast(buf.data_ptr(), mc, nbytes)
+            out["multicast"] = measure("none: result rows stored through the NVLink multicast mapping inside the kernel (multimem.st), "
+                                       "then a device-side cross-rank barrier")
+        else:
+            out["multicast"] = {"unavailable": "no NVLink multicast mapping for the symmetric allocation on this box"}
     finally:
         tb.set_result_multicast(None, None, 0)
+    best = min((v for v in out.values() if "ms_per_step" in v), key=lambda v: v["ms_per_step"], default=None)
+    if best is not None:
+        out.update(value=best["value"], unit=best["unit"], ms_per_step=best["ms_per_step"])
+    return out
 
 
 def e2e_mode(wl, fam, ws, stats, args, D, flops_job, sparse_out, sharded):

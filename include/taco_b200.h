@@ -103,6 +103,12 @@ void  taco_b200_free(void* p);                    /* frees device OR pinned-host
  * every row a kernel produces is delivered by the NVSwitch to all GPUs of the group in the same store, so after the step (and
  * a cross-rank barrier) every rank holds the whole gathered result -- no separate all-gather.  NULL, NULL, 0 clears. */
 int  taco_b200_set_result_multicast(const void* local_base, void* multicast_base, size_t bytes);
+/* The same fusion with plain peer-to-peer stores: `peer_bases[i]` is the window of peer GPU i as mapped into THIS process
+ * (symmetric memory buffer_ptrs of the other ranks, or cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess pointers), 1 <= npeers <= 7.
+ * Every result row is stored locally and to each peer from inside the kernel.  Each GPU then receives N-1 shards over NVLink
+ * instead of the N a multicast store delivers (the switch also loops the sender's own copy back): the better trade for small
+ * groups.  Replaces a registered multicast window and vice versa; NULL / npeers 0 clears. */
+int  taco_b200_set_result_peers(const void* local_base, size_t bytes, int npeers, void* const* peer_bases);
 
 /* Residency cache: keep a device mirror of an immutable host array across calls (pinned upload once). */
 int  taco_b200_make_resident(const void* host_ptr, size_t bytes);

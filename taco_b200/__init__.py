@@ -7,5 +7,5 @@ fallback -- importing it fails if the library has not been built.
 from . import formats  # noqa: F401  (pure-python helpers, no GPU needed)
 from ._lib import LIB_PATH, TacoError  # noqa: F401
 from .tensor import (BCSR, CSF3, CSR, DCSR, Dense, Format, Kernel, Sparse, Tensor, compile, compressed, dense, launch_count,  # noqa: F401
-                     makeBCSR, makeCSF3, makeCSR, makeDCSR, makeDense, pack, partition_pos, read, pinned_empty, pinned_free, set_result_multicast, set_result_space,
+                     makeBCSR, makeCSF3, makeCSR, makeDCSR, makeDense, pack, partition_pos, read, pinned_empty, pinned_free, set_result_multicast, set_result_peers, set_result_space,
                      synchronize, use_torch_stream)

@@ -75,6 +75,7 @@ lib.taco_b200_device_alloc.restype = ctypes.c_void_p
 lib.taco_b200_device_alloc.argtypes = [ctypes.c_size_t]
 lib.taco_b200_free.argtypes = [ctypes.c_void_p]
 _sym("taco_b200_set_result_multicast").argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+_sym("taco_b200_set_result_peers").argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
 lib.taco_b200_make_resident.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 lib.taco_b200_invalidate.argtypes = [ctypes.c_void_p]
 lib.taco_b200_module_open.restype = ctypes.c_void_p

@@ -76,11 +76,18 @@ struct ProfScope {
   ~ProfScope();
 };
 
-// Result multicast window (taco_b200_set_result_multicast): when the dense result [p, p + bytes) lies inside the registered
-// local window, returns the byte distance to the same location of the NVLink multicast mapping (0 otherwise).  Kernels that get
-// a non-zero distance store their result rows through the multicast address: one store, delivered by the NVSwitch to every
-// GPU of the group (the local one included) -- the all-gather of the result happens inside the kernel.
-long long multicast_delta(const void* p, size_t bytes);
+// Where a dense result row goes besides (or instead of) its local address -- the all-gather of the result fused into the
+// kernel that produces it (taco_b200_set_result_multicast / taco_b200_set_result_peers).  result_fanout() returns a non-empty
+// fan-out when the result [p, p + bytes) lies inside the registered local window:
+//   n == -1: ONE store through the NVLink multicast mapping, d[0] bytes away: the NVSwitch delivers it to every GPU of the
+//            group, the local one included (each GPU receives N shards over NVLink);
+//   n  >  0: the local store plus n peer-to-peer stores, d[i] bytes away (the same window of peer i, mapped into this
+//            process): each GPU receives N-1 shards and sends n copies of its own -- the better trade for small groups.
+struct Fanout {
+  int n = 0;
+  long long d[7] = {0, 0, 0, 0, 0, 0, 0};
+};
+Fanout result_fanout(const void* p, size_t bytes);
 
 // A persistent 256-byte device buffer for tiny synchronous reductions (counters read back right away).  Deliberately NOT a
 // pool allocation: a 16-byte cudaMallocAsync between the large result arrays of consecutive calls splits the pool's big free

@@ -175,12 +175,15 @@ __global__ void mttkrp_slot_slices_kernel(const int* __restrict__ B1_pos, const 
 
 struct MkSlice { int f0, f1, l0, l1, row, zlo; };
 
-// result store: plain, or through the NVLink multicast mapping `mcd` bytes away (fused all-gather of A's rows, common.cuh)
+// result store with its fan-out (fused all-gather of A's rows, common.cuh): local only, one store through the NVLink
+// multicast mapping, or the local store plus one store into each peer GPU's copy
 template <typename T>
-__device__ __forceinline__ void mk_store(T* dst, T v, long long mcd) {
-  if (mcd == 0) *dst = v;
-  else if constexpr (sizeof(T) == 4) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"((char*)dst + mcd), "f"(v) : "memory");
-  else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"((char*)dst + mcd), "d"(v) : "memory");
+__device__ __forceinline__ void mk_store(T* dst, T v, const Fanout& fo) {
+  if (fo.n >= 0) {
+    *dst = v;
+    for (int i = 0; i < fo.n; i++) *(T*)((char*)dst + fo.d[i]) = v;
+  } else if constexpr (sizeof(T) == 4) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"((char*)dst + fo.d[0]), "f"(v) : "memory");
+  else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"((char*)dst + fo.d[0]), "d"(v) : "memory");
 }   // fibers, leaves, row of A, first row to zero before `row`
 
 template <typename T, int U, int WARPS, int MINB, bool SINGLE, bool MC>
@@ -188,8 +191,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd, const int* __restrict__ B2_pos,
                   const int* __restrict__ B2_crd, const int* __restrict__ B3_pos, const int* __restrict__ B3_crd,
                   const T* __restrict__ Bv, const T* __restrict__ C, const T* __restrict__ D, T* __restrict__ A, int R,
-                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed, long long mcd_arg) {
-  const long long mcd = MC ? mcd_arg : 0;         // a template flag: the single-GPU instantiation keeps the offset out of its registers
+                  int Idim, int nnz, int nslots, const int* __restrict__ slot_slices, int* __restrict__ chain, bool ticketed, Fanout fo_arg) {
+  Fanout fo;                                      // a template flag: the single-GPU instantiation keeps the offsets out of its registers
+  if constexpr (MC) fo = fo_arg;
   __shared__ MkLeaf<T> stage_all[WARPS][32];
   __shared__ MkSlice meta_all[WARPS][32];
   __shared__ int s_ticket;
@@ -245,10 +249,10 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
       const int l1 = hub ? min(hi, m.l1) : m.l1;
       if (!is_tail) {
         for (int r = m.zlo; r < m.row; r++)
-          for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), mcd);
+          for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), fo);
         if (sb + h == nslices - 1)                       // the last slice also owns the rows after it
           for (int r = m.row + 1; r < Idim; r++)
-            for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), mcd);
+            for (int j = lane; j < R; j += 32) mk_store<T>(A + (size_t)r * R + j, T(0), fo);
       }
       for (int j0 = 0; j0 < (SINGLE ? 1 : R); j0 += 32) {      // SINGLE: R <= 32, one pass over the slice's leaves
         const bool active = j0 + lane < R;
@@ -298,9 +302,9 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
           // the row -- and every whole slice -- goes out through the multicast mapping, if there is one
           if (is_tail) {
             const T sum = __ldcg(dst) + acc;
-            if (tail_end <= hi) mk_store<T>(dst, sum, mcd); else *dst = sum;
+            if (tail_end <= hi) mk_store<T>(dst, sum, fo); else *dst = sum;
           } else if (hub) *dst = acc;
-          else mk_store<T>(dst, acc, mcd);
+          else mk_store<T>(dst, acc, fo);
         }
       }
       if (hub && (is_tail ? tail_end > hi : true)) {       // more pieces follow in the next slot: publish this one
@@ -369,7 +373,7 @@ static int dense_assemble(taco_tensor_t* A, int order, const char* what) {
 }
 
 template <typename T, int U, int WARPS, int MINB>
-static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain, long long mcd) {
+static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslots, const int* slot_slices, int* chain, Fanout fo) {
   const dim3 grid((nslots + WARPS - 1) / WARPS);
   // TACO_B200_MTTKRP_NOTICKET=1: slot numbers from blockIdx instead of the ticket (A/B measurements only: the ordered
   // hand-over of hub slices then relies on in-order CTA dispatch)
@@ -380,9 +384,9 @@ static void mttkrp_go(CsfCall& cc, const T* C, const T* D, T* A, int R, int nslo
 #define TB_MK_GO(SINGLE, MC)                                                                                                   \
   mttkrp_csf_kernel<T, U, WARPS, MINB, SINGLE, MC><<<grid, WARPS * 32, 0, stream()>>>(                                            \
       cc.p1.as<int>(), cc.c1.as<int>(), cc.p2.as<int>(), cc.c2.as<int>(), cc.p3.as<int>(), cc.c3.as<int>(), cc.vals.as<T>(), C, D, A, R, \
-      cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, mcd)
-  if (R <= 32 && single) { if (mcd) TB_MK_GO(true, true); else TB_MK_GO(true, false); }
-  else { if (mcd) TB_MK_GO(false, true); else TB_MK_GO(false, false); }
+      cc.B.dim[0], cc.nnz, nslots, slot_slices, chain, ticketed, fo)
+  if (R <= 32 && single) { if (fo.n) TB_MK_GO(true, true); else TB_MK_GO(true, false); }
+  else { if (fo.n) TB_MK_GO(false, true); else TB_MK_GO(false, false); }
 #undef TB_MK_GO
 }
 
@@ -407,17 +411,17 @@ static int mttkrp_launch(CsfCall& cc, const T* C, const T* D, T* A, size_t a_cou
     return fail(TACO_B200_ERR_CUDA, "mttkrp: memset failed");
   }
   static const int variant = getenv("TACO_B200_MTTKRP_VARIANT") ? atoi(getenv("TACO_B200_MTTKRP_VARIANT")) : 0;
-  const long long mcd = multicast_delta(A, a_count * sizeof(T));     // result inside the registered multicast window?
+  const Fanout fo = result_fanout(A, a_count * sizeof(T));     // result inside the registered fan-out window?
   {
     ProfScope ps("mttkrp_csf");
     const int* ss = (const int*)slot_slices;
     switch (variant) {
-      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
-      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
-      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
-      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
-      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
-      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, mcd); break;
+      case 1: mttkrp_go<T, 2, 8, 5>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
+      case 2: mttkrp_go<T, 2, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
+      case 3: mttkrp_go<T, 1, 8, 6>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
+      case 4: mttkrp_go<T, 2, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
+      case 5: mttkrp_go<T, 1, 16, 4>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
+      default: mttkrp_go<T, 1, 8, 8>(cc, C, D, A, R, nslots, ss, (int*)chain, fo); break;
     }
   }
   count_launch(2);

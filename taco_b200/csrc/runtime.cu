@@ -58,9 +58,10 @@ struct Context {
   std::unordered_set<const void*> pooled;   // device result arrays handed to the caller that came from the pool
   bool profile = false;
   std::vector<ProfEntry> prof;
-  const char* mc_local = nullptr;            // result multicast window: local base, multicast base, size
-  char* mc_base = nullptr;
-  size_t mc_bytes = 0;
+  const char* mc_local = nullptr;            // result fan-out window: local base, size, and either the multicast base
+  size_t mc_bytes = 0;                       // (mc_peers == -1) or the bases of the same window on mc_peers peer GPUs
+  int mc_peers = 0;
+  char* mc_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 static Context g;
 
@@ -148,11 +149,14 @@ Mem classify(const void* p) {
   }
 }
 
-long long multicast_delta(const void* p, size_t bytes) {
-  if (!g.mc_base || !p) return 0;
+Fanout result_fanout(const void* p, size_t bytes) {
+  Fanout fo;
+  if (g.mc_peers == 0 || !p) return fo;
   const char* c = (const char*)p;
-  if (c < g.mc_local || c + bytes > g.mc_local + g.mc_bytes) return 0;
-  return (long long)(g.mc_base - g.mc_local);
+  if (c < g.mc_local || c + bytes > g.mc_local + g.mc_bytes) return fo;
+  fo.n = g.mc_peers;
+  for (int i = 0; i < (g.mc_peers < 0 ? 1 : g.mc_peers); i++) fo.d[i] = (long long)(g.mc_base[i] - g.mc_local);
+  return fo;
 }
 
 bool trusts_vals_size(const void* p) {
@@ -509,8 +513,29 @@ int taco_b200_set_result_multicast(const void* local_base, void* multicast_base,
     return fail(TACO_B200_ERR_ARG, "set_result_multicast: bases must be 16-byte aligned");
   std::lock_guard<std::mutex> lk(g.mu);
   g.mc_local = (const char*)local_base;
-  g.mc_base = (char*)multicast_base;
+  g.mc_base[0] = (char*)multicast_base;
   g.mc_bytes = local_base ? bytes : 0;
+  g.mc_peers = local_base ? -1 : 0;
+  return TACO_B200_OK;
+}
+
+int taco_b200_set_result_peers(const void* local_base, size_t bytes, int npeers, void* const* peer_bases) {
+  TB_TRY(ensure_init());
+  if (!local_base || npeers == 0) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.mc_local = nullptr; g.mc_bytes = 0; g.mc_peers = 0;
+    return TACO_B200_OK;
+  }
+  if (npeers < 0 || npeers > 7 || !peer_bases) return fail(TACO_B200_ERR_ARG, "set_result_peers: 1..7 peer windows");
+  if ((uintptr_t)local_base & 15) return fail(TACO_B200_ERR_ARG, "set_result_peers: bases must be 16-byte aligned");
+  for (int i = 0; i < npeers; i++)
+    if (!peer_bases[i] || ((uintptr_t)peer_bases[i] & 15) || peer_bases[i] == local_base)
+      return fail(TACO_B200_ERR_ARG, "set_result_peers: peer bases must be non-NULL, 16-byte aligned and differ from the local base");
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.mc_local = (const char*)local_base;
+  g.mc_bytes = bytes;
+  g.mc_peers = npeers;
+  for (int i = 0; i < npeers; i++) g.mc_base[i] = (char*)peer_bases[i];
   return TACO_B200_OK;
 }
 

@@ -61,26 +61,8 @@ __device__ __forceinline__ void st_multicast(T* p, T v) {
   else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-// `mcd` != 0: the row goes out through the multicast mapping, `mcd` bytes away from the local address (common.cuh)
 template <typename T, int VEC, bool COLMAJOR>
-__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f,
-                                          long long mcd) {
-  if (mcd != 0) {
-    if constexpr (COLMAJOR) {
-#pragma unroll
-      for (int e = 0; e < VEC; e++) st_multicast<T>((T*)((char*)(C + (size_t)(col + e) * rows + row) + mcd), f.v[e]);
-    } else {
-      T* p = (T*)((char*)(C + row * K + col) + mcd);
-      if constexpr (VEC == 4 && sizeof(T) == 4) {
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
-                     "f"(f.v[3]) : "memory");
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; e++) st_multicast<T>(p + e, f.v[e]);
-      }
-    }
-    return;
-  }
+__device__ __forceinline__ void store_row_plain(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f) {
   if constexpr (COLMAJOR) {
 #pragma unroll
     for (int e = 0; e < VEC; e++) C[(size_t)(col + e) * rows + row] = f.v[e];
@@ -98,6 +80,32 @@ __device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col
       p[0] = f.v[0];
     }
   }
+}
+
+// The row with its fan-out (common.cuh): fo.n == 0 local only; -1 one store through the multicast mapping; n > 0 the local
+// store and one store into each of n peer GPUs' copies of the result.
+template <typename T, int VEC, bool COLMAJOR>
+__device__ __forceinline__ void store_row(T* __restrict__ C, size_t row, int col, int rows, int K, const Frag<T, VEC>& f,
+                                          const Fanout& fo) {
+  if (fo.n < 0) {
+    const long long mcd = fo.d[0];
+    if constexpr (COLMAJOR) {
+#pragma unroll
+      for (int e = 0; e < VEC; e++) st_multicast<T>((T*)((char*)(C + (size_t)(col + e) * rows + row) + mcd), f.v[e]);
+    } else {
+      T* p = (T*)((char*)(C + row * K + col) + mcd);
+      if constexpr (VEC == 4 && sizeof(T) == 4) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(f.v[0]), "f"(f.v[1]), "f"(f.v[2]),
+                     "f"(f.v[3]) : "memory");
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) st_multicast<T>(p + e, f.v[e]);
+      }
+    }
+    return;
+  }
+  store_row_plain<T, VEC, COLMAJOR>(C, row, col, rows, K, f);
+  for (int i = 0; i < fo.n; i++) store_row_plain<T, VEC, COLMAJOR>((T*)((char*)C + fo.d[i]), row, col, rows, K, f);
 }
 
 // A launch covers the row range [r0, r1) = nonzeros [p0, p1) (the whole matrix, or one row chunk of the host-operand
@@ -221,14 +229,15 @@ __device__ __forceinline__ void spmm_accumulate_shfl(Frag<T, VEC>& acc, const in
 
 // Schedule (1): the rows of at most `long_thresh` nonzeros.  RMAP: result row r is stored at row rowmap[r] of C (TTM: the
 // rows are the fibers of a CSF tensor, rowmap their cells in the dense (i,j) plane, csf.cu).
-// MC: the result goes out through the multicast mapping (`mcd_arg` bytes away); a template flag so that the common
+// MC: the result rows fan out to the other GPUs (`fo_arg`, common.cuh); a template flag so that the common
 // single-GPU instantiation does not carry the offset in registers (32-register budget, every spill is in the per-row path)
 template <typename T, int VEC, bool COLMAJOR, int U, int WARPS, int MINB, bool RMAP = false, bool MC = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const T* __restrict__ vals,
                 const T* __restrict__ B, T* __restrict__ C, int rows, int K, SpmmRange rg, int nslots,
-                const int* __restrict__ slot_rows, int long_thresh, long long mcd_arg, const unsigned* __restrict__ rowmap = nullptr) {
-  const long long mcd = MC ? mcd_arg : 0;
+                const int* __restrict__ slot_rows, int long_thresh, Fanout fo_arg, const unsigned* __restrict__ rowmap = nullptr) {
+  Fanout fo;
+  if constexpr (MC) fo = fo_arg;
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= nslots) return;
@@ -256,7 +265,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
     while (empty) {
       const int h = __ffs(empty) - 1;
       empty &= empty - 1;
-      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, mcd);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, fo);
     }
     while (full) {
       const int h = __ffs(full) - 1;
@@ -266,7 +275,7 @@ spmm_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
 #pragma unroll
       for (int x = 0; x < VEC; x++) acc.v[x] = T(0);
       spmm_accumulate_shfl<T, VEC, U>(acc, crd, vals, Bcol, K, hs, he, lane);
-      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, mcd);
+      if (active) store_row<T, VEC, COLMAJOR>(C, RMAP ? (size_t)__ldg(rowmap + rb + h) : (size_t)(rb + h), col, rows, K, acc, fo);
     }
   }
 }
@@ -438,7 +447,7 @@ __global__ void __launch_bounds__(256)
 spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restrict__ counters, const int* __restrict__ pair_loc,
                          const int* __restrict__ pair_cnt,
                          SpmmLongCfg cfg, const T* __restrict__ partials, T* __restrict__ C, int rows, int K,
-                         const unsigned* __restrict__ rowmap, long long mcd) {
+                         const unsigned* __restrict__ rowmap, Fanout fo) {
   const int lane = threadIdx.x & 31;
   const int nlong = min(__ldg(counters), cfg.nlong_max);
   const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
@@ -472,7 +481,7 @@ spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restric
           }
       }
     }
-    if (active) store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc, mcd);
+    if (active) store_row<T, VEC, COLMAJOR>(C, orow, col, rows, K, acc, fo);
   }
   }
 }
@@ -519,7 +528,7 @@ static void spmm_long_go(const int* crd, const T* vals, const T* B, int K, const
 template <typename T, int VEC, bool COLMAJOR, bool RMAP>
 static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int cols, int K, SpmmRange rg,
                           const SpmmLongCfg& cfg, const unsigned* rowmap, cudaStream_t run_st, cudaEvent_t fork, void** scratch_out,
-                          long long mcd) {
+                          Fanout fo) {
   const long long pairs = (long long)cfg.panels * cfg.nlong_max;
   // counters: [0] long rows, [1] item ticket, [2] items, [8..8+P) items per panel, [48..48+P) first item of a panel
   const size_t o_cnt = 0, o_rows = align256(sizeof(int) * 96), o_ab = o_rows + align256(sizeof(int) * (size_t)cfg.nlong_max),
@@ -562,7 +571,7 @@ static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T
     default: spmm_long_go<T, VEC, 4, 6>(crd, vals, B, K, items, counters, partials, run_st); break;
   }
   spmm_long_combine_kernel<T, VEC, COLMAJOR, RMAP><<<num_sms() * 8, 256, 0, run_st>>>(
-      long_rows, counters, pair_loc, pair_cnt, cfg, partials, C, rows, K, rowmap, mcd);
+      long_rows, counters, pair_loc, pair_cnt, cfg, partials, C, rows, K, rowmap, fo);
   count_launch(7);
   TB_CUDA(cudaGetLastError());
   return TACO_B200_OK;
@@ -572,14 +581,14 @@ static int spmm_long_rows(const int* pos, const int* crd, const T* vals, const T
 // selects one for tuning runs; the default is the measured best at config C2 (profiles/).
 template <typename T, int VEC, bool COLMAJOR, bool RMAP, int U, int WARPS, int MINB>
 static void spmm_go(const int* pos, const int* crd, const T* vals, const T* B, T* C, int rows, int K, SpmmRange rg, int nslots,
-                    const int* slot_rows, int long_thresh, const unsigned* rowmap, long long mcd, cudaStream_t st) {
+                    const int* slot_rows, int long_thresh, const unsigned* rowmap, Fanout fo, cudaStream_t st) {
   dim3 grid((nslots + WARPS - 1) / WARPS, (K + 32 * VEC - 1) / (32 * VEC));
-  if (mcd != 0 && !RMAP)
+  if (fo.n != 0 && !RMAP)
     spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, false, true><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                               slot_rows, long_thresh, mcd, rowmap);
+                                                                                               slot_rows, long_thresh, fo, rowmap);
   else
     spmm_csr_kernel<T, VEC, COLMAJOR, U, WARPS, MINB, RMAP, false><<<grid, WARPS * 32, 0, st>>>(pos, crd, vals, B, C, rows, K, rg, nslots,
-                                                                                                slot_rows, long_thresh, 0, rowmap);
+                                                                                                slot_rows, long_thresh, Fanout(), rowmap);
 }
 
 // The whole SpMM launch sequence over a row range: long-row plan + column-panel kernels, then the slot kernel.
@@ -592,8 +601,8 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   void* slot_rows = nullptr;
   TB_TRY(scratch_alloc(&slot_rows, sizeof(int) * (size_t)(nslots + 1)));
   ProfScope ps(prof_name);
-  // a result inside the registered multicast window is stored through the NVLink multicast mapping (fused all-gather)
-  const long long mcd = RMAP ? 0 : multicast_delta(C, sizeof(T) * (size_t)rows * K);
+  // a result inside the registered fan-out window also goes to the other GPUs from inside the kernels (fused all-gather)
+  const Fanout fo = RMAP ? Fanout() : result_fanout(C, sizeof(T) * (size_t)rows * K);
   const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
   static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 1);
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
@@ -605,7 +614,7 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   void* long_scratch = nullptr;
   int rc = TACO_B200_OK;
   if (cfg.nlong_max > 0)
-    rc = spmm_long_rows<T, VEC, COLMAJOR, RMAP>(pos, crd, vals, B, C, rows, cols, K, rg, cfg, rowmap, side, ev_fork, &long_scratch, mcd);
+    rc = spmm_long_rows<T, VEC, COLMAJOR, RMAP>(pos, crd, vals, B, C, rows, cols, K, rg, cfg, rowmap, side, ev_fork, &long_scratch, fo);
   if (rc != TACO_B200_OK) {
     if (side != stream()) { cudaEventRecord(ev_join, side); cudaStreamWaitEvent(stream(), ev_join, 0); }
     scratch_free(long_scratch); scratch_free(slot_rows);
@@ -616,11 +625,11 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   const int* sr = (const int*)slot_rows;
   cudaStream_t st = stream();
   switch (variant) {
-    case 1: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
-    case 2: spmm_go<T, VEC, COLMAJOR, RMAP, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
-    case 3: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
-    case 4: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
-    default: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, mcd, st); break;
+    case 1: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 4>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, fo, st); break;
+    case 2: spmm_go<T, VEC, COLMAJOR, RMAP, 1, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, fo, st); break;
+    case 3: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, fo, st); break;
+    case 4: spmm_go<T, VEC, COLMAJOR, RMAP, 4, 8, 6>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, fo, st); break;
+    default: spmm_go<T, VEC, COLMAJOR, RMAP, 2, 8, 8>(pos, crd, vals, B, C, rows, K, rg, nslots, sr, cfg.thresh, rowmap, fo, st); break;
   }
   count_launch(2);
   if (side != stream()) {                 // join: the scratch is released (stream-ordered) only after the side stream is done

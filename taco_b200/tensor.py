@@ -401,6 +401,14 @@ def set_result_multicast(local_ptr, multicast_ptr, nbytes):
     check(lib.taco_b200_set_result_multicast(ctypes.c_void_p(local_ptr or 0), ctypes.c_void_p(multicast_ptr or 0), int(nbytes or 0)))
 
 
+def set_result_peers(local_ptr, peer_ptrs, nbytes):
+    """dense results inside [local_ptr, local_ptr + nbytes) are also stored, from inside the kernels, into the same window of
+    every peer GPU (`peer_ptrs`: the peers' windows as mapped into this process, at most 7; None / empty clears)"""
+    peers = [int(p) for p in (peer_ptrs or [])]
+    arr = (ctypes.c_void_p * max(len(peers), 1))(*peers)
+    check(lib.taco_b200_set_result_peers(ctypes.c_void_p(local_ptr or 0), int(nbytes or 0), len(peers), arr))
+
+
 def synchronize():
     check(lib.taco_b200_synchronize())
 

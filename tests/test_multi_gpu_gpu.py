@@ -167,40 +167,53 @@ def _nccl_worker(rank, world, port, results):
         rb = np.array([0] + [int(e.item()) for e in ends])
         A = partition.allgather_rows(a_local, rb, row_len=R).cpu().numpy().reshape(I, R)
         ok_mttkrp = bool(np.array_equal(A, oracle.mttkrp(t, t["C"].reshape(Kd, R), t["D"].reshape(L, R), I)))
-        # fused compute + all-gather: results stored through the NVLink multicast mapping of a symmetric allocation
+        # fused compute + all-gather: result rows stored to every GPU from inside the kernels, through peer-to-peer mappings
+        # and through the NVLink multicast mapping of a symmetric allocation
         ok_fused = None
         try:
             import torch.distributed._symmetric_memory as symm
             buf = symm.empty(n * K, dtype=torch.float64, device="cuda")
             hdl = symm.rendezvous(buf, dist.group.WORLD)
-            mc = int(hdl.multicast_ptr)
+            abuf = symm.empty(I * R, dtype=torch.float64, device="cuda")
+            ah = symm.rendezvous(abuf, dist.group.WORLD)
+            have = True
         except Exception:  # noqa: BLE001
-            mc = 0
-        if mc:
-            buf.fill_(-1.0)
-            hdl.barrier()
-            tb.set_result_multicast(buf.data_ptr(), mc, buf.numel() * 8)
+            have = False
+        if have:
+            want_a = oracle.mttkrp(t, t["C"].reshape(Kd, R), t["D"].reshape(L, R), I)
+
+            def register(b_, h_, mode):
+                if mode == "peers":
+                    tb.set_result_peers(b_.data_ptr(), [int(p_) for r_, p_ in enumerate(h_.buffer_ptrs) if r_ != rank], b_.numel() * 8)
+                else:
+                    tb.set_result_multicast(b_.data_ptr(), int(h_.multicast_ptr), b_.numel() * 8)
+
+            modes = ["peers"] + (["multicast"] if int(hdl.multicast_ptr) and int(ah.multicast_ptr) else [])
+            ok_fused = True
+            tb.set_result_space("device")
             try:
-                kk, tt = G.build("spmm", dict(dims=[rows, m, K], A_pos=sh["pos"], A_crd=sh["crd"], A_vals=sh["vals"], B=wd["B"]))
-                tt[0].set_vals(buf[sh["row_begin"] * K: sh["row_end"] * K])
-                tb.set_result_space("device")
-                kk.compute(*tt)
-                hdl.barrier()
-                torch.cuda.synchronize()
-                got = buf.cpu().numpy().reshape(n, K)
-                ok_fused = bool(np.array_equal(got[deg <= 128], want[deg <= 128]) and np.allclose(got, want, rtol=1e-12, atol=0))
-                # MTTKRP rows through the same window
-                abuf = symm.empty(I * R, dtype=torch.float64, device="cuda")
-                ah = symm.rendezvous(abuf, dist.group.WORLD)
-                abuf.fill_(-1.0)
-                ah.barrier()
-                tb.set_result_multicast(abuf.data_ptr(), int(ah.multicast_ptr), abuf.numel() * 8)
-                kk, tt = G.build("mttkrp", dict(dims=[st["row_end"] - st["row_begin"], Kd, L, R], C=td["C"], D=td["D"], **sub))
-                tt[0].set_vals(abuf[st["row_begin"] * R: st["row_end"] * R])
-                kk.compute(*tt)
-                ah.barrier()
-                torch.cuda.synchronize()
-                ok_fused = ok_fused and bool(np.array_equal(abuf.cpu().numpy().reshape(I, R), oracle.mttkrp(t, t["C"].reshape(Kd, R), t["D"].reshape(L, R), I)))
+                for mode in modes:
+                    buf.fill_(-1.0)
+                    abuf.fill_(-1.0)
+                    torch.cuda.synchronize()
+                    hdl.barrier()
+                    ah.barrier()
+                    register(buf, hdl, mode)
+                    kk, tt = G.build("spmm", dict(dims=[rows, m, K], A_pos=sh["pos"], A_crd=sh["crd"], A_vals=sh["vals"], B=wd["B"]))
+                    tt[0].set_vals(buf[sh["row_begin"] * K: sh["row_end"] * K])
+                    kk.compute(*tt)
+                    hdl.barrier()
+                    torch.cuda.synchronize()
+                    got = buf.cpu().numpy().reshape(n, K)
+                    ok_fused = ok_fused and bool(np.array_equal(got[deg <= 128], want[deg <= 128]) and np.allclose(got, want, rtol=1e-12, atol=0))
+                    # MTTKRP rows through the same kind of window
+                    register(abuf, ah, mode)
+                    kk, tt = G.build("mttkrp", dict(dims=[st["row_end"] - st["row_begin"], Kd, L, R], C=td["C"], D=td["D"], **sub))
+                    tt[0].set_vals(abuf[st["row_begin"] * R: st["row_end"] * R])
+                    kk.compute(*tt)
+                    ah.barrier()
+                    torch.cuda.synchronize()
+                    ok_fused = ok_fused and bool(np.array_equal(abuf.cpu().numpy().reshape(I, R), want_a))
             finally:
                 tb.set_result_multicast(None, None, 0)
                 tb.set_result_space("host")
@@ -222,7 +235,7 @@ def test_nccl_world2_sharded_kernels_and_allgather():
         assert len(results) == world
         for r in range(world):
             ok_spmv, ok_spmm, ok_mttkrp, launched, ok_fused = results[r]
-            assert ok_fused is not False, "results stored through the NVLink multicast mapping differ from the oracle on some rank"
+            assert ok_fused is not False, "results stored to all GPUs from inside the kernels (peer stores / multicast) differ from the oracle on some rank"
             assert launched, "the CUDA kernels of libtaco_b200 must have run on every rank"
             assert ok_spmv, "iterative sharded SpMV + NCCL all-gather differs from the oracle"
             assert ok_spmm, "row-sharded SpMM + all-gather differs from the oracle"
