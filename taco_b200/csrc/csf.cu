@@ -316,6 +316,15 @@ mttkrp_csf_kernel(const int* __restrict__ B1_pos, const int* __restrict__ B1_crd
   }
 }
 
+// device-resident CSF: nslices = pos1[1] - pos1[0], nfib = pos2[nslices], nnz = pos3[nfib] (a negative size stops the chain)
+__global__ void csf3_level_sizes_kernel(const int* __restrict__ pos1, const int* __restrict__ pos2, const int* __restrict__ pos3,
+                                        int* __restrict__ out) {
+  const int nslices = pos1[1] - pos1[0];
+  const int nfib = nslices >= 0 ? pos2[nslices] : -1;
+  const int nnz = nfib >= 0 ? pos3[nfib] : -1;
+  out[0] = nslices; out[1] = nfib; out[2] = nnz;
+}
+
 struct CsfCall {
   Csf3View B; DType dt; int32_t nslices, nfib, nnz;
   In p1, c1, p2, c2, p3, c3, vals;
@@ -327,15 +336,25 @@ struct CsfCall {
 static int csf_prepare(taco_tensor_t* Bt, CsfCall* cc) {
   TB_TRY(view_csf3(Bt, "B", &cc->B));
   cc->dt = cc->B.dt;
-  // level sizes: pos1[1], pos2[nslices], pos3[nfib]  (host arrays are read directly; device arrays cost one
-  // small read-back each -- callers on the hot loop keep B host-described or pass sizes through vals_size)
-  int32_t p10 = 0;
-  TB_TRY(read_i32(cc->B.pos[0], &p10));
-  TB_TRY(read_i32(cc->B.pos[0] + 1, &cc->nslices));
-  cc->nslices -= p10;
-  TB_TRY(read_i32(cc->B.pos[1] + cc->nslices, &cc->nfib));
-  if (Bt->vals_size > 0 && trusts_vals_size(cc->B.pos[2])) cc->nnz = Bt->vals_size;
-  else TB_TRY(read_i32(cc->B.pos[2] + cc->nfib, &cc->nnz));
+  // level sizes: pos1[1], pos2[nslices], pos3[nfib].  Host arrays are read directly; when all three pos arrays are device
+  // memory the chain is followed by one single-thread kernel and read back with ONE synchronisation (it was one per level)
+  if (classify(cc->B.pos[0]) == Mem::Device && classify(cc->B.pos[1]) == Mem::Device && classify(cc->B.pos[2]) == Mem::Device) {
+    std::lock_guard<std::mutex> lk(small_scratch_mutex());
+    int* d = (int*)small_scratch();
+    if (!d) return fail(TACO_B200_ERR_ALLOC, "no device scratch");
+    csf3_level_sizes_kernel<<<1, 1, 0, stream()>>>(cc->B.pos[0], cc->B.pos[1], cc->B.pos[2], d);
+    int32_t h[3];
+    TB_TRY(read_back(h, d, sizeof(h)));
+    cc->nslices = h[0]; cc->nfib = h[1]; cc->nnz = h[2];
+  } else {
+    int32_t p10 = 0;
+    TB_TRY(read_i32(cc->B.pos[0], &p10));
+    TB_TRY(read_i32(cc->B.pos[0] + 1, &cc->nslices));
+    cc->nslices -= p10;
+    TB_TRY(read_i32(cc->B.pos[1] + cc->nslices, &cc->nfib));
+    if (Bt->vals_size > 0 && trusts_vals_size(cc->B.pos[2])) cc->nnz = Bt->vals_size;
+    else TB_TRY(read_i32(cc->B.pos[2] + cc->nfib, &cc->nnz));
+  }
   if (cc->nslices < 0 || cc->nfib < 0 || cc->nnz < 0) return fail(TACO_B200_ERR_ARG, "csf: corrupt pos arrays");
   cc->host_described = true;
   for (int l = 0; l < 3; l++) {
