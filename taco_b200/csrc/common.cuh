@@ -34,6 +34,7 @@ cudaStream_t stream();
 cudaStream_t aux_stream(int i);                        // 0: upload, 1: download (host-operand pipelines), 2: side compute stream
 bool is_resident(const void* host_ptr, size_t bytes);  // registered with taco_b200_make_resident
 int num_sms();
+size_t device_mem_total();
 void count_launch(int n = 1);
 int result_space();
 

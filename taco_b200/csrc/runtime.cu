@@ -49,6 +49,7 @@ struct Context {
   bool ready = false;
   int device = 0;
   int sms = 148;
+  size_t mem_total = (size_t)180 << 30;
   cudaStream_t own_stream = nullptr;
   cudaStream_t cur_stream = nullptr;
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // upload / download streams of the host-operand pipelines, side compute stream
@@ -81,6 +82,7 @@ static int init_locked(int device) {
                 prop.minor);
   g.device = device;
   g.sms = prop.multiProcessorCount;
+  g.mem_total = prop.totalGlobalMem;
   TB_CUDA(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
   g.cur_stream = g.own_stream;
   cudaMemPool_t pool;
@@ -120,6 +122,7 @@ bool is_resident(const void* host_ptr, size_t bytes) {
   return it != g.resident.end() && it->second.bytes >= bytes;
 }
 int num_sms() { return g.sms; }
+size_t device_mem_total() { return g.mem_total; }
 void count_launch(int n) { g.launches += n; }
 int result_space() { return g.space; }
 bool need_sync() { return g_need_sync; }

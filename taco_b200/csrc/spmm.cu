@@ -13,16 +13,18 @@
 //       and each C row is stored once with a streaming 128-bit store.  Empty rows are zeroed by their owner.  Inside a
 //       row the products are accumulated in ascending position order with separate multiply and add -- the reference
 //       C kernel's order (Appendix A.1) -- so these rows are bit-identical to it.
-//   (2) long rows (> LONG nonzeros; 45 % of the nonzeros of the power-law config C2) -- COLUMN-PANEL schedule.  The
-//       columns are cut into P panels; a long row's nonzeros inside one panel form work items of at most CAP
+//   (2) long rows (> LONG = 128 nonzeros; 70 % of the nonzeros of the power-law config C2) -- balanced ITEMS in COLUMN-PANEL
+//       order.  The columns are cut into P panels; a long row's nonzeros inside one panel form work items of at most CAP
 //       nonzeros (fused multiply-add: these rows are reassociated by the partial sums anyway).  Items are laid out
-//       panel-major and handed out in that order by a ticket, so at any moment the
-//       whole chip gathers rows of B from ONE panel (B panel = cols/P rows, L2-resident): every B row a long row needs
-//       is fetched from HBM about once instead of once per reference.  Each item stores its partial row sum; a combine
-//       kernel adds the partials of a row in ascending column (= position) order.  The plan (long-row list, panel cuts by
-//       binary search, item slots by one warp-aggregated atomic per panel) is rebuilt on the device every call: no cached inspector state, no
-//       host read-back, results independent of scheduling (run-to-run deterministic, within 1e-5 / 1e-12 of the
-//       sequential order).
+//       panel-major and handed to persistent warps in that order by a ticket, so at any moment the whole chip gathers rows
+//       of B from one column window.  Each item stores its partial row sum; a combine kernel adds the partials of a row in
+//       ascending column (= position) order.  Measured at C2 (profiles/r02_variants.md): what pays is the balanced item
+//       decomposition with the lean staged inner loop (P = 1: 2.95 ms against 3.42 ms for row-owner warps with atomics on hub
+//       rows); the panel order adds 10 % at P = 4 (2.68 ms) and LOSES beyond P = 8 -- a (row, panel) piece of a 129..512-nonzero
+//       row becomes a handful of nonzeros whose 512-byte partial row costs more than the locality returns (P = 32: 3.63 ms).
+//       The plan (long-row list, panel cuts by binary search, item slots by one warp-aggregated atomic per panel) is rebuilt
+//       on the device every call: no cached inspector state, no host read-back, results independent of scheduling
+//       (run-to-run deterministic, within 1e-5 / 1e-12 of the sequential order).
 // Algorithmic bytes per launch: nnz*(4+sizeof T) + 4(n+1) + sizeof T*K*(cols + rows).
 #include <climits>
 #include <cstdlib>
@@ -339,7 +341,7 @@ spmm_long_cut_kernel(const int* __restrict__ pos, const int* __restrict__ crd, c
     const int p = (int)(t / nlong), li = (int)(t % nlong);
     const int r = __ldg(long_rows + li);
     const int s = __ldg(pos + r), e = __ldg(pos + r + 1);
-    cut[(long long)p * cfg.nlong_max + li] = (p == 0) ? s : (p == cfg.panels) ? e : tbd::search_first_ge(crd, s, e - 1, p * cfg.panel_w);
+    cut[(long long)p * cfg.nlong_max + li] = (p == 0) ? s : (p == cfg.panels) ? e : tbd::search_first_ge(crd, s, e - 1, (int)min((long long)p * cfg.panel_w, (long long)INT_MAX));
   }
 }
 
@@ -487,16 +489,18 @@ spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restric
 }
 
 
-// TACO_B200_SPMM_LONG / _PANELS / _CAP override the defaults (tuning runs); the partial-sum scratch is kept under 4 GiB by
-// halving the panel count, then doubling the threshold.
+// TACO_B200_SPMM_LONG / _PANELS / _CAP override the defaults (tuning runs).  The partial-sum scratch is sized for the worst case
+// (every long row has nonzeros in every panel: 8.7 GB at C2, of which the kernel touches 0.5 GB) and kept under an eighth of the
+// device memory (TACO_B200_SPMM_SCRATCH_GB overrides) by halving the panel count, then doubling the threshold.
 static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es) {
-  static const int e_thresh = env_int("TACO_B200_SPMM_LONG", 128), e_panels = env_int("TACO_B200_SPMM_PANELS", 32),
+  static const int e_thresh = env_int("TACO_B200_SPMM_LONG", 128), e_panels = env_int("TACO_B200_SPMM_PANELS", 4),
                    e_cap = env_int("TACO_B200_SPMM_CAP", 256);
   SpmmLongCfg c;
   c.thresh = e_thresh < 64 ? 64 : e_thresh;
   c.panels = e_panels < 1 ? 1 : (e_panels > 32 ? 32 : e_panels);
   c.cap = e_cap < 32 ? 32 : e_cap;
-  const size_t budget = (size_t)4 << 30;
+  static const int e_gb = env_int("TACO_B200_SPMM_SCRATCH_GB", 0);
+  const size_t budget = e_gb > 0 ? (size_t)e_gb << 30 : device_mem_total() / 8;
   for (;;) {
     c.nlong_max = nnz / (c.thresh + 1);
     c.items_max = (long long)nnz / c.cap + 1 + (long long)c.nlong_max * c.panels;
