@@ -9,19 +9,9 @@ for l in sys.stdin:
 "; }
 {
 run spmm X=0
-run spmm TACO_B200_SPMM_CAP=128
-run spmm TACO_B200_SPMM_CAP=512
-run spmm TACO_B200_SPMM_CAP=1024
-run spmm TACO_B200_SPMM_LONGVAR=1
-run spmm TACO_B200_SPMM_LONGVAR=2
-run spmm TACO_B200_SPMM_LONGVAR=3
+run spmm TACO_B200_SPMM_PANELS=8
+run spmm TACO_B200_SPMM_PANELS=2
 run spmm TACO_B200_SPMM_OVERLAP=0
-run spmm TACO_B200_SPMM_LONG=96
-run spmm TACO_B200_SPMM_LONG=192
-run spmm TACO_B200_SPMM_LONGCTAS=4
-run spmm TACO_B200_SPMM_VARIANT=3
-run spmm TACO_B200_SPMM_VARIANT=4
 run spmm X=0
-run ttm X=0
-} > gpurun_out/exp_r2_19.txt 2>&1
-cat gpurun_out/exp_r2_19.txt
+} > gpurun_out/exp_r2_22.txt 2>&1
+cat gpurun_out/exp_r2_22.txt
