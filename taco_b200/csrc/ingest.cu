@@ -312,6 +312,12 @@ static int parse_mtx_header(const HostFile& f, std::vector<int>* dims, long long
 
 using namespace tb;
 
+__global__ void ing_gather_starts_kernel(const long long* __restrict__ line_start, const long long* __restrict__ lines, int n,
+                                         long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = line_start[lines[i]];
+}
+
 extern "C" int taco_b200_read(const char* path, taco_tensor_t* A) {
   TB_TRY(ensure_init());
   if (!path || !A) return fail(TACO_B200_ERR_ARG, "read: NULL argument");
@@ -341,6 +347,8 @@ extern "C" int taco_b200_read(const char* path, taco_tensor_t* A) {
     if (tokens - 1 != order) return fail(TACO_B200_ERR_ARG, "read: the file holds an order-%d tensor, the result tensor has order %d", tokens - 1, order);
   }
   const long long nbytes = (long long)(f.size - body);
+  if (nbytes >= INT_MAX)      // line numbers and entry counts are int32 (as the tensor's positions are)
+    return fail(TACO_B200_ERR_UNSUPPORTED, "read: '%s': files of 2 GiB and more are not read on the device", path);
   // ---- device: bytes -> lines -> entries ------------------------------------------------------------------------
   cudaStream_t st = stream();
   PipelineGuard g;                                   // releases every scratch buffer on all exit paths
@@ -429,11 +437,14 @@ extern "C" int taco_b200_read(const char* path, taco_tensor_t* A) {
     std::vector<int> slots(2 * (size_t)nslow);
     TB_TRY(read_back(lines.data(), slow_lines, sizeof(long long) * (size_t)nslow));
     TB_TRY(read_back(slots.data(), slow_slots, sizeof(int) * 2 * (size_t)nslow));
+    void* dstarts = nullptr;                         // the byte offsets of those lines: one gather, one read-back
+    TB_TRY(g.alloc(&dstarts, sizeof(long long) * (size_t)nslow));
+    ing_gather_starts_kernel<<<(nslow + 255) / 256, 256, 0, st>>>((const long long*)dls, (const long long*)slow_lines, nslow, (long long*)dstarts);
+    count_launch(1);
+    TB_TRY(read_back(starts.data(), dstarts, sizeof(long long) * (size_t)nslow));
     std::vector<double> fixed(nslow);
     for (int s = 0; s < nslow; s++) {
-      long long start = 0;
-      TB_TRY(read_back(&start, (long long*)dls + lines[s], sizeof(long long)));
-      char* lp = f.data + body + start;
+      char* lp = f.data + body + starts[s];
       for (int m = 0; m < order; m++) strtol(lp, &lp, 10);
       fixed[s] = strtod(lp, &lp);
     }

@@ -123,6 +123,67 @@ def test_sddmm_and_csf_shards(world):
     assert np.array_equal(np.concatenate(blocks).reshape(I, R), want)
 
 
+def test_result_fanout_into_mirror_windows_on_one_gpu():
+    """taco_b200_set_result_peers on ONE GPU: two more windows of the same device stand in for the peers.  Every rank's shard
+    is computed with its rows inside the gathered buffer; the kernels must leave the identical gathered result in the local
+    window and in both mirrors (SpMM short + long rows, row-major; MTTKRP whole slices + hub slices)."""
+    import torch
+    import oracle
+    import synth
+    import gpu_util as G
+    import taco_b200 as tb
+    from taco_b200 import partition
+    world = 3
+    w = synth.make("spmm", None, scale=12, K=32, dtype="float64")
+    n, m, K = w["dims"]
+    wd = _dev(w)
+    deg = np.diff(w["A_pos"])
+    assert (deg > 128).any(), "the operand must exercise the long-row schedule too"
+    want = oracle.spmm(w["A_pos"], w["A_crd"], w["A_vals"], w["B"].reshape(m, K))
+    bufs = [torch.full((n * K,), -1.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    bounds = partition.row_bounds(wd["A_pos"], n, world)
+    tb.set_result_space("device")
+    try:
+        tb.set_result_peers(bufs[0].data_ptr(), [bufs[1].data_ptr(), bufs[2].data_ptr()], n * K * 8)
+        for r in range(world):
+            sh = partition.shard_csr(wd["A_pos"], wd["A_crd"], wd["A_vals"], n, r, world, bounds)
+            rows = sh["row_end"] - sh["row_begin"]
+            kk, tt = G.build("spmm", dict(dims=[rows, m, K], A_pos=sh["pos"], A_crd=sh["crd"], A_vals=sh["vals"], B=wd["B"]))
+            tt[0].set_vals(bufs[0][sh["row_begin"] * K: sh["row_end"] * K])
+            kk.compute(*tt)
+        torch.cuda.synchronize()
+        got = [b.cpu().numpy().reshape(n, K) for b in bufs]
+        assert np.array_equal(got[0][deg <= 128], want[deg <= 128]) and np.allclose(got[0], want, rtol=1e-12, atol=0)
+        assert np.array_equal(got[1], got[0]) and np.array_equal(got[2], got[0]), "a mirror window differs from the local result"
+        # a result OUTSIDE the window must not fan out
+        for b in bufs[1:]:
+            b.fill_(-1.0)
+        G.run("spmm", dict(dims=[n, m, K], A_pos=wd["A_pos"], A_crd=wd["A_crd"], A_vals=wd["A_vals"], B=wd["B"]))
+        torch.cuda.synchronize()
+        assert float(bufs[1].max()) == -1.0 and float(bufs[2].max()) == -1.0
+
+        # MTTKRP, including slices long enough for the slot-ordered hub chain (> 512 leaves)
+        t = synth.make("mttkrp", None, I=64, K=300, L=250, nnz=60_000, R=16, dtype="float64")
+        I, Kd, L, R = t["dims"]
+        td = _dev(t)
+        want_a = oracle.mttkrp(t, t["C"].reshape(Kd, R), t["D"].reshape(L, R), I)
+        abufs = [torch.full((I * R,), -1.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+        tb.set_result_peers(abufs[0].data_ptr(), [abufs[1].data_ptr()], I * R * 8)
+        for r in range(2):
+            st = partition.shard_csf3(td, r, 2, rebase_rows=True, dim0=I)
+            sub = {k: v for k, v in st.items() if k.startswith("B")}
+            kk, tt = G.build("mttkrp", dict(dims=[st["row_end"] - st["row_begin"], Kd, L, R], C=td["C"], D=td["D"], **sub))
+            tt[0].set_vals(abufs[0][st["row_begin"] * R: st["row_end"] * R])
+            kk.compute(*tt)
+        torch.cuda.synchronize()
+        ga = [b.cpu().numpy().reshape(I, R) for b in abufs]
+        assert np.allclose(ga[0], want_a, rtol=1e-12, atol=0)
+        assert np.array_equal(ga[1], ga[0]), "the mirror window of the MTTKRP result differs from the local result"
+    finally:
+        tb.set_result_peers(None, None, 0)
+        tb.set_result_space("host")
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def _nccl_worker(rank, world, port, results):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TACO_B200_DEVICE=str(rank))
