@@ -1,3 +1,4 @@
+// build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/probe/pcie2d tools/probe/pcie2d.cu
 // PCIe probe: strided (2D) pinned<->device copies of a column slice of a row-major [rows x 128] fp32 matrix, alone and duplex.
 #include <cstdio>
 #include <cuda_runtime.h>

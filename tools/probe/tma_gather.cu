@@ -1,3 +1,4 @@
+// build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/probe/tma_gather tools/probe/tma_gather.cu
 // Probe: random 8-byte gathers from an L2-resident 8 MB table -- LSU loads against 16-byte bulk copies (TMA path) and a mix.
 #include <cstdio>
 #include <cstdint>
