@@ -162,6 +162,26 @@ def test_result_fanout_into_mirror_windows_on_one_gpu():
         torch.cuda.synchronize()
         assert float(bufs[1].max()) == -1.0 and float(bufs[2].max()) == -1.0
 
+        # fp32 (16-byte fragments of 4 columns) and a column-major result: the whole matrix inside the window
+        w32 = synth.make("spmm", None, scale=11, K=64, dtype="float32")
+        n2, m2, K2 = w32["dims"]
+        wd32 = _dev(w32)
+        want32 = oracle.spmm(w32["A_pos"], w32["A_crd"], w32["A_vals"], w32["B"].reshape(m2, K2))
+        deg32 = np.diff(w32["A_pos"])
+        for colmajor in (False, True):
+            fb = [torch.full((n2 * K2,), -1.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+            tb.set_result_peers(fb[0].data_ptr(), [fb[1].data_ptr()], n2 * K2 * 4)
+            kk, tt = G.build("spmm", dict(dims=[n2, m2, K2], A_pos=wd32["A_pos"], A_crd=wd32["A_crd"], A_vals=wd32["A_vals"], B=wd32["B"]),
+                             colmajor_c=colmajor)
+            tt[0].set_vals(fb[0])
+            kk.compute(*tt)
+            torch.cuda.synchronize()
+            g0, g1 = (b.cpu().numpy().reshape((K2, n2) if colmajor else (n2, K2)) for b in fb)
+            if colmajor:
+                g0, g1 = g0.T, g1.T
+            assert np.array_equal(g0[deg32 <= 128], want32[deg32 <= 128]) and np.allclose(g0, want32, rtol=1e-5, atol=1e-30)
+            assert np.array_equal(g1, g0), "fp32 mirror window differs (colmajor=%s)" % colmajor
+
         # MTTKRP, including slices long enough for the slot-ordered hub chain (> 512 leaves)
         t = synth.make("mttkrp", None, I=64, K=300, L=250, nnz=60_000, R=16, dtype="float64")
         I, Kd, L, R = t["dims"]
