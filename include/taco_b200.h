@@ -107,7 +107,8 @@ int  taco_b200_set_result_multicast(const void* local_base, void* multicast_base
  * (symmetric memory buffer_ptrs of the other ranks, or cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess pointers), 1 <= npeers <= 7.
  * Every result row is stored locally and to each peer from inside the kernel.  Each GPU then receives N-1 shards over NVLink
  * instead of the N a multicast store delivers (the switch also loops the sender's own copy back): the better trade for small
- * groups.  Replaces a registered multicast window and vice versa; NULL / npeers 0 clears. */
+ * groups.  Replaces a registered multicast window and vice versa; NULL / npeers 0 clears.  Register or clear a window only
+ * while no compute call of this process is in flight. */
 int  taco_b200_set_result_peers(const void* local_base, size_t bytes, int npeers, void* const* peer_bases);
 
 /* Residency cache: keep a device mirror of an immutable host array across calls (pinned upload once). */
