@@ -25,7 +25,9 @@
  *   - compute() writes result values where result->vals points (host or device).
  *   - Work is enqueued on the stream set by taco_b200_set_stream() (default: a private non-blocking stream).
  *     Entry points with host-visible results synchronise that stream before returning; with all-device tensors
- *     they return immediately (stream-ordered), like a kernel launch.
+ *     they return immediately (stream-ordered), like a kernel launch.  Device operands written by, and device results
+ *     read by, work on ANOTHER stream are the caller's to order: hand the library that stream (taco_b200_set_stream)
+ *     or synchronise (taco_b200_synchronize) -- exactly as between any two CUDA streams.
  *
  * There is NO CPU fallback: every entry point fails with TACO_B200_ERR_CUDA if no sm_100 device is usable.
  */

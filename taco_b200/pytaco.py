@@ -246,6 +246,11 @@ def evaluate(expr, *operands, out_format=None, dtype=None, shape=None):
     for n, o in zip(names, ops):
         o._t.name = n
     on_dev = any(o.on_device() for o in ops)
+    if on_dev and torch is not None:
+        # device operands were (and the result will be) produced / consumed by the caller's torch stream: enqueue the library's
+        # work on that same stream, so that neither side reads an array the other is still writing (found by running this
+        # front end's test under compute-sanitizer, whose slowdown exposed the race with the library's private stream)
+        _t.use_torch_stream()
     prev = _t.lib.taco_b200_get_result_space()
     _t.set_result_space("device" if on_dev else "host")
     try:
