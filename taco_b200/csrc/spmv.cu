@@ -197,6 +197,10 @@ spmv_csr_kernel(const int* __restrict__ pos, const int* __restrict__ crd, const 
   }
 
   // ---- (4) the row that covers nonzero `lo` but started in an earlier tile -----------------------------------------------
+  // The tile in which such a row ENDS waits for the partial sums of the lower-numbered tiles it runs through.  This relies on
+  // the CTAs of a 1-D grid being dispatched in blockIdx order (a lower tile is running or done whenever a higher one is
+  // resident).  An arrival-order ticket would remove the assumption but measured 64 -> 70 us on config C1
+  // (profiles/r02_variants.md); spmv_warp_kernel below has no cross-CTA wait at all (TACO_B200_SPMV_KERNEL=1).
   if (r_lo > 0 && lo < nnz) {
     const int e_head = __ldg(pos + r_lo);          // uniform over the CTA
     if (e_head > lo) {
