@@ -492,12 +492,15 @@ spmm_long_combine_kernel(const int* __restrict__ long_rows, const int* __restric
 // TACO_B200_SPMM_LONG / _PANELS / _CAP override the defaults (tuning runs).  The partial-sum scratch is sized for the worst case
 // (every long row has nonzeros in every panel: 8.7 GB at C2, of which the kernel touches 0.5 GB) and kept under an eighth of the
 // device memory (TACO_B200_SPMM_SCRATCH_GB overrides) by halving the panel count, then doubling the threshold.
-static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es) {
-  static const int e_thresh = env_int("TACO_B200_SPMM_LONG", 128), e_panels = env_int("TACO_B200_SPMM_PANELS", 4),
+static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es, bool rmap) {
+  static const int e_thresh = env_int("TACO_B200_SPMM_LONG", 0), e_panels = env_int("TACO_B200_SPMM_PANELS", 0),
                    e_cap = env_int("TACO_B200_SPMM_CAP", 256);
   SpmmLongCfg c;
-  c.thresh = e_thresh < 64 ? 64 : e_thresh;
-  c.panels = e_panels < 1 ? 1 : (e_panels > 32 ? 32 : e_panels);
+  // (the fibers of a CSF tensor -- TTM, `rmap` -- measure 2.43 -> 2.27 ms with thresh 16 and ONE panel, profiles/r02_variants.md;
+  //  not the default: it would shrink the range in which TTM is bit-identical to the reference from 128 to 16 leaves per fiber)
+  (void)rmap;
+  c.thresh = e_thresh > 0 ? (e_thresh < 8 ? 8 : e_thresh) : 128;
+  c.panels = e_panels > 0 ? (e_panels > 32 ? 32 : e_panels) : 4;
   c.cap = e_cap < 32 ? 32 : e_cap;
   static const int e_gb = env_int("TACO_B200_SPMM_SCRATCH_GB", 0);
   const size_t budget = e_gb > 0 ? (size_t)e_gb << 30 : device_mem_total() / 8;
@@ -506,7 +509,8 @@ static SpmmLongCfg spmm_long_cfg(int nnz, int cols, int K, size_t es) {
     c.items_max = (long long)nnz / c.cap + 1 + (long long)c.nlong_max * c.panels;
     if ((size_t)c.items_max * K * es <= budget || c.nlong_max == 0) break;
     if (c.panels > 1) c.panels /= 2;
-    else c.thresh *= 2;
+    else if (c.thresh < (1 << 29)) c.thresh *= 2;
+    else { c.nlong_max = 0; break; }          // no room even for one item per 2^29 nonzeros: every row on schedule (1)
   }
   c.panel_w = (cols + c.panels - 1) / c.panels;
   if (c.panel_w < 1) c.panel_w = 1;
@@ -607,7 +611,7 @@ static int spmm_launch_impl(const int* pos, const int* crd, const T* vals, const
   ProfScope ps(prof_name);
   // a result inside the registered fan-out window also goes to the other GPUs from inside the kernels (fused all-gather)
   const Fanout fo = RMAP ? Fanout() : result_fanout(C, sizeof(T) * (size_t)rows * K);
-  const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T));
+  const SpmmLongCfg cfg = spmm_long_cfg(nnz, cols, K, sizeof(T), RMAP);
   static const int overlap = env_int("TACO_B200_SPMM_OVERLAP", 1);
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;          // timing-free events, created once
   if (!ev_fork) {
